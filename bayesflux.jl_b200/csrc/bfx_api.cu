@@ -1,0 +1,967 @@
+// C ABI of libbfx (include/bfx.h): handles, descriptor translation, memory, launches.
+// No exceptions cross the boundary; every entry returns a status and records a message.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/bfx.h"
+#include "bfx_common.cuh"
+#include "bfx_kernels.h"
+
+using namespace bfx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(BFX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+inline int round4(int v) { return (v + 3) & ~3; }
+inline int odd_ld(int v) {
+  int ld = round4(v);
+  if (((ld >> 2) & 1) == 0) ld += 4;
+  return ld;
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+}  // namespace
+
+struct bfx_model {
+  int device = 0;
+  ModelDev M{};
+  LaunchCfg cfg{256, 64};
+  std::vector<bfx_layer_desc> layers;
+  std::vector<int64_t> starts, ends;
+  float* x = nullptr;
+  float* y = nullptr;
+  int64_t n = 0;
+  cudaStream_t stream = nullptr;
+};
+
+struct bfx_sampler {
+  bfx_model* m = nullptr;
+  bfx_sampler_desc d{};
+  SamplerDev S{};
+  int C = 0;
+  int Ps = 0;
+  float *theta = nullptr, *mom = nullptr, *minv = nullptr, *theta_old = nullptr, *rms_v = nullptr, *ring = nullptr;
+  ChainScalars* sc = nullptr;
+  unsigned long long* progress_host = nullptr;  // mapped pinned
+  unsigned long long* progress_dev = nullptr;
+  long long gstep = 0;     // update! calls done since init
+  long long nsampled = 0;  // lock-step host mirror
+  long long launches = 0;
+  bool initialised = false;
+  cudaStream_t copy_stream = nullptr;
+};
+
+// ---------------------------------------------------------------------------------
+// model construction
+// ---------------------------------------------------------------------------------
+static int32_t build_model_dev(bfx_model* m, const bfx_like_desc* like, const bfx_prior_desc* prior) {
+  ModelDev& M = m->M;
+  const int nl = (int)m->layers.size();
+  M.nlayers = nl;
+  M.rec_layer = -1;
+  int flat = 0, s_off = 0, nseg = 0;
+  m->starts.clear();
+  m->ends.clear();
+  for (int l = 0; l < nl; ++l) {
+    const bfx_layer_desc& d = m->layers[l];
+    if (d.in <= 0 || d.out <= 0) return fail(BFX_ERR_BAD_ARG, "layer sizes must be positive");
+    if (l > 0 && m->layers[l - 1].out != d.in) return fail(BFX_ERR_BAD_ARG, "layer fan-in does not match previous fan-out");
+    if (d.act < BFX_IDENTITY || d.act > BFX_SIGMOID) return fail(BFX_ERR_BAD_ARG, "unknown activation");
+    LayerDev& L = M.L[l];
+    L.kind = d.kind;
+    L.nin = d.in;
+    L.nout = d.out;
+    L.act = d.act;
+    L.H = d.out;
+    L.nin_pad = round4(d.in);
+    m->starts.push_back(flat);
+    if (d.kind == BFX_DENSE) {
+      L.nout_pad = round4(d.out);
+      L.ldw = odd_ld(d.out);
+      L.ldh = 0;
+      L.w_s = s_off;
+      M.seg[nseg++] = SegDesc{flat, d.in * d.out, s_off, d.out, L.ldw, 1.0f / (float)d.out};
+      flat += d.in * d.out;
+      s_off += L.nin_pad * L.ldw;
+      L.wh_s = 0;
+      L.b_s = s_off;
+      M.seg[nseg++] = SegDesc{flat, d.out, s_off, d.out, d.out, 1.0f / (float)d.out};
+      flat += d.out;
+      s_off += L.nout_pad;
+    } else if (d.kind == BFX_RNN || d.kind == BFX_LSTM) {
+      if (M.rec_layer >= 0) return fail(BFX_ERR_UNSUPPORTED, "at most one recurrent layer is supported");
+      if (l != 0) return fail(BFX_ERR_UNSUPPORTED, "the recurrent layer must be the first layer of the chain");
+      M.rec_layer = l;
+      const int G = d.out * (d.kind == BFX_LSTM ? 4 : 1);
+      L.nout_pad = round4(G);
+      L.ldw = odd_ld(G);
+      L.ldh = odd_ld(G);
+      L.w_s = s_off;
+      M.seg[nseg++] = SegDesc{flat, d.in * G, s_off, G, L.ldw, 1.0f / (float)G};
+      flat += d.in * G;
+      s_off += L.nin_pad * L.ldw;
+      L.wh_s = s_off;
+      M.seg[nseg++] = SegDesc{flat, d.out * G, s_off, G, L.ldh, 1.0f / (float)G};
+      flat += d.out * G;
+      s_off += round4(d.out) * L.ldh;
+      L.b_s = s_off;
+      M.seg[nseg++] = SegDesc{flat, G, s_off, G, G, 1.0f / (float)G};
+      flat += G;
+      s_off += L.nout_pad;
+    } else {
+      return fail(BFX_ERR_BAD_ARG, "unknown layer kind");
+    }
+    m->ends.push_back(flat);
+  }
+  if (m->layers[nl - 1].out != 1)
+    return fail(BFX_ERR_BAD_ARG, "the likelihoods assume a single network output (feedforward.jl:13)");
+  M.Pnet = flat;
+  M.like_s = s_off;
+  M.seg[nseg++] = SegDesc{flat, 1, s_off, 1, 1, 1.0f};
+  s_off += 4;
+  M.P = flat + 1;
+  M.S = s_off;
+  M.nsegs = nseg;
+  M.d_in = m->layers[0].in;
+  // likelihood
+  if (like->kind != BFX_LIKE_NORMAL && like->kind != BFX_LIKE_TDIST) return fail(BFX_ERR_BAD_ARG, "unknown likelihood");
+  M.like_kind = like->kind;
+  M.nu = (float)like->nu;
+  if (like->kind == BFX_LIKE_TDIST && !(like->nu > 0)) return fail(BFX_ERR_BAD_ARG, "TDist needs nu > 0");
+  M.tdist_const = like->kind == BFX_LIKE_TDIST
+                      ? std::lgamma(0.5 * (like->nu + 1)) - std::lgamma(0.5 * like->nu) - 0.5 * std::log(like->nu * M_PI)
+                      : 0.0;
+  M.sprior_kind = like->sigma_prior_kind;
+  M.sprior_a = (float)like->sigma_prior_a;
+  M.sprior_b = (float)like->sigma_prior_b;
+  if (!(like->sigma_prior_a > 0) || !(like->sigma_prior_b > 0)) return fail(BFX_ERR_BAD_ARG, "sigma prior parameters must be > 0");
+  if (like->sigma_prior_kind == BFX_SIGMA_GAMMA)
+    M.sprior_const = -std::lgamma(like->sigma_prior_a) - like->sigma_prior_a * std::log(like->sigma_prior_b);
+  else if (like->sigma_prior_kind == BFX_SIGMA_INVGAMMA)
+    M.sprior_const = like->sigma_prior_a * std::log(like->sigma_prior_b) - std::lgamma(like->sigma_prior_a);
+  else
+    return fail(BFX_ERR_BAD_ARG, "unknown sigma prior");
+  // network prior: logprior = Pnet*c0 - 0.5*c2*sum(theta^2)
+  const double l2pi = std::log(2.0 * M_PI);
+  double c0, c2;
+  if (prior->kind == BFX_PRIOR_GAUSSIAN) {
+    if (!(prior->sigma0 > 0)) return fail(BFX_ERR_BAD_ARG, "sigma0 must be > 0");
+    c0 = -0.5 * l2pi - std::log(prior->sigma0);
+    c2 = 1.0 / (prior->sigma0 * prior->sigma0);
+  } else if (prior->kind == BFX_PRIOR_MIXTURE) {
+    if (!(prior->sigma1 > 0) || !(prior->sigma2 > 0)) return fail(BFX_ERR_BAD_ARG, "sigma1/sigma2 must be > 0");
+    const double pi2 = 1.0 - prior->pi1;
+    c0 = prior->pi1 * (-0.5 * l2pi - std::log(prior->sigma1)) + pi2 * (-0.5 * l2pi - std::log(prior->sigma2));
+    c2 = prior->pi1 / (prior->sigma1 * prior->sigma1) + pi2 / (prior->sigma2 * prior->sigma2);
+  } else {
+    return fail(BFX_ERR_BAD_ARG, "unknown network prior");
+  }
+  M.prior_c0n = c0 * M.Pnet;
+  M.prior_c2 = (float)c2;
+  // launch shape: tiny nets get one warp per chain, wide ones 256 threads
+  int max_rows = 0;
+  for (int l = 0; l < nl; ++l) max_rows = std::max(max_rows, M.L[l].nout_pad);
+  if (M.rec_layer >= 0) return fail(BFX_ERR_UNSUPPORTED, "recurrent layers: kernel not built in this version");
+  if (max_rows >= 48)
+    m->cfg = LaunchCfg{256, 64};
+  else if (max_rows >= 16)
+    m->cfg = LaunchCfg{128, 64};
+  else
+    m->cfg = LaunchCfg{32, 32};
+  const int LDB = m->cfg.bt + 4;
+  int off = 0;
+  M.act_rows[0] = round4(M.d_in);
+  M.act_off[0] = 0;
+  off = M.act_rows[0] * LDB;
+  for (int l = 0; l < nl; ++l) {
+    M.act_rows[l + 1] = M.L[l].nout_pad;
+    M.act_off[l + 1] = off;
+    off += M.L[l].nout_pad * LDB;
+  }
+  M.act_total = off;
+  if (smallp_smem_bytes(M, m->cfg.bt) > kMaxSmem)
+    return fail(BFX_ERR_UNSUPPORTED,
+                "network does not fit the shared-memory regime (theta + gradient + one batch tile > 227 KB)");
+  return BFX_OK;
+}
+
+// ---------------------------------------------------------------------------------
+extern "C" {
+
+int32_t bfx_version(void) { return BFX_VERSION; }
+
+int32_t bfx_last_error(char* buf, size_t n) {
+  if (!buf || n == 0) return BFX_ERR_BAD_ARG;
+  std::snprintf(buf, n, "%s", g_err.c_str());
+  return BFX_OK;
+}
+
+int32_t bfx_device_count(int32_t* count) {
+  if (!count) return fail(BFX_ERR_BAD_ARG, "count is NULL");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(BFX_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = c;
+  return BFX_OK;
+}
+
+int32_t bfx_model_create(const bfx_layer_desc* layers, int32_t nlayers, const bfx_like_desc* like,
+                         const bfx_prior_desc* prior, int32_t device, bfx_model** out) {
+  if (!layers || !like || !prior || !out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (nlayers < 1 || nlayers > BFX_MAX_LAYERS) return fail(BFX_ERR_BAD_ARG, "nlayers must be in 1..8");
+  bfx_model* m = new (std::nothrow) bfx_model();
+  if (!m) return fail(BFX_ERR_BAD_ARG, "out of host memory");
+  m->device = device;
+  m->layers.assign(layers, layers + nlayers);
+  int32_t st = build_model_dev(m, like, prior);
+  if (st != BFX_OK) {
+    delete m;
+    return st;
+  }
+  *out = m;
+  return BFX_OK;
+}
+
+int32_t bfx_model_destroy(bfx_model* m) {
+  if (!m) return BFX_OK;
+  if (m->x || m->y || m->stream) {
+    cudaSetDevice(m->device);
+    if (m->x) cudaFree(m->x);
+    if (m->y) cudaFree(m->y);
+    if (m->stream) cudaStreamDestroy(m->stream);
+  }
+  delete m;
+  return BFX_OK;
+}
+
+int32_t bfx_model_num_params(const bfx_model* m, int64_t* p_total, int64_t* p_net) {
+  if (!m) return fail(BFX_ERR_BAD_ARG, "model is NULL");
+  if (p_total) *p_total = m->M.P;
+  if (p_net) *p_net = m->M.Pnet;
+  return BFX_OK;
+}
+
+int32_t bfx_model_layer_bounds(const bfx_model* m, int32_t layer, int64_t* start, int64_t* end) {
+  if (!m || layer < 0 || layer >= (int)m->layers.size()) return fail(BFX_ERR_BAD_ARG, "bad layer index");
+  if (start) *start = m->starts[layer];
+  if (end) *end = m->ends[layer];
+  return BFX_OK;
+}
+
+static int32_t ensure_stream(bfx_model* m) {
+  CK(cudaSetDevice(m->device));
+  if (!m->stream) CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  return BFX_OK;
+}
+
+static int32_t set_data_impl(bfx_model* m, const float* x, const int64_t* dims, int32_t ndims, const float* y,
+                             int64_t n, cudaMemcpyKind kind) {
+  if (!m || !x || !y || !dims) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (ndims != 2 && ndims != 3) return fail(BFX_ERR_BAD_ARG, "x must be d x n or T x d x n");
+  const int64_t d = dims[ndims - 2], nn = dims[ndims - 1];
+  if (nn != n || n <= 0) return fail(BFX_ERR_BAD_ARG, "last dimension of x must equal length(y) > 0");
+  if (d != m->M.d_in) return fail(BFX_ERR_BAD_ARG, "feature dimension of x does not match the first layer");
+  if (n > 2147483647LL) return fail(BFX_ERR_UNSUPPORTED, "n must fit in int32");
+  if (ndims == 3 && m->M.rec_layer < 0) return fail(BFX_ERR_BAD_ARG, "3-d x needs a recurrent network");
+  if (ndims == 2 && m->M.rec_layer >= 0) return fail(BFX_ERR_BAD_ARG, "recurrent networks need T x d x n input");
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  if (m->x) cudaFree(m->x);
+  if (m->y) cudaFree(m->y);
+  m->x = m->y = nullptr;
+  size_t per = (size_t)d * (ndims == 3 ? (size_t)dims[0] : 1);
+  CK(cudaMalloc(&m->x, per * (size_t)n * sizeof(float)));
+  CK(cudaMalloc(&m->y, (size_t)n * sizeof(float)));
+  CK(cudaMemcpyAsync(m->x, x, per * (size_t)n * sizeof(float), kind, m->stream));
+  CK(cudaMemcpyAsync(m->y, y, (size_t)n * sizeof(float), kind, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  m->n = n;
+  m->M.seq = ndims == 3;
+  m->M.T = ndims == 3 ? (int)dims[0] : 1;
+  return BFX_OK;
+}
+
+int32_t bfx_model_set_data(bfx_model* m, const float* x, const int64_t* dims, int32_t ndims, const float* y,
+                           int64_t n) {
+  return set_data_impl(m, x, dims, ndims, y, n, cudaMemcpyHostToDevice);
+}
+
+int32_t bfx_model_set_data_device(bfx_model* m, const float* x_dev, const int64_t* dims, int32_t ndims,
+                                  const float* y_dev, int64_t n) {
+  return set_data_impl(m, x_dev, dims, ndims, y_dev, n, cudaMemcpyDeviceToDevice);
+}
+
+// ---------------------------------------------------------------------------------
+// loglikeprior / ∇loglikeprior
+// ---------------------------------------------------------------------------------
+static int32_t eval_impl(bfx_model* m, const float* theta, int32_t C, const int64_t* idx, int64_t B, int64_t stride,
+                         float num_batches, double* v_out, float* g_out) {
+  if (!m || !theta || !v_out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (C <= 0) return fail(BFX_ERR_BAD_ARG, "nchains must be > 0");
+  if (!m->x) return fail(BFX_ERR_NO_DATA, "bfx_model_set_data has not been called");
+  if (idx && B <= 0) return fail(BFX_ERR_BAD_ARG, "B must be > 0 with explicit indices");
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  const int P = m->M.P;
+  const int64_t nidx = idx ? (stride ? (int64_t)(C - 1) * stride + B : B) : 0;
+  if (idx)
+    for (int64_t i = 0; i < nidx; ++i)
+      if (idx[i] < 0 || idx[i] >= m->n) return fail(BFX_ERR_BAD_ARG, "batch index out of range");
+  float *d_theta = nullptr, *d_g = nullptr;
+  double* d_v = nullptr;
+  long long* d_idx = nullptr;
+  int32_t rc = BFX_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_theta);
+    cudaFree(d_g);
+    cudaFree(d_v);
+    cudaFree(d_idx);
+  };
+#define CKC(call)                                                                     \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      cleanup();                                                                      \
+      return fail(BFX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    }                                                                                 \
+  } while (0)
+  CKC(cudaMalloc(&d_theta, (size_t)C * P * sizeof(float)));
+  CKC(cudaMalloc(&d_v, (size_t)C * sizeof(double)));
+  if (g_out) CKC(cudaMalloc(&d_g, (size_t)C * P * sizeof(float)));
+  if (idx) {
+    CKC(cudaMalloc(&d_idx, (size_t)nidx * sizeof(long long)));
+    CKC(cudaMemcpyAsync(d_idx, idx, (size_t)nidx * sizeof(long long), cudaMemcpyHostToDevice, m->stream));
+  }
+  CKC(cudaMemcpyAsync(d_theta, theta, (size_t)C * P * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  EvalDev E{};
+  E.M = m->M;
+  E.x = m->x;
+  E.y = m->y;
+  E.n = m->n;
+  E.C = C;
+  E.theta = d_theta;
+  E.idx = d_idx;
+  E.idx_chain_stride = stride;
+  E.B = idx ? B : m->n;
+  E.num_batches = num_batches;
+  E.want_grad = g_out ? 1 : 0;
+  E.v_out = d_v;
+  E.g_out = d_g;
+  CKC(launch_eval(E, m->cfg, m->stream));
+  CKC(cudaMemcpyAsync(v_out, d_v, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (g_out) CKC(cudaMemcpyAsync(g_out, d_g, (size_t)C * P * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CKC(cudaStreamSynchronize(m->stream));
+  cleanup();
+  return rc;
+}
+
+int32_t bfx_loglikeprior(bfx_model* m, const float* theta, int32_t nchains, const int64_t* idx, int64_t B,
+                         int64_t idx_chain_stride, float num_batches, double* v_out) {
+  return eval_impl(m, theta, nchains, idx, B, idx_chain_stride, num_batches, v_out, nullptr);
+}
+
+int32_t bfx_grad_loglikeprior(bfx_model* m, const float* theta, int32_t nchains, const int64_t* idx, int64_t B,
+                              int64_t idx_chain_stride, float num_batches, double* v_out, float* g_out) {
+  if (!g_out) return fail(BFX_ERR_BAD_ARG, "g_out is NULL");
+  return eval_impl(m, theta, nchains, idx, B, idx_chain_stride, num_batches, v_out, g_out);
+}
+
+// ---------------------------------------------------------------------------------
+// samplers
+// ---------------------------------------------------------------------------------
+static void free_sampler(bfx_sampler* s) {
+  if (!s) return;
+  cudaSetDevice(s->m->device);
+  cudaFree(s->theta);
+  cudaFree(s->mom);
+  cudaFree(s->minv);
+  cudaFree(s->theta_old);
+  cudaFree(s->rms_v);
+  cudaFree(s->ring);
+  cudaFree(s->sc);
+  if (s->progress_host) cudaFreeHost(s->progress_host);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  delete s;
+}
+
+int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t nchains, bfx_sampler** out) {
+  if (!d || !m || !out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (nchains <= 0) return fail(BFX_ERR_BAD_ARG, "nchains must be > 0");
+  if (d->kind < BFX_SGLD || d->kind > BFX_HMC) return fail(BFX_ERR_BAD_ARG, "unknown sampler kind");
+  if (d->madapter_kind == BFX_MASS_FULLCOV)
+    return fail(BFX_ERR_UNSUPPORTED,
+                "FullCovMassAdapter (dense P x P mass matrix) is outside the many-chain engine; use DiagCovMassAdapter");
+  if (d->madapter_kind < BFX_MASS_FIXED || d->madapter_kind > BFX_MASS_RMSPROP)
+    return fail(BFX_ERR_BAD_ARG, "unknown mass adapter");
+  if (d->sadapter_kind != BFX_STEP_CONSTANT && d->sadapter_kind != BFX_STEP_DUAL_AVERAGING)
+    return fail(BFX_ERR_BAD_ARG, "unknown stepsize adapter");
+  if (d->kind == BFX_GGMC && d->steps < 1) return fail(BFX_ERR_BAD_ARG, "GGMC steps must be >= 1");
+  if (d->kind == BFX_HMC && d->path_len < 1) return fail(BFX_ERR_BAD_ARG, "HMC path_len must be >= 1");
+  if (d->kind != BFX_SGLD && !(d->l > 0)) return fail(BFX_ERR_BAD_ARG, "stepsize l must be > 0");
+  if (d->madapter_kind == BFX_MASS_DIAGCOV && d->ma_windowlength < 2)
+    return fail(BFX_ERR_BAD_ARG, "DiagCov windowlength must be >= 2");
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  bfx_sampler* s = new (std::nothrow) bfx_sampler();
+  if (!s) return fail(BFX_ERR_BAD_ARG, "out of host memory");
+  s->m = m;
+  s->d = *d;
+  s->C = nchains;
+  s->Ps = round4(m->M.P);
+  SamplerDev& S = s->S;
+  S.kind = d->kind;
+  S.steps = d->kind == BFX_GGMC ? d->steps : 1;
+  S.path_len = d->kind == BFX_HMC ? d->path_len : 1;
+  const bool mh = d->kind == BFX_GGMC || d->kind == BFX_HMC;
+  S.sadapter_kind = mh ? d->sadapter_kind : SA_CONST;
+  S.madapter_kind = (d->kind == BFX_SGLD || d->kind == BFX_SGNHT) ? MA_FIXED : d->madapter_kind;
+  S.da_t0 = d->da_t0;
+  S.da_adapt_steps = d->da_adapt_steps;
+  S.ma_adapt_steps = d->ma_adapt_steps;
+  S.ma_windowlength = d->ma_windowlength;
+  S.stepsize_a = d->stepsize_a;
+  S.stepsize_b = d->stepsize_b;
+  S.stepsize_gamma = d->stepsize_gamma;
+  S.min_stepsize = d->min_stepsize;
+  S.maxnorm = d->maxnorm;
+  S.l = d->l;
+  S.A = d->A;
+  S.sigmaA = d->sigmaA;
+  S.xi = d->xi;
+  S.mu = d->mu;
+  S.beta = d->beta;
+  S.da_target_accept = d->da_target_accept;
+  S.da_gamma = d->da_gamma;
+  S.da_kappa = d->da_kappa;
+  S.da_mu = std::log(10.0f * d->l);  // dualaveragestepsize.jl:36
+  S.ma_kappa = d->ma_kappa;
+  S.ma_epsilon = d->ma_epsilon;
+  S.ma_lambda = d->ma_lambda;
+  S.ma_alpha = d->ma_alpha;
+  const size_t row = (size_t)s->Ps * sizeof(float), all = row * (size_t)nchains;
+  cudaError_t e = cudaMalloc(&s->theta, all);
+  if (e == cudaSuccess) e = cudaMalloc(&s->sc, sizeof(ChainScalars) * (size_t)nchains);
+  if (e == cudaSuccess && d->kind != BFX_SGLD) e = cudaMalloc(&s->mom, all);
+  if (e == cudaSuccess && mh) e = cudaMalloc(&s->theta_old, all);
+  if (e == cudaSuccess && S.madapter_kind != MA_FIXED) e = cudaMalloc(&s->minv, all);
+  if (e == cudaSuccess && S.madapter_kind == MA_RMSPROP) e = cudaMalloc(&s->rms_v, all);
+  if (e == cudaSuccess && S.madapter_kind == MA_DIAGCOV) e = cudaMalloc(&s->ring, all * (size_t)S.ma_windowlength);
+  if (e == cudaSuccess) e = cudaHostAlloc(&s->progress_host, sizeof(unsigned long long), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&s->progress_dev, s->progress_host, 0);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    free_sampler(s);
+    return fail(BFX_ERR_CUDA, std::string("sampler allocation: ") + cudaGetErrorString(e));
+  }
+  *s->progress_host = 0;
+  *out = s;
+  return BFX_OK;
+}
+
+int32_t bfx_sampler_destroy(bfx_sampler* s) {
+  free_sampler(s);
+  return BFX_OK;
+}
+
+// rows of P floats (host, dense) <-> rows of Ps floats (device)
+static cudaError_t copy_rows_h2d(float* dst, int Ps, const float* src, int P, int C, cudaStream_t st) {
+  return cudaMemcpy2DAsync(dst, (size_t)Ps * 4, src, (size_t)P * 4, (size_t)P * 4, C, cudaMemcpyHostToDevice, st);
+}
+static cudaError_t copy_rows_d2h(float* dst, int P, const float* src, int Ps, int C, cudaStream_t st) {
+  return cudaMemcpy2DAsync(dst, (size_t)P * 4, src, (size_t)Ps * 4, (size_t)P * 4, C, cudaMemcpyDeviceToHost, st);
+}
+
+int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) {
+  if (!s || !theta_start) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  bfx_model* m = s->m;
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  const size_t all = (size_t)s->Ps * sizeof(float) * (size_t)s->C;
+  CK(cudaMemsetAsync(s->theta, 0, all, m->stream));
+  CK(copy_rows_h2d(s->theta, s->Ps, theta_start, m->M.P, s->C, m->stream));
+  if (s->mom) CK(cudaMemsetAsync(s->mom, 0, all, m->stream));
+  if (s->theta_old) CK(cudaMemsetAsync(s->theta_old, 0, all, m->stream));
+  if (s->minv) {
+    std::vector<float> ones((size_t)s->Ps * s->C, 1.0f);
+    CK(cudaMemcpyAsync(s->minv, ones.data(), all, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
+  if (s->rms_v) CK(cudaMemsetAsync(s->rms_v, 0, all, m->stream));
+  if (s->ring) CK(cudaMemsetAsync(s->ring, 0, all * (size_t)s->S.ma_windowlength, m->stream));
+  ChainScalars z{};
+  z.t = 1;
+  z.nsampled = 0;
+  z.xi = s->S.xi;
+  z.l = s->S.l;
+  z.lMH = 0.f;
+  z.current_step = 1;
+  z.da_t = s->S.da_t0;  // counter starts at t0 (dualaveragestepsize.jl:39)
+  z.da_error_sum = 0.f;
+  z.da_log_avg = 0.f;
+  z.ma_t = 1;
+  z.status = 0;
+  std::vector<ChainScalars> sc((size_t)s->C, z);
+  CK(cudaMemcpyAsync(s->sc, sc.data(), sizeof(ChainScalars) * sc.size(), cudaMemcpyHostToDevice, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  s->gstep = 0;
+  s->nsampled = 0;
+  *s->progress_host = 0;
+  s->initialised = true;
+  return BFX_OK;
+}
+
+static int32_t fetch_scalars(bfx_sampler* s, std::vector<ChainScalars>& sc) {
+  sc.resize((size_t)s->C);
+  CK(cudaSetDevice(s->m->device));
+  CK(cudaMemcpy(sc.data(), s->sc, sizeof(ChainScalars) * sc.size(), cudaMemcpyDeviceToHost));
+  return BFX_OK;
+}
+
+int32_t bfx_sampler_get_state(bfx_sampler* s, int32_t field, void* out, int64_t nbytes) {
+  if (!s || !out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (!s->initialised) return fail(BFX_ERR_STATE, "sampler not initialised");
+  bfx_model* m = s->m;
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  const int P = m->M.P, C = s->C;
+  const float* src = nullptr;
+  switch (field) {
+    case BFX_STATE_THETA: src = s->theta; break;
+    case BFX_STATE_MOMENTUM: src = s->mom; break;
+    case BFX_STATE_MINV: src = s->minv; break;
+    default: break;
+  }
+  if (field == BFX_STATE_THETA || field == BFX_STATE_MOMENTUM || field == BFX_STATE_MINV) {
+    if (nbytes != (int64_t)P * C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold P x C floats");
+    float* o = static_cast<float*>(out);
+    if (!src) {  // state this sampler does not carry: momentum 0, Minv identity
+      for (int64_t i = 0; i < (int64_t)P * C; ++i) o[i] = field == BFX_STATE_MINV ? 1.f : 0.f;
+      return BFX_OK;
+    }
+    CK(copy_rows_d2h(o, P, src, s->Ps, C, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    return BFX_OK;
+  }
+  std::vector<ChainScalars> sc;
+  st = fetch_scalars(s, sc);
+  if (st) return st;
+  if (field == BFX_STATE_XI || field == BFX_STATE_STEPSIZE) {
+    if (nbytes != (int64_t)C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold C floats");
+    float* o = static_cast<float*>(out);
+    for (int c = 0; c < C; ++c) o[c] = field == BFX_STATE_XI ? sc[c].xi : sc[c].l;
+    return BFX_OK;
+  }
+  if (field == BFX_STATE_T || field == BFX_STATE_NSAMPLED) {
+    if (nbytes != (int64_t)C * 8) return fail(BFX_ERR_BAD_ARG, "buffer must hold C int64");
+    int64_t* o = static_cast<int64_t*>(out);
+    for (int c = 0; c < C; ++c) o[c] = field == BFX_STATE_T ? sc[c].t : sc[c].nsampled;
+    return BFX_OK;
+  }
+  if (field == BFX_STATE_STATUS) {
+    if (nbytes != (int64_t)C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold C int32");
+    int32_t* o = static_cast<int32_t*>(out);
+    for (int c = 0; c < C; ++c) o[c] = sc[c].status;
+    return BFX_OK;
+  }
+  return fail(BFX_ERR_BAD_ARG, "unknown state field");
+}
+
+int32_t bfx_sampler_set_state(bfx_sampler* s, int32_t field, const void* in, int64_t nbytes) {
+  if (!s || !in) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (!s->initialised) return fail(BFX_ERR_STATE, "sampler not initialised");
+  bfx_model* m = s->m;
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  const int P = m->M.P, C = s->C;
+  if (field == BFX_STATE_THETA || field == BFX_STATE_MOMENTUM || field == BFX_STATE_MINV) {
+    float* dst = field == BFX_STATE_THETA ? s->theta : field == BFX_STATE_MOMENTUM ? s->mom : s->minv;
+    if (!dst) return fail(BFX_ERR_STATE, "this sampler does not carry that state");
+    if (nbytes != (int64_t)P * C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold P x C floats");
+    CK(copy_rows_h2d(dst, s->Ps, static_cast<const float*>(in), P, C, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    return BFX_OK;
+  }
+  std::vector<ChainScalars> sc;
+  st = fetch_scalars(s, sc);
+  if (st) return st;
+  if (field == BFX_STATE_XI || field == BFX_STATE_STEPSIZE) {
+    if (nbytes != (int64_t)C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold C floats");
+    const float* v = static_cast<const float*>(in);
+    for (int c = 0; c < C; ++c) (field == BFX_STATE_XI ? sc[c].xi : sc[c].l) = v[c];
+  } else if (field == BFX_STATE_T || field == BFX_STATE_NSAMPLED) {
+    if (nbytes != (int64_t)C * 8) return fail(BFX_ERR_BAD_ARG, "buffer must hold C int64");
+    const int64_t* v = static_cast<const int64_t*>(in);
+    for (int c = 0; c < C; ++c) (field == BFX_STATE_T ? sc[c].t : sc[c].nsampled) = v[c];
+    if (field == BFX_STATE_NSAMPLED) s->nsampled = v[0];
+  } else if (field == BFX_STATE_STATUS) {
+    if (nbytes != (int64_t)C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold C int32");
+    const int32_t* v = static_cast<const int32_t*>(in);
+    for (int c = 0; c < C; ++c) sc[c].status = v[c];
+  } else {
+    return fail(BFX_ERR_BAD_ARG, "unknown state field");
+  }
+  CK(cudaMemcpy(s->sc, sc.data(), sizeof(ChainScalars) * sc.size(), cudaMemcpyHostToDevice));
+  return BFX_OK;
+}
+
+static void fill_run_common(bfx_sampler* s, RunDev& R) {
+  bfx_model* m = s->m;
+  R.M = m->M;
+  R.S = s->S;
+  R.x = m->x;
+  R.y = m->y;
+  R.n = m->n;
+  R.C = s->C;
+  R.chain0 = 0;
+  R.Ps = s->Ps;
+  R.theta = s->theta;
+  R.mom = s->mom;
+  R.minv = s->minv;
+  R.theta_old = s->theta_old;
+  R.rms_v = s->rms_v;
+  R.ring = s->ring;
+  R.sc = s->sc;
+  R.keep_every = 1;
+  R.progress = nullptr;
+}
+
+static int ndraws_of(int kind) { return kind == BFX_GGMC ? 2 : 1; }
+
+static int32_t status_after(bfx_sampler* s) {
+  std::vector<ChainScalars> sc;
+  int32_t st = fetch_scalars(s, sc);
+  if (st) return st;
+  for (int c = 0; c < s->C; ++c)
+    if (sc[c].status != 0) {
+      char buf[96];
+      std::snprintf(buf, sizeof buf, "NaN in %s (chain %d)", sc[c].status == BFX_ERR_NAN_G ? "g" : "θ", c);
+      return fail(sc[c].status, buf);
+    }
+  s->nsampled = sc[0].nsampled;
+  return BFX_OK;
+}
+
+int32_t bfx_sampler_step_injected(bfx_sampler* s, const int64_t* idx, int64_t B, int64_t stride, float num_batches,
+                                  const float* normals, const float* uniforms, float* theta_out) {
+  if (!s || !idx || !normals) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (!s->initialised) return fail(BFX_ERR_STATE, "sampler not initialised");
+  bfx_model* m = s->m;
+  if (!m->x) return fail(BFX_ERR_NO_DATA, "bfx_model_set_data has not been called");
+  if (B <= 0) return fail(BFX_ERR_BAD_ARG, "B must be > 0");
+  const bool mh = s->S.kind == S_GGMC || s->S.kind == S_HMC;
+  if (mh && !uniforms) return fail(BFX_ERR_BAD_ARG, "uniforms required for GGMC/HMC");
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  const int P = m->M.P, C = s->C;
+  const int64_t nidx = stride ? (int64_t)(C - 1) * stride + B : B;
+  for (int64_t i = 0; i < nidx; ++i)
+    if (idx[i] < 0 || idx[i] >= m->n) return fail(BFX_ERR_BAD_ARG, "batch index out of range");
+  const size_t nn = (size_t)ndraws_of(s->S.kind) * P * C;
+  float *d_n = nullptr, *d_u = nullptr;
+  long long* d_idx = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_n);
+    cudaFree(d_u);
+    cudaFree(d_idx);
+  };
+  CKC(cudaMalloc(&d_n, nn * 4));
+  CKC(cudaMalloc(&d_idx, (size_t)nidx * 8));
+  CKC(cudaMemcpyAsync(d_n, normals, nn * 4, cudaMemcpyHostToDevice, m->stream));
+  CKC(cudaMemcpyAsync(d_idx, idx, (size_t)nidx * 8, cudaMemcpyHostToDevice, m->stream));
+  if (uniforms) {
+    CKC(cudaMalloc(&d_u, (size_t)C * 4));
+    CKC(cudaMemcpyAsync(d_u, uniforms, (size_t)C * 4, cudaMemcpyHostToDevice, m->stream));
+  }
+  RunDev R{};
+  fill_run_common(s, R);
+  R.B = B;
+  R.nb = 1;
+  R.num_batches = num_batches;
+  R.shuffle = 0;
+  R.idx = d_idx;
+  R.idx_chain_stride = stride;
+  R.seed = 0;
+  R.gstep0 = s->gstep;
+  R.nsteps = 1;
+  R.inj_normals = d_n;
+  R.inj_uniforms = d_u;
+  CKC(launch_mcmc(R, m->cfg, m->stream));
+  s->launches += 1;
+  s->gstep += 1;
+  if (theta_out) CKC(copy_rows_d2h(theta_out, P, s->theta, s->Ps, C, m->stream));
+  CKC(cudaStreamSynchronize(m->stream));
+  cleanup();
+  return status_after(s);
+}
+
+static int32_t run_counts(const bfx_sampler* s, const bfx_run_desc* run, int64_t* nnew, int64_t* nkept) {
+  if (!s || !run) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (run->numsamples < 0 || run->batchsize <= 0) return fail(BFX_ERR_BAD_ARG, "bad batchsize / numsamples");
+  const int64_t ke = run->keep_every > 0 ? run->keep_every : 1;
+  const int64_t base = run->continue_sampling ? s->nsampled : 0;
+  if (run->continue_sampling && !s->initialised) return fail(BFX_ERR_STATE, "continue_sampling needs a previous run");
+  int64_t nn = run->numsamples - base;
+  if (nn < 0) nn = 0;
+  if (nnew) *nnew = nn;
+  if (nkept) *nkept = (base + nn) / ke - base / ke;
+  return BFX_OK;
+}
+
+int32_t bfx_mcmc_num_kept(const bfx_sampler* s, const bfx_run_desc* run, int64_t* nnew, int64_t* nkept) {
+  return run_counts(s, run, nnew, nkept);
+}
+
+static int32_t prepare_schedule(bfx_sampler* s, const bfx_run_desc* run, RunDev& R) {
+  bfx_model* m = s->m;
+  if (!m->x) return fail(BFX_ERR_NO_DATA, "bfx_model_set_data has not been called");
+  fill_run_common(s, R);
+  R.B = run->batchsize < m->n ? run->batchsize : m->n;
+  R.nb = run->partial ? (m->n + R.B - 1) / R.B : m->n / R.B;  // length(DataLoader)
+  if (R.nb < 1) R.nb = 1;
+  R.num_batches = (float)R.nb;
+  R.shuffle = run->shuffle ? 1 : 0;
+  R.batch_shared = run->batch_mode == BFX_BATCH_SHARED;
+  R.idx = nullptr;
+  R.seed = run->seed;
+  R.chain0 = (unsigned)run->chain_offset;
+  R.keep_every = run->keep_every > 0 ? run->keep_every : 1;
+  return BFX_OK;
+}
+
+int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta_start, float* samples_out,
+                     float* kinetic_out, int32_t* accepted_out) {
+  int64_t nnew = 0, nkept = 0;
+  int32_t st = run_counts(s, run, &nnew, &nkept);
+  if (st) return st;
+  bfx_model* m = s->m;
+  st = ensure_stream(m);
+  if (st) return st;
+  if (!run->continue_sampling) {
+    if (!theta_start) return fail(BFX_ERR_BAD_ARG, "theta_start is NULL");
+    st = bfx_sampler_init(s, theta_start);
+    if (st) return st;
+  }
+  if (nnew == 0) return BFX_OK;
+  if (run->continue_sampling) {
+    // initialise!(...; continue_sampling=true) re-zeroes the momentum (sgnht.jl:54, sgnht-s.jl:72,
+    // ggmc.jl:122, hmc.jl:92-93) and GGMC restarts its window (ggmc.jl:116); everything else is kept
+    if (s->mom) CK(cudaMemsetAsync(s->mom, 0, (size_t)s->Ps * sizeof(float) * (size_t)s->C, m->stream));
+    if (s->S.kind == S_GGMC) {
+      std::vector<ChainScalars> sc;
+      st = fetch_scalars(s, sc);
+      if (st) return st;
+      for (auto& c : sc) c.current_step = 1;
+      CK(cudaMemcpy(s->sc, sc.data(), sizeof(ChainScalars) * sc.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  RunDev R{};
+  st = prepare_schedule(s, run, R);
+  if (st) return st;
+  const int P = m->M.P, C = s->C;
+  const int64_t ke = R.keep_every;
+  const int64_t ups = s->S.kind == S_HMC ? s->S.path_len : 1;  // update! calls per sample
+  const int64_t win = s->S.kind == S_GGMC ? s->S.steps : 1;    // samples that may be rewritten together
+  const int64_t base = s->nsampled;
+  // chunking: device sample buffers of <= ~1 GiB each, double buffered
+  int64_t chunk_samples = nnew;
+  const int64_t bytes_per_kept = (int64_t)C * P * 4;
+  if (samples_out) {
+    int64_t max_kept = (int64_t)(1ll << 30) / bytes_per_kept;
+    if (max_kept < 1) max_kept = 1;
+    chunk_samples = max_kept * ke;
+  }
+  const int64_t max_steps_per_launch = 1 << 16;
+  if (chunk_samples * ups > max_steps_per_launch) chunk_samples = max_steps_per_launch / ups;
+  chunk_samples = chunk_samples / win * win;
+  if (chunk_samples < win) chunk_samples = win;
+  float* d_samp[2] = {nullptr, nullptr};
+  float* d_kin = nullptr;
+  int* d_acc = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  bool registered = false;
+  auto cleanup = [&]() {
+    cudaFree(d_samp[0]);
+    cudaFree(d_samp[1]);
+    cudaFree(d_kin);
+    cudaFree(d_acc);
+    for (int i = 0; i < 2; ++i) {
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+      if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+    }
+    if (registered) cudaHostUnregister(samples_out);
+  };
+  int64_t slots_per_chunk = 0;
+  if (samples_out && nkept > 0) {
+    slots_per_chunk = chunk_samples / ke + 1;
+    for (int i = 0; i < 2; ++i) {
+      CKC(cudaMalloc(&d_samp[i], (size_t)slots_per_chunk * bytes_per_kept));
+      CKC(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+      CKC(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+    }
+    registered = cudaHostRegister(samples_out, (size_t)nkept * bytes_per_kept, cudaHostRegisterDefault) == cudaSuccess;
+    if (!registered) cudaGetLastError();
+  }
+  if (kinetic_out && (s->S.kind == S_SGNHT || s->S.kind == S_SGNHTS)) {
+    CKC(cudaMalloc(&d_kin, (size_t)C * nnew * 4));
+    CKC(cudaMemsetAsync(d_kin, 0, (size_t)C * nnew * 4, m->stream));
+  }
+  if (accepted_out && (s->S.kind == S_GGMC || s->S.kind == S_HMC)) {
+    CKC(cudaMalloc(&d_acc, (size_t)C * nnew * 4));
+    CKC(cudaMemsetAsync(d_acc, 0, (size_t)C * nnew * 4, m->stream));
+  }
+  R.kinetic_out = d_kin;
+  R.accepted_out = d_acc;
+  R.hist_stride = nnew;
+  R.hist_origin = base;
+  R.progress = s->progress_dev;
+  int64_t done = 0;
+  int buf = 0;
+  int64_t kept_written = 0;
+  while (done < nnew) {
+    const int64_t cs = std::min(chunk_samples, nnew - done);
+    const int64_t a = base + done, b = a + cs;
+    const int64_t slots = b / ke - a / ke;
+    R.gstep0 = s->gstep;
+    R.nsteps = (int)(cs * ups);
+    if (d_samp[buf] && slots > 0) {
+      CKC(cudaStreamWaitEvent(m->stream, ev_copied[buf], 0));  // buffer free again?
+      R.samples = d_samp[buf];
+      R.samples_chain_stride = slots * P;
+      R.kept_origin = a / ke;
+    } else {
+      R.samples = nullptr;
+    }
+    CKC(launch_mcmc(R, m->cfg, m->stream));
+    s->launches += 1;
+    s->gstep += R.nsteps;
+    if (R.samples) {
+      CKC(cudaEventRecord(ev_done[buf], m->stream));
+      CKC(cudaStreamWaitEvent(s->copy_stream, ev_done[buf], 0));
+      // device [C][slots][P]  ->  host [C][nkept][P] at column kept_written
+      CKC(cudaMemcpy2DAsync(samples_out + kept_written * P, (size_t)nkept * P * 4, d_samp[buf], (size_t)slots * P * 4,
+                            (size_t)slots * P * 4, C, cudaMemcpyDeviceToHost, s->copy_stream));
+      CKC(cudaEventRecord(ev_copied[buf], s->copy_stream));
+      kept_written += slots;
+      buf ^= 1;
+    }
+    done += cs;
+  }
+  CKC(cudaStreamSynchronize(m->stream));
+  CKC(cudaStreamSynchronize(s->copy_stream));
+  if (d_kin) {
+    // device [C][nnew] -> host nnew x C column-major == the same bytes
+    CKC(cudaMemcpy(kinetic_out, d_kin, (size_t)C * nnew * 4, cudaMemcpyDeviceToHost));
+  }
+  if (d_acc) CKC(cudaMemcpy(accepted_out, d_acc, (size_t)C * nnew * 4, cudaMemcpyDeviceToHost));
+  cleanup();
+  return status_after(s);
+}
+
+int32_t bfx_progress(const bfx_sampler* s, int64_t* nsampled) {
+  if (!s || !nsampled) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  *nsampled = (int64_t) * (volatile unsigned long long*)s->progress_host;
+  return BFX_OK;
+}
+
+int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, void* stream_handle) {
+  if (!s || !run) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (!s->initialised) return fail(BFX_ERR_STATE, "sampler not initialised");
+  if (nsteps <= 0) return BFX_OK;
+  bfx_model* m = s->m;
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  RunDev R{};
+  st = prepare_schedule(s, run, R);
+  if (st) return st;
+  cudaStream_t stream = stream_handle ? (cudaStream_t)stream_handle : m->stream;
+  int64_t done = 0;
+  while (done < nsteps) {
+    const int64_t cs = std::min<int64_t>(nsteps - done, 1 << 16);
+    R.gstep0 = s->gstep;
+    R.nsteps = (int)cs;
+    CK(launch_mcmc(R, m->cfg, stream));
+    s->launches += 1;
+    s->gstep += cs;
+    done += cs;
+  }
+  return BFX_OK;
+}
+
+int32_t bfx_sampler_launch_count(const bfx_sampler* s, int64_t* n) {
+  if (!s || !n) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  *n = s->launches;
+  return BFX_OK;
+}
+
+int32_t bfx_debug_batch_indices(const bfx_sampler* s, const bfx_run_desc* run, int64_t chain, int64_t step,
+                                int64_t* idx_out, int64_t* B_out) {
+  if (!s || !run || !idx_out || !B_out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  bfx_model* m = s->m;
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  RunDev R{};
+  st = prepare_schedule(const_cast<bfx_sampler*>(s), run, R);
+  if (st) return st;
+  long long *d_out = nullptr, *d_B = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_out);
+    cudaFree(d_B);
+  };
+  CKC(cudaMalloc(&d_out, (size_t)R.B * 8));
+  CKC(cudaMalloc(&d_B, 8));
+  CKC(launch_debug_batch(R, (int)chain, (unsigned long long)step, d_out, d_B, m->stream));
+  long long Bk = 0;
+  CKC(cudaMemcpyAsync(&Bk, d_B, 8, cudaMemcpyDeviceToHost, m->stream));
+  CKC(cudaStreamSynchronize(m->stream));
+  CKC(cudaMemcpy(idx_out, d_out, (size_t)Bk * 8, cudaMemcpyDeviceToHost));
+  *B_out = Bk;
+  cleanup();
+  return BFX_OK;
+}
+
+int32_t bfx_debug_noise(const bfx_sampler* s, const bfx_run_desc* run, int64_t chain, int64_t step, int32_t slot,
+                        float* normals_out, float* uniform_out) {
+  if (!s || !run || !normals_out || !uniform_out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  bfx_model* m = s->m;
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  const int P = m->M.P;
+  float *d_n = nullptr, *d_u = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_n);
+    cudaFree(d_u);
+  };
+  CKC(cudaMalloc(&d_n, (size_t)P * 4));
+  CKC(cudaMalloc(&d_u, 4));
+  CKC(launch_debug_noise(run->seed, (unsigned)(run->chain_offset + chain), (unsigned long long)step, (unsigned)slot, P, d_n, d_u, m->stream));
+  CKC(cudaMemcpyAsync(normals_out, d_n, (size_t)P * 4, cudaMemcpyDeviceToHost, m->stream));
+  CKC(cudaMemcpyAsync(uniform_out, d_u, 4, cudaMemcpyDeviceToHost, m->stream));
+  CKC(cudaStreamSynchronize(m->stream));
+  cleanup();
+  return BFX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Chain-level device functions: log posterior value / gradient over a whole minibatch
+// (loop over batch tiles), and the per-sampler update steps.  One CTA = one chain.
+#pragma once
+#include "bfx_device.cuh"
+
+namespace bfx {
+
+// ---------------------------------------------------------------------------------
+// value (and gradient into s.g) of  num_batches*loglike + logprior  on one minibatch.
+// src/model/BNN.jl:50-69.  Returns the value on every thread; gn2 = ||g||^2 over all P.
+// ---------------------------------------------------------------------------------
+template <int NT, int BT>
+BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
+                          const float* __restrict__ y, const BatchSrc& bs, long long B, float nb, bool want_grad,
+                          float& gn2) {
+  if (want_grad) {
+    for (int k = threadIdx.x; k < M.S; k += NT) s.g[k] = 0.f;
+  }
+  const float sl = s.th[M.like_s];
+  const float sigma = expf(sl);
+  LikeCoef lc;
+  lc.inv_sigma = 1.f / sigma;
+  lc.nb = nb;
+  double ds0 = 0.0, ds1 = 0.0;
+  __syncthreads();
+  for (long long t0 = 0; t0 < B; t0 += BT) {
+    int nvalid = (int)((B - t0) < (long long)BT ? (B - t0) : (long long)BT);
+    float sums[2] = {0.f, 0.f};
+    mlp_tile<NT, BT>(M, s, x, y, bs, t0, nvalid, lc, want_grad, sums);
+    ds0 += (double)sums[0];
+    ds1 += (double)sums[1];
+    __syncthreads();
+  }
+  // reduce the likelihood sums in double
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds0 += __shfl_xor_sync(0xffffffffu, ds0, o);
+    ds1 += __shfl_xor_sync(0xffffffffu, ds1, o);
+  }
+  if (NT > 32) {
+    double* dred = reinterpret_cast<double*>(s.red);  // 32*4 floats = 64 doubles
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+      dred[2 * w] = ds0;
+      dred[2 * w + 1] = ds1;
+    }
+    __syncthreads();
+    ds0 = 0.0;
+    ds1 = 0.0;
+    for (int ww = 0; ww < NT / 32; ++ww) {
+      ds0 += dred[2 * ww];
+      ds1 += dred[2 * ww + 1];
+    }
+    __syncthreads();
+  }
+  // sigma prior (log link): logpdf(prior, e^s) + s and its derivative w.r.t. s
+  double lps, dlps;
+  if (M.sprior_kind == SP_GAMMA) {
+    lps = M.sprior_const + ((double)M.sprior_a - 1.0) * (double)sl - (double)sigma / (double)M.sprior_b + (double)sl;
+    dlps = (double)M.sprior_a - (double)sigma / (double)M.sprior_b;
+  } else {
+    lps = M.sprior_const - ((double)M.sprior_a + 1.0) * (double)sl - (double)M.sprior_b / (double)sigma + (double)sl;
+    dlps = -(double)M.sprior_a + (double)M.sprior_b / (double)sigma;
+  }
+  double like, dlike_ds;
+  if (M.like_kind == LK_NORMAL) {
+    like = -0.5 * (double)B * 1.8378770664093453 - 0.5 * ds0;
+    dlike_ds = ds0;
+  } else {
+    like = (double)B * M.tdist_const - 0.5 * ((double)M.nu + 1.0) * ds0;
+    dlike_ds = ds1;
+  }
+  like += -(double)B * (double)sl + lps;
+  dlike_ds += -(double)B + dlps;
+  // prior over theta_net + finish the gradient
+  float acc[2] = {0.f, 0.f};  // sum theta_net^2, sum g^2
+  const float c2 = M.prior_c2;
+  const float glike = (float)((double)nb * dlike_ds);
+  const int Pnet = M.Pnet;
+  for_each_param<NT>(M, [&](int J, int k) {
+    float th = s.th[k];
+    float g;
+    if (J < Pnet) {
+      acc[0] += th * th;
+      g = s.g[k] - c2 * th;
+    } else {
+      g = glike;
+    }
+    if (want_grad) {
+      s.g[k] = g;
+      acc[1] += g * g;
+    }
+  });
+  block_sum<NT, 2>(acc, s.red);
+  gn2 = acc[1];
+  return (double)nb * like + (M.prior_c0n - 0.5 * (double)c2 * (double)acc[0]);
+}
+
+BFX_DEV float clip_scale(float gn2, float maxnorm) {
+  float ng = sqrtf(gn2);
+  return ng > maxnorm ? maxnorm / ng : 1.f;  // src/utils/gradient_utils.jl:6-10
+}
+
+}  // namespace bfx

@@ -1,0 +1,160 @@
+// Shared host/device descriptors of the bfx engine (sm_100a).
+//
+// Device-side picture of one BNN (reference: src/model/BNN.jl:5-38):
+//   * flat theta  = [theta_net ; theta_like]  exactly as the reference lays it out
+//     (src/model/deconstruct.jl:45-58, src/layers/dense.jl:13-26, recurrent.jl:13-68);
+//     this is the HBM layout (one row of P floats per chain) and the ABI layout.
+//   * inside a chain's CTA the parameters live in shared memory in a PADDED layout:
+//     every weight matrix keeps the reference's column-major order (W[o,i] at
+//     i*ldw + o) but its leading dimension ldw is rounded so that ldw/4 is odd
+//     (conflict-free 128-bit shared loads for all three GEMM shapes) and the row
+//     count is rounded to 4 (zero filled).  SegDesc maps flat <-> padded.
+#pragma once
+#include <cstdint>
+
+#define BFX_MAX_LAYERS 8
+#define BFX_MAX_SEGS (3 * BFX_MAX_LAYERS + 1)
+
+namespace bfx {
+
+enum { L_DENSE = 0, L_RNN = 1, L_LSTM = 2 };
+enum { A_IDENTITY = 0, A_RELU = 1, A_TANH = 2, A_SIGMOID = 3 };
+enum { LK_NORMAL = 0, LK_TDIST = 1 };
+enum { SP_GAMMA = 0, SP_INVGAMMA = 1 };
+enum { S_SGLD = 0, S_SGNHT = 1, S_SGNHTS = 2, S_GGMC = 3, S_HMC = 4 };
+enum { SA_CONST = 0, SA_DUAL = 1 };
+enum { MA_FIXED = 0, MA_DIAGCOV = 1, MA_RMSPROP = 2 };
+
+// one contiguous run of the flat theta (a weight matrix, a bias vector, theta_like)
+struct SegDesc {
+  int flat_off;  // first flat index
+  int count;     // number of flat entries
+  int s_off;     // offset in the padded shared-memory parameter block
+  int rows;      // fast (contiguous) dimension of the matrix (= out); count for vectors
+  int ld;        // padded leading dimension in shared memory (== rows for vectors)
+  float rcp_rows;
+};
+
+struct LayerDev {
+  int kind, nin, nout, act;
+  int nout_pad;  // round4(rows of the gate/output block): Dense out, RNN H, LSTM 4H
+  int nin_pad;   // round4(nin)
+  int H;         // hidden size for recurrent layers (== nout)
+  int ldw;       // leading dim of W / Wi in smem
+  int ldh;       // leading dim of Wh in smem (recurrent only)
+  int w_s, wh_s, b_s;  // smem offsets: W (or Wi), Wh, bias
+};
+
+struct ModelDev {
+  int nlayers;
+  int P, Pnet;   // total / network parameters
+  int S;         // floats in the padded smem parameter block (multiple of 4)
+  int nsegs;
+  int like_s;    // smem offset of theta_like
+  int like_kind, sprior_kind;
+  float nu;
+  float sprior_a, sprior_b;
+  float prior_c2;      // logprior = Pnet*c0 - 0.5*c2*sum(theta_net^2)
+  double prior_c0n;    // Pnet*c0
+  double tdist_const;  // lgamma((nu+1)/2) - lgamma(nu/2) - 0.5*log(nu*pi)
+  double sprior_const; // constant of logpdf(prior_sigma)
+  int d_in;            // features per observation (per time step)
+  int seq;             // 1: x is T x d x n
+  int T;
+  int rec_layer;       // index of the recurrent layer or -1
+  int act_off[BFX_MAX_LAYERS + 1];   // float offsets of the activation buffers in smem
+  int act_rows[BFX_MAX_LAYERS + 1];  // padded row counts
+  int act_total;                     // floats of activation smem for one batch tile
+  LayerDev L[BFX_MAX_LAYERS];
+  SegDesc seg[BFX_MAX_SEGS];
+};
+
+// sampler hyper-parameters (device copy of bfx_sampler_desc, see include/bfx.h)
+struct SamplerDev {
+  int kind, steps, path_len, sadapter_kind, madapter_kind;
+  int da_t0, da_adapt_steps, ma_adapt_steps, ma_windowlength;
+  float stepsize_a, stepsize_b, stepsize_gamma, min_stepsize, maxnorm;
+  float l, A, sigmaA, xi, mu, beta;
+  float da_target_accept, da_gamma, da_kappa, da_mu;
+  float ma_kappa, ma_epsilon, ma_lambda, ma_alpha;
+};
+
+// per-chain scalar state kept in HBM between launches (mutable fields of the
+// reference's sampler and adapter structs)
+struct ChainScalars {
+  long long t;          // sampler step counter, 1-based like the reference
+  long long nsampled;
+  float xi;             // thermostat (SGNHT / SGNHTS)
+  float l;              // current step size
+  float lMH;            // GGMC running log MH ratio
+  int current_step;     // GGMC / HMC position inside the window / trajectory
+  // DualAveragingStepSize (adapters/stepsize/dualaveragestepsize.jl:11-23)
+  int da_t;
+  float da_error_sum;
+  float da_log_avg;
+  // mass adapters: own counter t (diagcovariancemassadapter.jl:13-20, rmspropmassadapter.jl:9-16)
+  int ma_t;
+  int status;           // 0 | BFX_ERR_NAN_G | BFX_ERR_NAN_THETA
+  double start_lp;      // HMC: -loglikeprior(theta_old) cache is NOT used (reference recomputes)
+  long long accepted_total;
+};
+
+// everything a launch needs (passed by value as a __grid_constant__ kernel parameter)
+struct RunDev {
+  ModelDev M;
+  SamplerDev S;
+  const float* x;
+  const float* y;
+  long long n;
+  int C;
+  unsigned chain0;  // global id of local chain 0 (noise / permutation keys)
+  // per-chain state, flat layout, row stride Ps floats
+  int Ps;
+  float* theta;
+  float* mom;
+  float* minv;
+  float* theta_old;
+  float* rms_v;
+  float* ring;  // [C][w][Ps] DiagCov window
+  ChainScalars* sc;
+  // batch schedule (src/inference/mcmc/abstract.jl:102-105,117-118)
+  long long B, nb;
+  float num_batches;
+  int shuffle, batch_shared;
+  const long long* idx;  // explicit minibatch (injected step) or nullptr
+  long long idx_chain_stride;
+  unsigned long long seed;
+  long long gstep0;  // global update! count before this launch
+  int nsteps;
+  // injected noise (parity entry) or nullptr
+  const float* inj_normals;  // [ndraw][C][P]
+  const float* inj_uniforms; // [C]
+  // outputs
+  float* samples;            // [C][slots][P] or nullptr
+  long long samples_chain_stride;
+  long long kept_origin;     // number of kept samples that precede slot 0
+  int keep_every;
+  float* kinetic_out;        // [C][hist_stride]
+  int* accepted_out;         // [C][hist_stride]
+  long long hist_stride, hist_origin;
+  unsigned long long* progress;
+};
+
+// evaluation-only launch (bfx_loglikeprior / bfx_grad_loglikeprior)
+struct EvalDev {
+  ModelDev M;
+  const float* x;
+  const float* y;
+  long long n;
+  int C;
+  const float* theta;  // [C][P]
+  const long long* idx;
+  long long idx_chain_stride;
+  long long B;
+  float num_batches;
+  int want_grad;
+  double* v_out;  // [C]
+  float* g_out;   // [C][P]
+};
+
+}  // namespace bfx

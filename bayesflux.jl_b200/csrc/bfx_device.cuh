@@ -1,0 +1,526 @@
+// Device building blocks of the small-P ("theta resident in shared memory") regime:
+// Philox noise, keyed batch permutation, block reductions, the three register-tiled
+// shared-memory GEMM shapes, the fused MLP forward / likelihood / backward pass over one
+// minibatch tile, and the element-wise parameter passes the samplers are made of.
+//
+// One CTA owns one chain.  theta and the gradient stay in shared memory for the whole
+// launch; only minibatch rows (L2-resident data set) and recorded samples touch HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "bfx_common.cuh"
+
+namespace bfx {
+
+#define BFX_DEV __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  counter = (quad index, step, chain, draw slot)
+// ---------------------------------------------------------------------------------
+BFX_DEV uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// two uint32 -> two independent N(0,1) (Box-Muller)
+BFX_DEV float2 box_muller(unsigned a, unsigned b) {
+  float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  float u2 = (float)b * 2.3283064365386963e-10f;           // [0,1)
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+struct NoiseKey {
+  unsigned long long seed;
+  unsigned chain;  // global chain id
+};
+
+// the 4 standard normals of flat parameters 4q..4q+3 for (chain, step, slot)
+BFX_DEV float4 normal_quad(const NoiseKey& k, unsigned long long step, unsigned slot, unsigned q) {
+  uint4 ctr = make_uint4(q, (unsigned)step, k.chain, (slot << 24) | (unsigned)((step >> 32) & 0xFFFFFFu));
+  uint2 key = make_uint2((unsigned)k.seed, (unsigned)(k.seed >> 32));
+  uint4 r = philox4x32_10(ctr, key);
+  float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// the uniform(0,1) of (chain, step) used by the MH accept tests
+BFX_DEV float uniform_draw(const NoiseKey& k, unsigned long long step) {
+  uint4 ctr = make_uint4(0xFFFFFFFFu, (unsigned)step, k.chain, 0xFF000000u | (unsigned)((step >> 32) & 0xFFFFFFu));
+  uint2 key = make_uint2((unsigned)k.seed, (unsigned)(k.seed >> 32));
+  uint4 r = philox4x32_10(ctr, key);
+  return ((float)(r.x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // (0,1)
+}
+
+// ---------------------------------------------------------------------------------
+// per-epoch pseudo-random permutation of [0,n): keyed Feistel network on the next
+// power of two, cycle-walked into range.  Replaces MLUtils' randperm(n) per epoch
+// (src/inference/mcmc/abstract.jl:102-103): every observation exactly once per epoch.
+// ---------------------------------------------------------------------------------
+BFX_DEV unsigned mix32(unsigned x) {
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+
+BFX_DEV unsigned long long perm_index(unsigned long long pos, unsigned long long n, unsigned k0, unsigned k1) {
+  if (n <= 1) return 0;
+  int bits = 64 - __clzll((long long)(n - 1));
+  if (bits < 2) bits = 2;
+  const int lb = bits >> 1, rb = bits - lb;  // left (high) / right (low) widths
+  const unsigned long long lmask = (1ull << lb) - 1, rmask = (1ull << rb) - 1;
+  unsigned long long v = pos;
+  do {
+    unsigned long long L = (v >> rb) & lmask, R = v & rmask;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      // alternate which half is updated so that widths stay fixed (unbalanced Feistel)
+      if ((r & 1) == 0)
+        L = (L ^ (unsigned long long)mix32((unsigned)R * 0x9E3779B1u + k0 + (unsigned)r * 0x85EBCA6Bu + (unsigned)(R >> 32))) & lmask;
+      else
+        R = (R ^ (unsigned long long)mix32((unsigned)L * 0xC2B2AE35u + k1 + (unsigned)r * 0x27D4EB2Fu)) & rmask;
+    }
+    v = (L << rb) | R;
+  } while (v >= n);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------
+// block reductions (warp shuffle + one smem hop).  `red` holds >= 32*N floats.
+// ---------------------------------------------------------------------------------
+template <int N>
+BFX_DEV void warp_sum(float (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+}
+
+template <int NT, int N>
+BFX_DEV void block_sum(float (&v)[N], float* red) {
+  warp_sum<N>(v);
+  if (NT > 32) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0)
+#pragma unroll
+      for (int i = 0; i < N; ++i) red[w * N + i] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < NT / 32; ++ww) s += red[ww * N + i];
+      v[i] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// activations.  Accurate tanhf/expf forms: Flux's tanh_fast/sigmoid_fast are within a
+// few ulp of these, far inside the 1e-4 parity tolerance.
+// ---------------------------------------------------------------------------------
+BFX_DEV float act_apply(int a, float z) {
+  switch (a) {
+    case A_RELU: return fmaxf(z, 0.f);
+    case A_TANH: return tanhf(z);
+    case A_SIGMOID: return 1.f / (1.f + expf(-z));
+    default: return z;
+  }
+}
+BFX_DEV float act_deriv_from_out(int a, float o) {
+  switch (a) {
+    case A_RELU: return o > 0.f ? 1.f : 0.f;
+    case A_TANH: return 1.f - o * o;
+    case A_SIGMOID: return o * (1.f - o);
+    default: return 1.f;
+  }
+}
+
+BFX_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+BFX_DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+#define BFX_FMA4x4(ACC, WV, AV) \
+  ACC[0][0] = fmaf(WV.x, AV.x, ACC[0][0]); \
+  ACC[0][1] = fmaf(WV.x, AV.y, ACC[0][1]); \
+  ACC[0][2] = fmaf(WV.x, AV.z, ACC[0][2]); \
+  ACC[0][3] = fmaf(WV.x, AV.w, ACC[0][3]); \
+  ACC[1][0] = fmaf(WV.y, AV.x, ACC[1][0]); \
+  ACC[1][1] = fmaf(WV.y, AV.y, ACC[1][1]); \
+  ACC[1][2] = fmaf(WV.y, AV.z, ACC[1][2]); \
+  ACC[1][3] = fmaf(WV.y, AV.w, ACC[1][3]); \
+  ACC[2][0] = fmaf(WV.z, AV.x, ACC[2][0]); \
+  ACC[2][1] = fmaf(WV.z, AV.y, ACC[2][1]); \
+  ACC[2][2] = fmaf(WV.z, AV.z, ACC[2][2]); \
+  ACC[2][3] = fmaf(WV.z, AV.w, ACC[2][3]); \
+  ACC[3][0] = fmaf(WV.w, AV.x, ACC[3][0]); \
+  ACC[3][1] = fmaf(WV.w, AV.y, ACC[3][1]); \
+  ACC[3][2] = fmaf(WV.w, AV.z, ACC[3][2]); \
+  ACC[3][3] = fmaf(WV.w, AV.w, ACC[3][3]);
+
+// ---------------------------------------------------------------------------------
+// GEMM shape 1 (forward):  Z[m][n] = act( sum_k W[k*ldw + m] * A[k*lda + n] + bias[m] )
+//   M = Mpad rows (multiple of 4), N = BT batch columns, K = fan-in.
+//   W is the reference's column-major weight (m contiguous), A is feature-major.
+//   If `accumulate`, Z is read first (used to add the recurrent term) and no bias is added.
+// ---------------------------------------------------------------------------------
+template <int NT, int BT>
+BFX_DEV void gemm_fwd(const float* __restrict__ W, int ldw, const float* __restrict__ A, int lda,
+                      const float* __restrict__ bias, float* __restrict__ Z, int ldz, int Mpad, int K, int act,
+                      bool accumulate = false) {
+  constexpr int NTN = BT / 4;
+  const int ntiles = (Mpad >> 2) * NTN;
+  for (int t = threadIdx.x; t < ntiles; t += NT) {
+    const int tm = t / NTN, tn = t - tm * NTN;
+    const float* wp = W + 4 * tm;
+    const float* ap = A + 4 * tn;
+    float* zp = Z + (4 * tm) * ldz + 4 * tn;
+    float acc[4][4];
+    if (accumulate) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 z = ld4(zp + i * ldz);
+        acc[i][0] = z.x; acc[i][1] = z.y; acc[i][2] = z.z; acc[i][3] = z.w;
+      }
+    } else {
+      float4 b = ld4(bias + 4 * tm);
+      float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = bb[i];
+    }
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float4 w = ld4(wp + (k + kk) * ldw);
+        float4 a = ld4(ap + (k + kk) * lda);
+        BFX_FMA4x4(acc, w, a);
+      }
+    }
+    for (; k < K; ++k) {
+      float4 w = ld4(wp + k * ldw);
+      float4 a = ld4(ap + k * lda);
+      BFX_FMA4x4(acc, w, a);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 o;
+      o.x = act_apply(act, acc[i][0]);
+      o.y = act_apply(act, acc[i][1]);
+      o.z = act_apply(act, acc[i][2]);
+      o.w = act_apply(act, acc[i][3]);
+      st4(zp + i * ldz, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// GEMM shape 2 (input gradient):  C[m][n] = sum_k W[m*ldw + k] * D[k*ldd + n]
+//   m = fan-in index (Mpad rows), k = fan-out index (Kpad, multiple of 4, zero padded),
+//   result is multiplied by act'(Aprev[m][n]) and written IN PLACE over Aprev, or
+//   (add_to) accumulated into `Out` without masking (used for recurrent dh).
+// ---------------------------------------------------------------------------------
+template <int NT, int BT>
+BFX_DEV void gemm_dx(const float* __restrict__ W, int ldw, const float* __restrict__ D, int ldd, float* Out,
+                     int ldo, int Mpad, int Kpad, int act_prev, bool add_to = false) {
+  constexpr int NTN = BT / 4;
+  const int ntiles = (Mpad >> 2) * NTN;
+  for (int t = threadIdx.x; t < ntiles; t += NT) {
+    const int tm = t / NTN, tn = t - tm * NTN;
+    const float* wp = W + (4 * tm) * ldw;
+    const float* dp = D + 4 * tn;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k = 0; k < Kpad; k += 4) {
+      float4 w0 = ld4(wp + k), w1 = ld4(wp + ldw + k), w2 = ld4(wp + 2 * ldw + k), w3 = ld4(wp + 3 * ldw + k);
+      float4 d;
+      float4 wc;
+      d = ld4(dp + (k + 0) * ldd); wc = make_float4(w0.x, w1.x, w2.x, w3.x); BFX_FMA4x4(acc, wc, d);
+      d = ld4(dp + (k + 1) * ldd); wc = make_float4(w0.y, w1.y, w2.y, w3.y); BFX_FMA4x4(acc, wc, d);
+      d = ld4(dp + (k + 2) * ldd); wc = make_float4(w0.z, w1.z, w2.z, w3.z); BFX_FMA4x4(acc, wc, d);
+      d = ld4(dp + (k + 3) * ldd); wc = make_float4(w0.w, w1.w, w2.w, w3.w); BFX_FMA4x4(acc, wc, d);
+    }
+    float* op = Out + (4 * tm) * ldo + 4 * tn;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 a = ld4(op + i * ldo);
+      float4 o;
+      if (add_to) {
+        o = make_float4(a.x + acc[i][0], a.y + acc[i][1], a.z + acc[i][2], a.w + acc[i][3]);
+      } else {
+        o.x = acc[i][0] * act_deriv_from_out(act_prev, a.x);
+        o.y = acc[i][1] * act_deriv_from_out(act_prev, a.y);
+        o.z = acc[i][2] * act_deriv_from_out(act_prev, a.z);
+        o.w = acc[i][3] * act_deriv_from_out(act_prev, a.w);
+      }
+      st4(op + i * ldo, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// GEMM shape 3 (weight gradient):  G[n*ldg + m] += sum_k D[m*ldd + k] * A[n*lda + k]
+//   m = fan-out (Mpad), n = fan-in (Npad, multiple of 4), k = batch column (BT).
+//   The n rows of a thread's tile are strided by Npad/4 so the 128-bit loads of A are
+//   bank-conflict free.  G uses the weight layout (m contiguous).
+// ---------------------------------------------------------------------------------
+template <int NT, int BT>
+BFX_DEV void gemm_dw(const float* __restrict__ D, int ldd, const float* __restrict__ A, int lda, float* __restrict__ G,
+                     int ldg, int Mpad, int Npad) {
+  const int ntn = Npad >> 2;
+  const int ntiles = (Mpad >> 2) * ntn;
+  for (int t = threadIdx.x; t < ntiles; t += NT) {
+    const int tm = t / ntn, tn = t - tm * ntn;
+    const float* dp = D + (4 * tm) * ldd;
+    const float* ap = A + tn * lda;
+    const int as = ntn * lda;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < BT; k += 4) {
+      float4 d0 = ld4(dp + k), d1 = ld4(dp + ldd + k), d2 = ld4(dp + 2 * ldd + k), d3 = ld4(dp + 3 * ldd + k);
+      float4 a0 = ld4(ap + k), a1 = ld4(ap + as + k), a2 = ld4(ap + 2 * as + k), a3 = ld4(ap + 3 * as + k);
+      float4 wc, ac;
+      wc = make_float4(d0.x, d1.x, d2.x, d3.x); ac = make_float4(a0.x, a1.x, a2.x, a3.x); BFX_FMA4x4(acc, wc, ac);
+      wc = make_float4(d0.y, d1.y, d2.y, d3.y); ac = make_float4(a0.y, a1.y, a2.y, a3.y); BFX_FMA4x4(acc, wc, ac);
+      wc = make_float4(d0.z, d1.z, d2.z, d3.z); ac = make_float4(a0.z, a1.z, a2.z, a3.z); BFX_FMA4x4(acc, wc, ac);
+      wc = make_float4(d0.w, d1.w, d2.w, d3.w); ac = make_float4(a0.w, a1.w, a2.w, a3.w); BFX_FMA4x4(acc, wc, ac);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* gp = G + (tn + j * ntn) * ldg + 4 * tm;
+      float4 g = ld4(gp);
+      g.x += acc[0][j]; g.y += acc[1][j]; g.z += acc[2][j]; g.w += acc[3][j];
+      st4(gp, g);
+    }
+  }
+}
+
+// bias gradient: G[m] += sum_k D[m*ldd + k], one warp per row
+template <int NT, int BT>
+BFX_DEV void rowsum_acc(const float* __restrict__ D, int ldd, float* __restrict__ G, int M) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int m = w; m < M; m += NT / 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = lane; k < BT; k += 32) s += D[m * ldd + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) G[m] += s;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// flat <-> padded parameter mapping
+// ---------------------------------------------------------------------------------
+BFX_DEV int seg_map(const SegDesc& sg, int j /* index inside the segment */) {
+  if (sg.ld == sg.rows) return sg.s_off + j;
+  int i = __float2int_rz(((float)j + 0.5f) * sg.rcp_rows);
+  return sg.s_off + i * sg.ld + (j - i * sg.rows);
+}
+
+// call f(flat index, smem index) for every parameter of the chain
+template <int NT, class F>
+BFX_DEV void for_each_param(const ModelDev& M, F f) {
+  for (int s = 0; s < M.nsegs; ++s) {
+    const SegDesc sg = M.seg[s];
+    for (int j = threadIdx.x; j < sg.count; j += NT) f(sg.flat_off + j, seg_map(sg, j));
+  }
+}
+
+// find the smem index of flat index J, remembering the segment in `hint`
+BFX_DEV int map_flat(const ModelDev& M, int J, int& hint) {
+  while (J >= M.seg[hint].flat_off + M.seg[hint].count) ++hint;
+  while (J < M.seg[hint].flat_off) --hint;
+  return seg_map(M.seg[hint], J - M.seg[hint].flat_off);
+}
+
+// call f(flat index J, smem index k, standard normal z) for every parameter; the normals are
+// either injected (inj[J]) or Philox draws of (key, step, slot)
+template <int NT, class F>
+BFX_DEV void for_each_param_noise(const ModelDev& M, const NoiseKey& key, unsigned long long step, unsigned slot,
+                                  const float* __restrict__ inj, F f) {
+  const int nq = (M.P + 3) >> 2;
+  int hint = 0;
+  for (int q = threadIdx.x; q < nq; q += NT) {
+    float z[4];
+    if (inj) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) z[e] = (4 * q + e < M.P) ? inj[4 * q + e] : 0.f;
+    } else {
+      float4 zz = normal_quad(key, step, slot, (unsigned)q);
+      z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int J = 4 * q + e;
+      if (J < M.P) f(J, map_flat(M, J, hint), z[e]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// per-CTA working set
+// ---------------------------------------------------------------------------------
+template <int BT>
+struct TileCfg {
+  static constexpr int LDB = BT + 4;  // (BT+4)/4 odd for BT % 8 == 0
+};
+
+struct ChainSmem {
+  float* th;    // [S]   padded parameters
+  float* g;     // [S]   padded gradient
+  float* act;   // activation buffers of one batch tile
+  float* ys;    // [BT]  targets of the tile
+  int* idx;     // [BT]  observation indices of the tile (-1 = masked)
+  float* red;   // [32*4] reduction scratch
+  double* dacc; // [4]   double accumulators (thread 0)
+};
+
+template <int BT>
+__host__ __device__ inline size_t chain_smem_bytes(const ModelDev& M) {
+  size_t f = (size_t)2 * M.S + M.act_total + BT /*ys*/ + BT /*idx*/ + 32 * 4 /*red*/;
+  return f * 4 + 4 * sizeof(double) + 16;
+}
+
+template <int BT>
+BFX_DEV ChainSmem carve_smem(const ModelDev& M, unsigned char* base) {
+  ChainSmem s;
+  double* d = reinterpret_cast<double*>(base);
+  s.dacc = d;
+  float* f = reinterpret_cast<float*>(d + 4);
+  s.th = f; f += M.S;
+  s.g = f; f += M.S;
+  s.act = f; f += M.act_total;
+  s.ys = f; f += BT;
+  s.idx = reinterpret_cast<int*>(f); f += BT;
+  s.red = f;
+  return s;
+}
+
+// where a chain's minibatch comes from
+struct BatchSrc {
+  const long long* idx;  // explicit indices (B per chain) or nullptr
+  long long n;           // data set size
+  long long first;       // explicit==nullptr: position of the first element inside the epoch permutation
+  unsigned k0, k1;       // permutation key of this (chain, epoch)
+  int shuffle;           // 0: identity permutation
+  int full;              // 1: batch = [0, n) in order (full-data evaluations)
+};
+
+BFX_DEV long long batch_obs(const BatchSrc& b, long long j) {
+  if (b.full) return j;
+  if (b.idx) return b.idx[j];
+  long long pos = b.first + j;
+  return b.shuffle ? (long long)perm_index((unsigned long long)pos, (unsigned long long)b.n, b.k0, b.k1) : pos;
+}
+
+// ---------------------------------------------------------------------------------
+// network pass over one batch tile (MLP).  On return (want_grad) the gradient of
+//   sum_b dl[b] * yhat[b]   has been ACCUMULATED into s.g.  Returns per-thread partial
+//   likelihood sums in `sums` (to be block-reduced by the caller).
+// Likelihood arithmetic: src/likelihoods/feedforward.jl:30-43 (Normal), :86-97 (TDist);
+// closed-form deltas: SURVEY.md section 8 rows a8/a9.
+// ---------------------------------------------------------------------------------
+struct LikeCoef {
+  float inv_sigma;
+  float nb;  // num_batches (scales the delta; src/model/BNN.jl:55)
+};
+
+template <int NT, int BT>
+BFX_DEV void mlp_tile(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
+                      const float* __restrict__ y, const BatchSrc& bs, long long tile0, int nvalid,
+                      const LikeCoef& lc, bool want_grad, float (&sums)[2]) {
+  constexpr int LDB = TileCfg<BT>::LDB;
+  const int d = M.d_in;
+  // ---- stage the tile: indices, targets, transposed inputs ------------------
+  for (int b = threadIdx.x; b < BT; b += NT) {
+    long long o = (b < nvalid) ? batch_obs(bs, tile0 + b) : -1;
+    s.idx[b] = (int)o;
+    s.ys[b] = (o >= 0) ? __ldg(y + o) : 0.f;
+  }
+  __syncthreads();
+  {
+    float* X = s.act + M.act_off[0];
+    const int dpad = M.act_rows[0];
+    for (int e = threadIdx.x; e < dpad * BT; e += NT) {
+      int b = e / dpad, f = e - b * dpad;
+      int o = s.idx[b];
+      X[f * LDB + b] = (o >= 0 && f < d) ? __ldg(x + (long long)o * d + f) : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- forward ----------------------------------------------------------------
+  for (int l = 0; l < M.nlayers; ++l) {
+    const LayerDev& L = M.L[l];
+    gemm_fwd<NT, BT>(s.th + L.w_s, L.ldw, s.act + M.act_off[l], LDB, s.th + L.b_s, s.act + M.act_off[l + 1], LDB,
+                     L.nout_pad, L.nin, L.act);
+    __syncthreads();
+  }
+  // ---- likelihood epilogue ------------------------------------------------------
+  float* out = s.act + M.act_off[M.nlayers];
+  const int out_act = M.L[M.nlayers - 1].act;
+  for (int b = threadIdx.x; b < BT; b += NT) {
+    float dl = 0.f;
+    if (b < nvalid) {
+      float yh = out[b];
+      float z = (s.ys[b] - yh) * lc.inv_sigma;
+      if (M.like_kind == LK_NORMAL) {
+        sums[0] += z * z;
+        dl = lc.nb * z * lc.inv_sigma;
+      } else {
+        float zz = z * z;
+        float w = (M.nu + 1.f) * z / (M.nu + zz);
+        sums[0] += log1pf(zz / M.nu);
+        sums[1] += w * z;
+        dl = lc.nb * w * lc.inv_sigma;
+      }
+      dl *= act_deriv_from_out(out_act, yh);
+    }
+    if (want_grad) {
+      out[b] = dl;
+      out[LDB + b] = 0.f;
+      out[2 * LDB + b] = 0.f;
+      out[3 * LDB + b] = 0.f;
+    }
+  }
+  if (!want_grad) return;
+  __syncthreads();
+  // ---- backward -------------------------------------------------------------------
+  for (int l = M.nlayers - 1; l >= 0; --l) {
+    const LayerDev& L = M.L[l];
+    const float* D = s.act + M.act_off[l + 1];
+    float* A = s.act + M.act_off[l];
+    gemm_dw<NT, BT>(D, LDB, A, LDB, s.g + L.w_s, L.ldw, L.nout_pad, L.nin_pad);
+    rowsum_acc<NT, BT>(D, LDB, s.g + L.b_s, L.nout);
+    if (l > 0) {
+      __syncthreads();
+      gemm_dx<NT, BT>(s.th + L.w_s, L.ldw, D, LDB, A, LDB, L.nin_pad, L.nout_pad, M.L[l - 1].act);
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace bfx

@@ -1,0 +1,22 @@
+// Host-side declarations of the kernel launchers (implemented in bfx_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bfx_common.cuh"
+
+namespace bfx {
+
+struct LaunchCfg {
+  int nt;  // threads per CTA: 32 | 128 | 256
+  int bt;  // batch tile: 32 | 64
+};
+
+size_t smallp_smem_bytes(const ModelDev& M, int bt);
+cudaError_t launch_eval(const EvalDev& E, const LaunchCfg& cfg, cudaStream_t st);
+cudaError_t launch_mcmc(const RunDev& R, const LaunchCfg& cfg, cudaStream_t st);
+cudaError_t launch_debug_batch(const RunDev& R, int c, unsigned long long gstep, long long* out, long long* Bout,
+                               cudaStream_t st);
+cudaError_t launch_debug_noise(unsigned long long seed, unsigned chain, unsigned long long gstep, unsigned slot, int P,
+                               float* normals, float* uni, cudaStream_t st);
+
+}  // namespace bfx

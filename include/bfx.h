@@ -1,0 +1,248 @@
+/*
+ * bfx.h  --  C ABI of libbfx, the B200-native engine for the BayesFlux hot path.
+ *
+ * The reference (enweg/BayesFlux.jl v0.2.4) has no FFI of its own: its seams
+ * are the Julia generic functions cited beside every entry point below.  A
+ * Julia shim (julia/BayesFluxB200.jl) translates the
+ * reference's objects into these plain-C descriptors and `ccall`s the entry
+ * points; the Python host mirror (bayesflux.jl_b200/) binds the very same
+ * symbols through ctypes.
+ *
+ * Conventions
+ *   - every function returns an int32 status (BFX_OK == 0); the message of the
+ *     last failure on the calling thread is available via bfx_last_error().
+ *     Nothing aborts, nothing throws across the boundary.
+ *   - all host buffers are owned by the caller; the library copies in/out and
+ *     keeps no host pointer after returning.
+ *   - Float32 everywhere, `double` only for returned log-density values.
+ *   - Julia column-major: theta is P x C (one chain per column), samples are
+ *     P x nkept x C, feed-forward x is d x n, sequence x is T x d x n.
+ *   - indices are 0-based on this side of the boundary.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     returns BFX_ERR_CUDA.
+ *
+ * All file:line citations are relative to the reference tree.
+ */
+#ifndef BFX_H
+#define BFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFX_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+  BFX_OK = 0,
+  BFX_ERR_BAD_ARG = 1,
+  BFX_ERR_UNSUPPORTED = 2, /* e.g. FullCovMassAdapter, nets beyond the smem regime */
+  BFX_ERR_CUDA = 3,
+  BFX_ERR_NAN_G = 4,     /* error("NaN in g")  src/inference/mcmc/sgnht.jl:70-72   */
+  BFX_ERR_NAN_THETA = 5, /* error("NaN in θ")  src/inference/mcmc/sgnht.jl:81-83, ggmc.jl:160-162 */
+  BFX_ERR_NO_DATA = 6,
+  BFX_ERR_STATE = 7
+};
+
+/* ---- model description ------------------------------------------------- */
+/* layer kinds: src/layers/dense.jl:13-26, src/layers/recurrent.jl:13-34,41-68 */
+enum { BFX_DENSE = 0, BFX_RNN = 1, BFX_LSTM = 2 };
+/* activations kept from the template layer (dense.jl:14,23) */
+enum { BFX_IDENTITY = 0, BFX_RELU = 1, BFX_TANH = 2, BFX_SIGMOID = 3 };
+
+typedef struct bfx_layer_desc {
+  int32_t kind; /* BFX_DENSE | BFX_RNN | BFX_LSTM */
+  int32_t in;
+  int32_t out;
+  int32_t act; /* Dense: activation; RNN: cell activation; LSTM: ignored */
+} bfx_layer_desc;
+
+/* likelihoods: FeedforwardNormal / SeqToOneNormal (feedforward.jl:21-43,
+ * seq_to_one.jl:22-44) and FeedforwardTDist / SeqToOneTDist (feedforward.jl:76-97,
+ * seq_to_one.jl:79-100).  Feed-forward vs seq-to-one follows the rank of x. */
+enum { BFX_LIKE_NORMAL = 0, BFX_LIKE_TDIST = 1 };
+/* prior on sigma, mapped through the log link (sigma = exp(theta_like)) */
+enum { BFX_SIGMA_GAMMA = 0 /* Gamma(shape a, scale b) */, BFX_SIGMA_INVGAMMA = 1 /* InverseGamma(shape a, scale b) */ };
+
+typedef struct bfx_like_desc {
+  int32_t kind;
+  int32_t sigma_prior_kind;
+  double nu; /* TDist degrees of freedom (fixed) */
+  double sigma_prior_a;
+  double sigma_prior_b;
+} bfx_like_desc;
+
+/* network priors: GaussianPrior (netpriors/gaussian.jl:6-28),
+ * MixtureScalePrior (netpriors/mixturescale.jl:18-33, ctor order sigma1, sigma2, pi1) */
+enum { BFX_PRIOR_GAUSSIAN = 0, BFX_PRIOR_MIXTURE = 1 };
+
+typedef struct bfx_prior_desc {
+  int32_t kind;
+  int32_t _pad;
+  double sigma0;
+  double sigma1;
+  double sigma2;
+  double pi1;
+} bfx_prior_desc;
+
+typedef struct bfx_model bfx_model;     /* opaque: BNN (src/model/BNN.jl:5-38) on one device */
+typedef struct bfx_sampler bfx_sampler; /* opaque: MCMCState for nchains chains            */
+
+/* ---- samplers ---------------------------------------------------------- */
+enum { BFX_SGLD = 0, BFX_SGNHT = 1, BFX_SGNHTS = 2, BFX_GGMC = 3, BFX_HMC = 4 };
+enum { BFX_STEP_CONSTANT = 0, BFX_STEP_DUAL_AVERAGING = 1 };
+enum { BFX_MASS_FIXED = 0, BFX_MASS_DIAGCOV = 1, BFX_MASS_RMSPROP = 2, BFX_MASS_FULLCOV = 3 /* rejected */ };
+
+/* One struct carries the keyword sets of all five constructors:
+ *   SGLD   sgld.jl:47-54      stepsize_a, stepsize_b, stepsize_gamma, min_stepsize, maxnorm
+ *   SGNHT  sgnht.jl:32        l, A, xi
+ *   SGNHTS sgnht-s.jl:41-47   l, sigmaA, xi, mu, madapter
+ *   GGMC   ggmc.jl:59-67      beta, l, steps, maxnorm, sadapter, madapter
+ *   HMC    hmc.jl:59-65       l, path_len, maxnorm, sadapter, madapter
+ *   DualAveragingStepSize dualaveragestepsize.jl:25-32; DiagCovMassAdapter
+ *   diagcovariancemassadapter.jl:23-33; RMSPropMassAdapter rmspropmassadapter.jl:17-24 */
+typedef struct bfx_sampler_desc {
+  int32_t kind;
+  int32_t steps;    /* GGMC delayed-acceptance window */
+  int32_t path_len; /* HMC leapfrog stages */
+  int32_t sadapter_kind;
+  int32_t madapter_kind;
+  int32_t da_t0;
+  int32_t da_adapt_steps;
+  int32_t ma_adapt_steps;
+  int32_t ma_windowlength;
+  int32_t _pad;
+  float stepsize_a, stepsize_b, stepsize_gamma, min_stepsize;
+  float maxnorm;
+  float l;
+  float A;      /* SGNHT diffusion */
+  float sigmaA; /* SGNHTS diffusion */
+  float xi;     /* initial thermostat */
+  float mu;
+  float beta;
+  float da_target_accept, da_gamma, da_kappa;
+  float ma_kappa, ma_epsilon; /* DiagCov */
+  float ma_lambda, ma_alpha;  /* RMSProp */
+} bfx_sampler_desc;
+
+/* state fields for bfx_sampler_get_state / set_state (checkpoint / resume,
+ * mirrors the mutable fields of the reference structs) */
+enum {
+  BFX_STATE_THETA = 0,    /* float  P x C */
+  BFX_STATE_MOMENTUM = 1, /* float  P x C   (p / momentum) */
+  BFX_STATE_MINV = 2,     /* float  P x C   diagonal of the inverse mass matrix */
+  BFX_STATE_XI = 3,       /* float  C       thermostat */
+  BFX_STATE_STEPSIZE = 4, /* float  C       l */
+  BFX_STATE_T = 5,        /* int64  C       step counter t (1-based like the reference) */
+  BFX_STATE_NSAMPLED = 6, /* int64  C */
+  BFX_STATE_STATUS = 7    /* int32  C       BFX_OK | BFX_ERR_NAN_G | BFX_ERR_NAN_THETA */
+};
+
+enum { BFX_BATCH_PER_CHAIN = 0, BFX_BATCH_SHARED = 1 };
+
+/* mcmc(bnn, batchsize, numsamples, sampler; shuffle, partial, continue_sampling, θstart)
+ * src/inference/mcmc/abstract.jl:74-127, plus the engine's extensions (nchains is
+ * fixed by the sampler handle; keep_every, seed, batch_mode). */
+typedef struct bfx_run_desc {
+  int64_t batchsize;
+  int64_t numsamples;        /* total target, as in the reference */
+  int32_t shuffle;           /* default 1 */
+  int32_t partial;           /* default 1 */
+  int32_t continue_sampling; /* 1: draw numsamples - nsampled more, starting from the state */
+  int32_t keep_every;        /* record sample t (1-based) iff t % keep_every == 0; default 1 */
+  int32_t batch_mode;        /* BFX_BATCH_PER_CHAIN (reference semantics) | BFX_BATCH_SHARED */
+  int32_t _pad;
+  uint64_t seed;        /* Philox key */
+  int64_t chain_offset; /* global id of this handle's chain 0: chains sharded over several GPUs / ranks
+                           keep distinct noise and batch streams (chain c uses stream chain_offset + c) */
+} bfx_run_desc;
+
+/* ---- library ----------------------------------------------------------- */
+int32_t bfx_version(void);
+/* copies the calling thread's last error message (NUL-terminated) into buf */
+int32_t bfx_last_error(char* buf, size_t n);
+int32_t bfx_device_count(int32_t* count);
+
+/* ---- model: destruct(::Chain) + likelihood + prior + BNN ---------------- *
+ * replaces  destruct  src/model/deconstruct.jl:45-58,  BNN(...)  src/model/BNN.jl:32-38 */
+int32_t bfx_model_create(const bfx_layer_desc* layers, int32_t nlayers, const bfx_like_desc* like,
+                         const bfx_prior_desc* prior, int32_t device, bfx_model** out);
+int32_t bfx_model_destroy(bfx_model* m);
+/* num_total_params (BNN.jl:36) and like.nc.num_params_network */
+int32_t bfx_model_num_params(const bfx_model* m, int64_t* p_total, int64_t* p_net);
+/* 0-based [start,end) of layer i in theta_net  (NetConstructor.starts/ends, deconstruct.jl:24-25) */
+int32_t bfx_model_layer_bounds(const bfx_model* m, int32_t layer, int64_t* start, int64_t* end);
+/* bnn.x / bnn.y: one H2D copy, Julia column-major as is.  ndims 2: dims = {d, n};
+ * ndims 3: dims = {T, d, n}  (make_rnn_tensor layout, src/utils/rnn_utils.jl:11-21) */
+int32_t bfx_model_set_data(bfx_model* m, const float* x, const int64_t* dims, int32_t ndims, const float* y,
+                           int64_t n);
+/* same, but x and y are DEVICE pointers on the model's device (copied device-to-device) */
+int32_t bfx_model_set_data_device(bfx_model* m, const float* x_dev, const int64_t* dims, int32_t ndims,
+                                  const float* y_dev, int64_t n);
+
+/* ---- log posterior and its gradient (parity entries) -------------------- *
+ * loglikeprior(bnn, θ, x, y; num_batches)   src/model/BNN.jl:50-56
+ * ∇loglikeprior(bnn, θ, x, y; num_batches)  src/model/BNN.jl:61-69
+ * theta: P x C host floats.  idx == NULL: the full data set; otherwise B
+ * observation indices (0-based) per chain, chain c reading idx + c*idx_chain_stride
+ * (stride 0 = one batch shared by all chains).  v_out: C doubles. g_out: P x C. */
+int32_t bfx_loglikeprior(bfx_model* m, const float* theta, int32_t nchains, const int64_t* idx, int64_t B,
+                         int64_t idx_chain_stride, float num_batches, double* v_out);
+int32_t bfx_grad_loglikeprior(bfx_model* m, const float* theta, int32_t nchains, const int64_t* idx, int64_t B,
+                              int64_t idx_chain_stride, float num_batches, double* v_out, float* g_out);
+
+/* ---- samplers ----------------------------------------------------------- *
+ * SGLD/SGNHT/SGNHTS/GGMC/HMC constructors + initialise!  (sgld.jl:47-88 etc.) for
+ * nchains independent chains living on the model's device. */
+int32_t bfx_sampler_create(const bfx_sampler_desc* desc, bfx_model* m, int32_t nchains, bfx_sampler** out);
+int32_t bfx_sampler_destroy(bfx_sampler* s);
+/* initialise!(sampler, θ, numsamples; continue_sampling=false): zero momentum, reset
+ * counters/adapters, theta_start P x C host floats. */
+int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start);
+int32_t bfx_sampler_get_state(bfx_sampler* s, int32_t field, void* out, int64_t nbytes);
+int32_t bfx_sampler_set_state(bfx_sampler* s, int32_t field, const void* in, int64_t nbytes);
+
+/* update!(sampler, θ, bnn, ∇θ) with every random draw supplied by the caller
+ * (sgld.jl:96-112, sgnht.jl:64-90, sgnht-s.jl:81-116, ggmc.jl:140-198, hmc.jl:113-159).
+ * One call = one update! of every chain on the minibatch idx (layout as above).
+ * normals: ndraws x P x C floats (SGLD/SGNHT/SGNHTS/HMC: 1 draw, GGMC: 2);
+ * uniforms: C floats (GGMC/HMC accept test) or NULL.  theta_out (P x C) may be NULL. */
+int32_t bfx_sampler_step_injected(bfx_sampler* s, const int64_t* idx, int64_t B, int64_t idx_chain_stride,
+                                  float num_batches, const float* normals, const float* uniforms,
+                                  float* theta_out);
+
+/* the whole mcmc loop on the device (abstract.jl:102-126).
+ * theta_start: P x C or NULL with continue_sampling.  samples_out: P x nkept x C where
+ * nkept = number of NEW recorded samples (bfx_mcmc_num_kept); may be NULL (throughput
+ * runs that only want the final state).  kinetic_out: nnew x C (SGNHT/SGNHTS) or NULL;
+ * accepted_out: nnew x C int32 (GGMC/HMC) or NULL.  Returns BFX_ERR_NAN_* if any chain
+ * hit a NaN guard (per-chain codes via BFX_STATE_STATUS); other chains keep going. */
+int32_t bfx_mcmc_num_kept(const bfx_sampler* s, const bfx_run_desc* run, int64_t* nnew, int64_t* nkept);
+int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta_start, float* samples_out,
+                     float* kinetic_out, int32_t* accepted_out);
+/* progress poll from another host thread (ProgressMeter replacement, abstract.jl:122) */
+int32_t bfx_progress(const bfx_sampler* s, int64_t* nsampled);
+
+/* device-resident variant used by throughput benchmarks: runs nsteps update! calls for all
+ * chains without touching host memory (state stays on the device, nothing is recorded).
+ * Asynchronous: returns after enqueueing.  stream_handle: a cudaStream_t or 0 (own stream). */
+int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, void* stream_handle);
+/* number of kernel launches issued by this sampler handle so far */
+int32_t bfx_sampler_launch_count(const bfx_sampler* s, int64_t* n);
+
+/* ---- test hooks: expose the engine's own random streams so the oracle can
+ * replay a device run draw for draw -------------------------------------- */
+/* the minibatch (indices into the data set) chain `chain` uses at global step `step` */
+int32_t bfx_debug_batch_indices(const bfx_sampler* s, const bfx_run_desc* run, int64_t chain, int64_t step,
+                                int64_t* idx_out, int64_t* B_out);
+/* the P standard normals of draw slot `slot` and the uniform used at global step `step` */
+int32_t bfx_debug_noise(const bfx_sampler* s, const bfx_run_desc* run, int64_t chain, int64_t step, int32_t slot,
+                        float* normals_out, float* uniform_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFX_H */
