@@ -12,4 +12,5 @@ from .api import (BNN, Chain, Dense, LSTM, RNN, NetConstructor, destruct, Gamma,
                   MixtureScalePrior, InitialiseAllSame, split_params, loglikeprior, grad_loglikeprior,
                   ConstantStepsize, DualAveragingStepSize, FixedMassAdapter, DiagCovMassAdapter,
                   RMSPropMassAdapter, FullCovMassAdapter, MCMCState, SGLD, SGNHT, SGNHTS, GGMC, HMC, mcmc,
+                  advance, launch_count,
                   identity, relu, tanh, sigmoid)

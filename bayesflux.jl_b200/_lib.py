@@ -80,7 +80,7 @@ SYMBOLS = {
     "bfx_mcmc_num_kept": [_vp, C.POINTER(RunDesc), _pi64, _pi64],
     "bfx_mcmc_run": [_vp, C.POINTER(RunDesc), _vp, _vp, _vp, _vp],
     "bfx_progress": [_vp, _pi64],
-    "bfx_mcmc_advance": [_vp, C.POINTER(RunDesc), _i64, _vp],
+    "bfx_mcmc_advance": [_vp, C.POINTER(RunDesc), _i64, _vp, _vp, _i64],
     "bfx_sampler_launch_count": [_vp, _pi64],
     "bfx_debug_batch_indices": [_vp, C.POINTER(RunDesc), _i64, _i64, _vp, _pi64],
     "bfx_debug_noise": [_vp, C.POINTER(RunDesc), _i64, _i64, _i32, _vp, _vp],

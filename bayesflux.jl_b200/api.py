@@ -626,3 +626,22 @@ def mcmc(bnn: BNN, batchsize: int, numsamples: int, sampler: MCMCState, shuffle=
     sampler.samples = sampler._samples3[:, :, 0] if nchains == 1 else sampler._samples3
     L.check(code)  # raises "NaN in g" / "NaN in θ" like the reference (sgnht.jl:70-72,81-83)
     return sampler.samples
+
+
+def advance(sampler: MCMCState, batchsize: int, nsteps: int, shuffle=True, partial=True, keep_every: int = 1,
+            seed: int = 0, batch_mode: str = "per_chain", chain_offset: int = 0, stream: int = 0,
+            samples_dev: int = 0, ring_slots: int = 0):
+    """Device-resident continuation of ``mcmc``: enqueue ``nsteps`` update! calls for every chain of an
+    initialised sampler (``sampler.initialise(bnn, theta)``) on ``stream`` (a raw cudaStream_t, 0 = the
+    engine's own stream) and return immediately.  Recorded samples (every ``keep_every``-th) are written
+    to the caller's device ring ``samples_dev`` ([C][ring_slots][P] floats) when given.  Same loop body as
+    mcmc (src/inference/mcmc/abstract.jl:117-124); nothing crosses PCIe."""
+    run = _run_desc(batchsize, 0, shuffle, partial, True, keep_every, seed, batch_mode, chain_offset)
+    L.check(L.lib.bfx_mcmc_advance(sampler._h, C.byref(run), int(nsteps), C.c_void_p(stream),
+                                   C.c_void_p(samples_dev), int(ring_slots)))
+
+
+def launch_count(sampler: MCMCState) -> int:
+    n = C.c_int64()
+    L.check(L.lib.bfx_sampler_launch_count(sampler._h, C.byref(n)))
+    return n.value

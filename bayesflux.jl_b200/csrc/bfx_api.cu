@@ -886,7 +886,8 @@ int32_t bfx_progress(const bfx_sampler* s, int64_t* nsampled) {
   return BFX_OK;
 }
 
-int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, void* stream_handle) {
+int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, void* stream_handle,
+                         float* samples_dev, int64_t ring_slots) {
   if (!s || !run) return fail(BFX_ERR_BAD_ARG, "NULL argument");
   if (!s->initialised) return fail(BFX_ERR_STATE, "sampler not initialised");
   if (nsteps <= 0) return BFX_OK;
@@ -897,6 +898,14 @@ int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps
   st = prepare_schedule(s, run, R);
   if (st) return st;
   cudaStream_t stream = stream_handle ? (cudaStream_t)stream_handle : m->stream;
+  if (samples_dev) {
+    if (ring_slots < (s->S.kind == S_GGMC ? s->S.steps : 1))
+      return fail(BFX_ERR_BAD_ARG, "ring_slots must be >= 1 (>= steps for GGMC)");
+    R.samples = samples_dev;
+    R.samples_chain_stride = ring_slots * (int64_t)m->M.P;
+    R.kept_origin = 0;
+    R.ring_slots = ring_slots;
+  }
   int64_t done = 0;
   while (done < nsteps) {
     const int64_t cs = std::min<int64_t>(nsteps - done, 1 << 16);

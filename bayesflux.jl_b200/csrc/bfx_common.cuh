@@ -133,6 +133,7 @@ struct RunDev {
   float* samples;            // [C][slots][P] or nullptr
   long long samples_chain_stride;
   long long kept_origin;     // number of kept samples that precede slot 0
+  long long ring_slots;      // > 0: the sample buffer is a ring of this many slots per chain
   int keep_every;
   float* kinetic_out;        // [C][hist_stride]
   int* accepted_out;         // [C][hist_stride]

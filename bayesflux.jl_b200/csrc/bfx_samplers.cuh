@@ -58,6 +58,7 @@ BFX_DEV void record_sample(Ctx<NT, BT>& X, long long ns, const float* src_global
   float* dst = nullptr;
   if (R.samples && (ns % R.keep_every) == 0) {
     long long slot = ns / R.keep_every - 1 - R.kept_origin;
+    if (R.ring_slots > 0) slot %= R.ring_slots;
     dst = R.samples + (long long)X.c * R.samples_chain_stride + slot * R.M.P;
   }
   float* rdst = nullptr;

@@ -226,10 +226,14 @@ int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta
 /* progress poll from another host thread (ProgressMeter replacement, abstract.jl:122) */
 int32_t bfx_progress(const bfx_sampler* s, int64_t* nsampled);
 
-/* device-resident variant used by throughput benchmarks: runs nsteps update! calls for all
- * chains without touching host memory (state stays on the device, nothing is recorded).
+/* device-resident variant (throughput runs, pipelines that consume the samples on the
+ * device): runs nsteps update! calls for all chains without touching host memory.  The state
+ * stays on the device; recorded samples (run->keep_every) go to the caller's DEVICE ring
+ * samples_dev laid out [C][ring_slots][P] (kept sample k of a chain lands in slot
+ * k % ring_slots), or nowhere when samples_dev is NULL.
  * Asynchronous: returns after enqueueing.  stream_handle: a cudaStream_t or 0 (own stream). */
-int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, void* stream_handle);
+int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, void* stream_handle,
+                         float* samples_dev, int64_t ring_slots);
 /* number of kernel launches issued by this sampler handle so far */
 int32_t bfx_sampler_launch_count(const bfx_sampler* s, int64_t* n);
 
