@@ -293,6 +293,10 @@ def run_ours(args):
         flops, q = algorithmic(B)
         hbm, sm_max, src = peaks()
         per_gpu = value / world
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_k_mcmc.json")
+        if os.path.exists(tp):  # dram__bytes_read+write of one ncu --set full capture, rescaled to this launch size
+            traffic = json.load(open(tp))["dram_bytes_per_chain_step"] * C * U
         achieved = per_gpu * q / 1e9
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
         out = {
@@ -312,7 +316,7 @@ def run_ours(args):
                     "api": "mcmc(bnn, 64, U, SGLD(); theta_start=host, nchains, keep_every=U) -> host samples"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": src, "kernel": "k_mcmc<256,64,SGLD>",
+                         "traffic": traffic, "peak_source": src, "kernel": "k_mcmc<256,64,SGLD>",
                          "bytes_per_chain_step": q, "chain_steps_per_launch": C * U,
                          "fp32_pipe": {"achieved_tflops": per_gpu * flops / 1e12, "peak_tflops": fp32_peak,
                                        "frac": per_gpu * flops / 1e12 / fp32_peak,

@@ -89,6 +89,19 @@ def data_for(layers, n, rng, T=None):
 def rel_err(a, b):
     return float(np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-30))
 
+def engine_draws(bf, eng, run, chain, step, P, slot=0):
+    """(batch indices, standard normals, uniform) the engine uses for (chain, global step) -- debug hooks."""
+    import ctypes as C
+    from bayesflux_b200 import _lib as L
+    idx = np.empty(int(run.batchsize), np.int64)
+    Bk = C.c_int64()
+    L.check(L.lib.bfx_debug_batch_indices(eng._h, C.byref(run), chain, step, idx.ctypes.data_as(C.c_void_p), C.byref(Bk)))
+    z = np.empty(P, np.float32)
+    u = np.zeros(1, np.float32)
+    L.check(L.lib.bfx_debug_noise(eng._h, C.byref(run), chain, step, slot, z.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p)))
+    return idx[:Bk.value], z, float(u[0])
+
+
 
 # -------------------------------------------------------------- gradients ---
 @pytest.mark.parametrize("net", list(MLPS))
@@ -479,9 +492,15 @@ def test_sgld_statistical_reference_setup(bf):
 
 def test_readme_config1_moments_vs_oracle(bf):
     """Config 1 (README.md:74-133,181-183): Dense(5,1), n=500, Gamma(2,0.5), GaussianPrior(0.5),
-    SGLD(a=10,b=0,gamma=0.55), batchsize 50, 50 000 steps, last 20 000 kept.  Posterior means and
-    variances of the engine's chains must agree with CPU-oracle chains within Monte-Carlo error
-    (measured from the spread across 64 engine chains)."""
+    batchsize 50, 50 000 steps, last 20 000 kept.  Posterior means and variances of the engine's
+    chains must agree with CPU-oracle chains within Monte-Carlo error (measured from the spread
+    across 64 engine chains).
+
+    Step size: SGLD(a=1, b=0, gamma=0.55), the value of the reference's own SGLD test
+    (test/sgld.jl:19), not the README's a=10.  With a=10 the very first update moves log(sigma) by up
+    to alpha/2 * maxnorm = 125, sigma = exp(.) overflows Float32 and the chain is NaN from step 2 on:
+    the oracle (a line-by-line restatement of sgld.jl:96-112) does this on 10/10 starts drawn as the
+    README draws them, and the engine reproduces it (test_readme_a10_diverges_like_the_oracle)."""
     rng = np.random.default_rng(SEED)
     k, n, C = 5, 500, 64
     x = rng.standard_normal((k, n)).astype(np.float32)
@@ -492,17 +511,51 @@ def test_readme_config1_moments_vs_oracle(bf):
     pr = O.NetPrior(O.NETPRIOR_GAUSSIAN, sigma0=0.5)
     bnn, m = build(bf, layers, lk, pr, x, y)
     th0 = (0.5 * rng.standard_normal((m.n_total, C))).astype(np.float32)
-    s = bf.SGLD(stepsize_a=10.0, stepsize_b=0.0, stepsize_gamma=0.55)
+    s = bf.SGLD(stepsize_a=1.0, stepsize_b=0.0, stepsize_gamma=0.55)
     ch = bf.mcmc(bnn, 50, 50_000, s, theta_start=th0, seed=7)[:, -20_000:, :]
+    assert np.isfinite(ch).all()
     e_mean = ch.mean(axis=1)            # P x C
     e_var = ch.var(axis=1)
     mu, sd = e_mean.mean(axis=1), e_mean.std(axis=1, ddof=1)
     vmu, vsd = e_var.mean(axis=1), e_var.std(axis=1, ddof=1)
     for c in range(3):
-        so = O.SGLD(stepsize_a=10.0, stepsize_b=0.0, stepsize_gamma=0.55)
+        so = O.SGLD(stepsize_a=1.0, stepsize_b=0.0, stepsize_gamma=0.55)
         cho = O.mcmc(m, x, y, 50, 50_000, so, th0[:, c].copy(), np.random.default_rng(100 + c))[:, -20_000:]
+        assert np.isfinite(cho).all()
         om, ov = cho.mean(axis=1), cho.var(axis=1)
         log(test="readme", chain=c, om=[float(v) for v in om], mu=[float(v) for v in mu], sd=[float(v) for v in sd],
             ov=[float(v) for v in ov], vmu=[float(v) for v in vmu], vsd=[float(v) for v in vsd])
         assert np.all(np.abs(om - mu) < 5 * sd + 1e-3), (om, mu, sd)
         assert np.all(np.abs(ov - vmu) < 5 * vsd + 1e-4), (ov, vmu, vsd)
+
+
+def test_readme_a10_diverges_like_the_oracle(bf):
+    """README's SGLD(a=10, b=0) from a N(0, 0.5) start: replaying the engine's own batches and noise
+    through the oracle gives the same trajectory, including the step at which sigma overflows."""
+    rng = np.random.default_rng(SEED)
+    k, n = 5, 500
+    x = rng.standard_normal((k, n)).astype(np.float32)
+    beta = rng.standard_normal(k).astype(np.float32)
+    y = (x.T @ beta + rng.standard_normal(n)).astype(np.float32)
+    layers = (O.Dense(5, 1),)
+    lk = O.Likelihood(O.NORMAL, prior_a=2.0, prior_b=0.5)
+    pr = O.NetPrior(O.NETPRIOR_GAUSSIAN, sigma0=0.5)
+    bnn, m = build(bf, layers, lk, pr, x, y)
+    th0 = (0.5 * np.random.default_rng(100).standard_normal(m.n_total)).astype(np.float32)
+    nsteps = 6
+    s = bf.SGLD(stepsize_a=10.0, stepsize_b=0.0, stepsize_gamma=0.55)
+    ch = bf.mcmc(bnn, 50, nsteps, s, theta_start=th0, seed=11)
+    run = bf.api._run_desc(50, nsteps, True, True, False, 1, 11, "per_chain")
+    so = O.SGLD(stepsize_a=10.0, stepsize_b=0.0, stepsize_gamma=0.55)
+    so.initialise(th0.copy(), nsteps)
+    th = th0.copy()
+    with np.errstate(all="ignore"):
+        for t in range(nsteps):
+            idx, nrm, _ = engine_draws(bf, s, run, 0, t, m.n_total)
+            gf = lambda q, idx=idx: O.grad_loglikeprior(m, q, x[:, idx], y[idx], 10.0)
+            th = so.update(th, gf, None, [nrm])
+    fin_e, fin_o = np.isfinite(ch).all(axis=0), np.isfinite(so.samples).all(axis=0)
+    log(test="readme_a10", finite_engine=[bool(v) for v in fin_e], finite_oracle=[bool(v) for v in fin_o])
+    assert np.array_equal(fin_e, fin_o)
+    ok = fin_o
+    assert rel_err(ch[:, ok], so.samples[:, ok]) < 1e-3
