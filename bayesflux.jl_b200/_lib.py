@@ -19,6 +19,7 @@ MASS_FIXED, MASS_DIAGCOV, MASS_RMSPROP, MASS_FULLCOV = range(4)
 (STATE_THETA, STATE_MOMENTUM, STATE_MINV, STATE_XI, STATE_STEPSIZE, STATE_T, STATE_NSAMPLED,
  STATE_STATUS) = range(8)
 BATCH_PER_CHAIN, BATCH_SHARED = 0, 1
+COMPUTE_FP32, COMPUTE_TC_BF16X3 = 0, 1
 
 
 class LayerDesc(C.Structure):
@@ -69,6 +70,8 @@ SYMBOLS = {
     "bfx_model_layer_bounds": [_vp, _i32, _pi64, _pi64],
     "bfx_model_set_data": [_vp, _vp, _pi64, _i32, _vp, _i64],
     "bfx_model_set_data_device": [_vp, _vp, _pi64, _i32, _vp, _i64],
+    "bfx_model_set_compute": [_vp, _i32],
+    "bfx_model_get_compute": [_vp, _pi32],
     "bfx_loglikeprior": [_vp, _vp, _i32, _vp, _i64, _i64, _f32, _vp],
     "bfx_grad_loglikeprior": [_vp, _vp, _i32, _vp, _i64, _i64, _f32, _vp, _vp],
     "bfx_sampler_create": [C.POINTER(SamplerDesc), _vp, _i32, C.POINTER(_vp)],

@@ -232,7 +232,11 @@ def _ptr(a):
 class BNN:
     """BNN(x, y, like, prior, init)  src/model/BNN.jl:5-38.  Owns the device model handle."""
 
-    def __init__(self, x, y, like: BNNLikelihood, prior: NetworkPrior, init=None, device: int = 0):
+    def __init__(self, x, y, like: BNNLikelihood, prior: NetworkPrior, init=None, device: int = 0,
+                 compute: str = "fp32"):
+        """compute: "fp32" (CUDA-core FMA path, the correctness gate), "tc" (tcgen05 tensor cores with
+        the 3-term BF16 split; raises BfxError(ERR_UNSUPPORTED) for nets it does not cover) or "auto"
+        (tensor cores when the net is eligible, FP32 otherwise)."""
         self.like, self.prior, self.init = like, prior, init
         self.device = device
         nc = like.nc
@@ -245,6 +249,15 @@ class BNN:
         h = C.c_void_p()
         L.check(L.lib.bfx_model_create(layers, len(nc.layers), C.byref(ld), C.byref(pd), device, C.byref(h)))
         self._h = h
+        self.compute = "fp32"
+        if compute in ("tc", "auto"):
+            code = L.lib.bfx_model_set_compute(h, L.COMPUTE_TC_BF16X3)
+            if code == L.OK:
+                self.compute = "tc"
+            elif compute == "tc" or code != L.ERR_UNSUPPORTED:
+                L.check(code)
+        elif compute != "fp32":
+            raise ValueError("compute must be 'fp32', 'tc' or 'auto'")
         self.x = self.y = None
         if x is not None:
             self.set_data(x, y)

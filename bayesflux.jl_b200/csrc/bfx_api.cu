@@ -205,8 +205,79 @@ static int32_t build_model_dev(bfx_model* m, const bfx_like_desc* like, const bf
   return BFX_OK;
 }
 
+// tensor-core path: eligibility + tile / TMEM layout (bfx_tc.cuh)
+static int32_t build_tc(bfx_model* m) {
+  ModelDev& M = m->M;
+  TcDesc T{};
+  const int nl = M.nlayers;
+  if (nl < 2) return fail(BFX_ERR_UNSUPPORTED, "tensor-core path: needs at least one hidden layer");
+  for (int l = 0; l < nl; ++l)
+    if (M.L[l].kind != L_DENSE) return fail(BFX_ERR_UNSUPPORTED, "tensor-core path: Dense layers only");
+  if (M.L[0].nin > 64) return fail(BFX_ERR_UNSUPPORTED, "tensor-core path: input dimension must be <= 64");
+  for (int l = 0; l + 1 < nl; ++l)
+    if (M.L[l].nout % 16 != 0 || M.L[l].nout > 64)
+      return fail(BFX_ERR_UNSUPPORTED, "tensor-core path: hidden widths must be multiples of 16 and <= 64");
+  T.nh = nl - 1;
+  int off = 0, col = 64;  // TMEM columns [0,64): the Z / dA accumulator
+  for (int l = 0; l < T.nh; ++l) {
+    TcLayer& L = T.L[l];
+    L.kpad = (M.L[l].nin + 15) & ~15;
+    L.ccols = L.kpad + 8;
+    L.hout = M.L[l].nout;
+    L.a_bytes = 64 * L.ccols * 2;
+    L.w_bytes = L.kpad * L.hout * 2;
+    L.a_off = off;
+    off += 2 * L.a_bytes;
+    L.w_off = off;
+    off += 2 * L.w_bytes;
+    off = (off + 127) & ~127;
+    L.dw_col = col;
+    col += L.ccols;
+  }
+  T.d_bytes = 64 * 64 * 2;
+  T.d_off = off;
+  off += 2 * T.d_bytes;
+  T.misc_off = off;
+  off += 1024;
+  T.total_bytes = off;
+  int cols = 32;
+  while (cols < col) cols <<= 1;
+  if (cols > 512) return fail(BFX_ERR_UNSUPPORTED, "tensor-core path: accumulators exceed the 512 TMEM columns");
+  T.tmem_cols = cols;
+  T.enabled = 1;
+  TcDesc saved = M.tc;
+  M.tc = T;
+  M.tc.smem_pad = 0;
+  size_t need = smallp_smem_bytes(M, 64);
+  if (need > kMaxSmem) {
+    M.tc = saved;
+    return fail(BFX_ERR_UNSUPPORTED, "tensor-core path: working set exceeds 227 KB of shared memory");
+  }
+  // CTAs co-resident on an SM share 512 TMEM columns: never let more CTAs fit by shared memory than by TMEM
+  const int by_tmem = 512 / cols;
+  const size_t min_smem = (kMaxSmem + 1024) / (size_t)(by_tmem + 1) + 1;
+  if (need < min_smem && min_smem <= kMaxSmem) M.tc.smem_pad = (int)(min_smem - need);
+  return BFX_OK;
+}
+
 // ---------------------------------------------------------------------------------
 extern "C" {
+
+int32_t bfx_model_set_compute(bfx_model* m, int32_t mode) {
+  if (!m) return fail(BFX_ERR_BAD_ARG, "model is NULL");
+  if (mode == BFX_COMPUTE_FP32) {
+    m->M.tc = TcDesc{};
+    return BFX_OK;
+  }
+  if (mode == BFX_COMPUTE_TC_BF16X3) return build_tc(m);
+  return fail(BFX_ERR_BAD_ARG, "unknown compute mode");
+}
+
+int32_t bfx_model_get_compute(const bfx_model* m, int32_t* mode) {
+  if (!m || !mode) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  *mode = m->M.tc.enabled ? BFX_COMPUTE_TC_BF16X3 : BFX_COMPUTE_FP32;
+  return BFX_OK;
+}
 
 int32_t bfx_version(void) { return BFX_VERSION; }
 

@@ -9,6 +9,10 @@ namespace bfx {
 // value (and gradient into s.g) of  num_batches*loglike + logprior  on one minibatch.
 // src/model/BNN.jl:50-69.  Returns the value on every thread; gn2 = ||g||^2 over all P.
 // ---------------------------------------------------------------------------------
+template <int NT>
+BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, float nb, double ds0, double ds1,
+                           bool want_grad, float& gn2);
+
 template <int NT, int BT>
 BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
                           const float* __restrict__ y, const BatchSrc& bs, long long B, float nb, bool want_grad,
@@ -31,6 +35,16 @@ BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __
     ds1 += (double)sums[1];
     __syncthreads();
   }
+  return eval_finish<NT>(M, s, B, nb, ds0, ds1, want_grad, gn2);
+}
+
+// likelihood sums -> value; sigma prior; network prior; finishes the gradient in s.g (which on entry
+// holds the gradient of  sum_b dl[b]*yhat[b]  w.r.t. theta_net) and its squared norm.
+template <int NT>
+BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, float nb, double ds0, double ds1,
+                           bool want_grad, float& gn2) {
+  const float sl = s.th[M.like_s];
+  const float sigma = expf(sl);
   // reduce the likelihood sums in double
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -45,6 +45,30 @@ struct LayerDev {
   int w_s, wh_s, b_s;  // smem offsets: W (or Wi), Wh, bias
 };
 
+// ---- tensor-core (tcgen05) path: MLPs whose hidden widths are multiples of 16 and <= 64 ----
+// Hidden layer l = Dense(Hin -> Hout): its input activations (X for l = 0) live in a bf16 "core
+// block" tile of 64 batch rows x ccols columns (ccols = round16(Hin) + 8; column round16(Hin) is a
+// constant 1 so that the weight-gradient GEMM also yields the bias gradient), its weights in a tile
+// of kpad rows (fan-in) x hout columns.  Every tile exists twice (hi and lo halves of the 3-term
+// BF16 split).  Byte offsets are relative to the 128-byte aligned tensor-core region of the CTA.
+struct TcLayer {
+  int kpad, ccols, hout;
+  int a_off, a_bytes;  // input-activation tile (hi); lo at a_off + a_bytes
+  int w_off, w_bytes;  // weight tile (hi); lo at w_off + w_bytes
+  int dw_col;          // TMEM column of the dW accumulator (64 rows = fan-out, ccols columns)
+};
+
+struct TcDesc {
+  int enabled;
+  int nh;              // hidden layers on the tensor cores (= nlayers - 1; the 1-wide output layer runs in the epilogue)
+  int d_off, d_bytes;  // delta tile 64 x 64 (hi); lo at d_off + d_bytes
+  int misc_off;        // float yh[128], float glast[72], uint64 bar[4], uint32 tmem slot
+  int total_bytes;
+  int tmem_cols;       // allocation (power of two >= 32); the Z accumulator sits at column 0
+  int smem_pad;        // extra dynamic smem requested at launch so that co-resident CTAs never over-subscribe TMEM
+  TcLayer L[BFX_MAX_LAYERS];
+};
+
 struct ModelDev {
   int nlayers;
   int P, Pnet;   // total / network parameters
@@ -67,6 +91,7 @@ struct ModelDev {
   int act_total;                     // floats of activation smem for one batch tile
   LayerDev L[BFX_MAX_LAYERS];
   SegDesc seg[BFX_MAX_SEGS];
+  TcDesc tc;
 };
 
 // sampler hyper-parameters (device copy of bfx_sampler_desc, see include/bfx.h)

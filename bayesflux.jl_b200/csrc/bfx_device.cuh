@@ -392,17 +392,25 @@ struct TileCfg {
 struct ChainSmem {
   float* th;    // [S]   padded parameters
   float* g;     // [S]   padded gradient
-  float* act;   // activation buffers of one batch tile
+  float* act;   // activation buffers of one batch tile (FP32 path only)
   float* ys;    // [BT]  targets of the tile
   int* idx;     // [BT]  observation indices of the tile (-1 = masked)
   float* red;   // [32*4] reduction scratch
   double* dacc; // [4]   double accumulators (thread 0)
+  unsigned char* tc;  // tensor-core region (128-byte aligned) or nullptr
 };
+
+// floats of the CTA working set that precede the tensor-core region
+template <int BT>
+__host__ __device__ inline size_t chain_smem_floats(const ModelDev& M) {
+  return (size_t)2 * M.S + (M.tc.enabled ? 0 : M.act_total) + BT /*ys*/ + BT /*idx*/ + 32 * 4 /*red*/;
+}
 
 template <int BT>
 __host__ __device__ inline size_t chain_smem_bytes(const ModelDev& M) {
-  size_t f = (size_t)2 * M.S + M.act_total + BT /*ys*/ + BT /*idx*/ + 32 * 4 /*red*/;
-  return f * 4 + 4 * sizeof(double) + 16;
+  size_t b = chain_smem_floats<BT>(M) * 4 + 4 * sizeof(double) + 16;
+  if (M.tc.enabled) b = ((b + 127) & ~(size_t)127) + (size_t)M.tc.total_bytes + 128;
+  return b;
 }
 
 template <int BT>
@@ -413,10 +421,15 @@ BFX_DEV ChainSmem carve_smem(const ModelDev& M, unsigned char* base) {
   float* f = reinterpret_cast<float*>(d + 4);
   s.th = f; f += M.S;
   s.g = f; f += M.S;
-  s.act = f; f += M.act_total;
+  s.act = f; f += (M.tc.enabled ? 0 : M.act_total);
   s.ys = f; f += BT;
   s.idx = reinterpret_cast<int*>(f); f += BT;
-  s.red = f;
+  s.red = f; f += 32 * 4;
+  s.tc = nullptr;
+  if (M.tc.enabled) {
+    unsigned long long a = reinterpret_cast<unsigned long long>(f);
+    s.tc = reinterpret_cast<unsigned char*>((a + 127ull) & ~127ull);
+  }
   return s;
 }
 

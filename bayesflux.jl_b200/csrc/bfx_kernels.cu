@@ -40,12 +40,17 @@ BFX_DEV void make_batch(const RunDev& R, int c, unsigned long long gstep, BatchS
   perm_keys(R.seed, chainkey, epoch, bs.k0, bs.k1);
 }
 
-template <int NT, int BT>
+template <int NT, int BT, bool TC>
 __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const ModelDev& M = E.M;
   ChainSmem s = carve_smem<BT>(M, smem_raw);
   const int c = blockIdx.x;
+  tc::Region tr{};
+  if constexpr (TC) {
+    tr = tc::region_of(M, s);
+    tc::setup<NT>(M, tr);
+  }
   for (int k = threadIdx.x; k < M.S; k += NT) s.th[k] = 0.f;
   __syncthreads();
   const float* th_in = E.theta + (long long)c * M.P;
@@ -59,21 +64,30 @@ __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) 
   bs.full = E.idx ? 0 : 1;
   bs.idx = E.idx ? E.idx + (long long)c * E.idx_chain_stride : nullptr;
   float gn2;
-  double v = chain_eval<NT, BT>(M, s, E.x, E.y, bs, E.B, E.num_batches, E.want_grad != 0, gn2);
+  double v;
+  if constexpr (TC) v = tc::chain_eval_tc<NT>(M, s, tr, E.x, E.y, bs, E.B, E.num_batches, E.want_grad != 0, gn2);
+  else v = chain_eval<NT, BT>(M, s, E.x, E.y, bs, E.B, E.num_batches, E.want_grad != 0, gn2);
   if (threadIdx.x == 0) E.v_out[c] = v;
   if (E.want_grad) {
     float* g_out = E.g_out + (long long)c * M.P;
     for_each_param<NT>(M, [&](int J, int k) { g_out[J] = s.g[k]; });
   }
+  if constexpr (TC) tc::teardown<NT>(M, tr);
 }
 
-template <int NT, int BT, int KIND>
+template <int NT, int BT, int KIND, bool TC>
 __global__ void __launch_bounds__(NT) k_mcmc(const __grid_constant__ RunDev R) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const ModelDev& M = R.M;
   ChainSmem s = carve_smem<BT>(M, smem_raw);
   const int c = blockIdx.x;
-  Ctx<NT, BT> X(R, s);
+  tc::Region tr{};
+  if constexpr (TC) {
+    tr = tc::region_of(M, s);
+    tc::setup<NT>(M, tr);
+  }
+  Ctx<NT, BT, TC> X(R, s);
+  X.tcr = &tr;
   X.c = c;
   X.key.seed = R.seed;
   X.key.chain = R.chain0 + (unsigned)c;
@@ -104,6 +118,7 @@ __global__ void __launch_bounds__(NT) k_mcmc(const __grid_constant__ RunDev R) {
   __syncthreads();
   for_each_param<NT>(M, [&](int J, int k) { X.th_g[J] = s.th[k]; });
   if (threadIdx.x == 0) R.sc[c] = X.sc;
+  if constexpr (TC) tc::teardown<NT>(M, tr);
 }
 
 // ---- test hooks -----------------------------------------------------------------
@@ -130,23 +145,23 @@ __global__ void k_debug_noise(unsigned long long seed, unsigned chain, unsigned 
 }
 
 // ---- launchers --------------------------------------------------------------------
-template <int NT, int BT>
+template <int NT, int BT, bool TC = false>
 static cudaError_t launch_eval_t(const EvalDev& E, cudaStream_t st) {
-  size_t smem = chain_smem_bytes<BT>(E.M);
-  auto kern = k_eval<NT, BT>;
+  size_t smem = chain_smem_bytes<BT>(E.M) + (size_t)E.M.tc.smem_pad;
+  auto kern = k_eval<NT, BT, TC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<E.C, NT, smem, st>>>(E);
   return cudaGetLastError();
 }
 
-template <int NT, int BT>
+template <int NT, int BT, bool TC = false>
 static cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
-  size_t smem = chain_smem_bytes<BT>(R.M);
+  size_t smem = chain_smem_bytes<BT>(R.M) + (size_t)R.M.tc.smem_pad;
   cudaError_t e;
 #define BFX_LAUNCH(KIND)                                                                        \
   {                                                                                             \
-    auto kern = k_mcmc<NT, BT, KIND>;                                                           \
+    auto kern = k_mcmc<NT, BT, KIND, TC>;                                                           \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     if (e != cudaSuccess) return e;                                                             \
     kern<<<R.C, NT, smem, st>>>(R);                                                             \
@@ -167,12 +182,14 @@ size_t smallp_smem_bytes(const ModelDev& M, int bt) {
 }
 
 cudaError_t launch_eval(const EvalDev& E, const LaunchCfg& cfg, cudaStream_t st) {
+  if (E.M.tc.enabled) return launch_eval_t<256, 64, true>(E, st);
   if (cfg.nt == 32) return launch_eval_t<32, 32>(E, st);
   if (cfg.nt == 128) return launch_eval_t<128, 64>(E, st);
   return launch_eval_t<256, 64>(E, st);
 }
 
 cudaError_t launch_mcmc(const RunDev& R, const LaunchCfg& cfg, cudaStream_t st) {
+  if (R.M.tc.enabled) return launch_mcmc_t<256, 64, true>(R, st);
   if (cfg.nt == 32) return launch_mcmc_t<32, 32>(R, st);
   if (cfg.nt == 128) return launch_mcmc_t<128, 64>(R, st);
   return launch_mcmc_t<256, 64>(R, st);

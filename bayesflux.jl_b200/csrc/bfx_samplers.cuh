@@ -3,13 +3,14 @@
 // work of one update (preconditioning, momentum / thermostat, noise, step size, sample
 // write) is done in at most two passes over theta with the reductions folded in.
 #pragma once
-#include "bfx_chain.cuh"
+#include "bfx_tc.cuh"
 
 namespace bfx {
 
-template <int NT, int BT>
+template <int NT, int BT, bool TC = false>
 struct Ctx {
   const RunDev& R;
+  tc::Region* tcr = nullptr;  // tensor-core region of this CTA (TC builds only)
   ChainSmem s;
   int c;  // local chain
   NoiseKey key;
@@ -31,14 +32,18 @@ struct Ctx {
   }
   BFX_DEV float uniform() const { return R.inj_uniforms ? R.inj_uniforms[c] : uniform_draw(key, gstep); }
 
-  BFX_DEV double grad(float& gn2) { return chain_eval<NT, BT>(R.M, s, R.x, R.y, bs, Bk, R.num_batches, true, gn2); }
+  BFX_DEV double eval(const BatchSrc& b, long long Bn, float nbs, bool want_grad, float& gn2) {
+    if constexpr (TC) return tc::chain_eval_tc<NT>(R.M, s, *tcr, R.x, R.y, b, Bn, nbs, want_grad, gn2);
+    else return chain_eval<NT, BT>(R.M, s, R.x, R.y, b, Bn, nbs, want_grad, gn2);
+  }
+  BFX_DEV double grad(float& gn2) { return eval(bs, Bk, R.num_batches, true, gn2); }
   // loglikeprior(bnn, θ, bnn.x, bnn.y): full data, num_batches = 1 (ggmc.jl:147,176; hmc.jl:135-136)
   BFX_DEV double full_lp() {
     BatchSrc f = bs;
     f.full = 1;
     f.idx = nullptr;
     float dummy;
-    return chain_eval<NT, BT>(R.M, s, R.x, R.y, f, R.n, 1.f, false, dummy);
+    return eval(f, R.n, 1.f, false, dummy);
   }
   BFX_DEV bool uses_minv() const { return R.S.madapter_kind != MA_FIXED; }
 };
@@ -52,8 +57,8 @@ BFX_DEV bool block_any(bool f, float* red) {
 }
 
 // s.samples[:, t] = copy(θ)  (+ DiagCov window ring).  ns = nsampled AFTER the increment.
-template <int NT, int BT>
-BFX_DEV void record_sample(Ctx<NT, BT>& X, long long ns, const float* src_global /* nullptr: smem theta */) {
+template <int NT, int BT, bool TC>
+BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns, const float* src_global /* nullptr: smem theta */) {
   const RunDev& R = X.R;
   float* dst = nullptr;
   if (R.samples && (ns % R.keep_every) == 0) {
@@ -88,8 +93,8 @@ BFX_DEV float mh_prob_of(float lMH) { return (lMH != lMH) ? lMH : fminf(expf(lMH
 
 // madapter(s, θ, bnn, ∇θ) -> Minv (diagonal).  The gradient RMSProp asks for is the one
 // of the current minibatch at the current θ, which is what s.g already holds.
-template <int NT, int BT>
-BFX_DEV void mass_adapt(Ctx<NT, BT>& X, float gn2) {
+template <int NT, int BT, bool TC>
+BFX_DEV void mass_adapt(Ctx<NT, BT, TC>& X, float gn2) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   if (S.madapter_kind == MA_RMSPROP) {
@@ -130,8 +135,8 @@ BFX_DEV void mass_adapt(Ctx<NT, BT>& X, float gn2) {
 // --------------------------------------------------------------------------------
 // SGLD  (src/inference/mcmc/sgld.jl:96-112)
 // --------------------------------------------------------------------------------
-template <int NT, int BT>
-BFX_DEV void step_sgld(Ctx<NT, BT>& X) {
+template <int NT, int BT, bool TC>
+BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
   const SamplerDev& S = X.R.S;
   float alpha = S.stepsize_a * powf(S.stepsize_b + (float)X.sc.t, -S.stepsize_gamma);  // sgld.jl:12
   alpha = fmaxf(alpha, S.min_stepsize);
@@ -151,8 +156,8 @@ BFX_DEV void step_sgld(Ctx<NT, BT>& X) {
 // --------------------------------------------------------------------------------
 // SGNHT  (src/inference/mcmc/sgnht.jl:64-90)
 // --------------------------------------------------------------------------------
-template <int NT, int BT>
-BFX_DEV void step_sgnht(Ctx<NT, BT>& X) {
+template <int NT, int BT, bool TC>
+BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   float gn2;
@@ -192,8 +197,8 @@ BFX_DEV void step_sgnht(Ctx<NT, BT>& X) {
 // --------------------------------------------------------------------------------
 // SGNHTS  (src/inference/mcmc/sgnht-s.jl:81-116), BAOAB-like splitting, diagonal Minv
 // --------------------------------------------------------------------------------
-template <int NT, int BT>
-BFX_DEV void step_sgnhts(Ctx<NT, BT>& X) {
+template <int NT, int BT, bool TC>
+BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   float gn2;
@@ -254,8 +259,8 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT>& X) {
 // --------------------------------------------------------------------------------
 // GGMC  (src/inference/mcmc/ggmc.jl:140-198), diagonal mass
 // --------------------------------------------------------------------------------
-template <int NT, int BT>
-BFX_DEV void step_ggmc(Ctx<NT, BT>& X) {
+template <int NT, int BT, bool TC>
+BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   const float N = (float)R.n;
@@ -335,8 +340,8 @@ BFX_DEV void step_ggmc(Ctx<NT, BT>& X) {
 // --------------------------------------------------------------------------------
 // HMC  (src/inference/mcmc/hmc.jl:105-159): one call = one leapfrog stage
 // --------------------------------------------------------------------------------
-template <int NT, int BT>
-BFX_DEV void step_hmc(Ctx<NT, BT>& X) {
+template <int NT, int BT, bool TC>
+BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   const float l = X.sc.l;

@@ -1,0 +1,557 @@
+// Tensor-core (tcgen05 / TMEM) evaluation of the log posterior and its gradient for MLP chains.
+//
+// Same contract as chain_eval (bfx_chain.cuh): one CTA = one chain, on return s.g holds
+// grad[num_batches*loglike + logprior] in the padded parameter layout.  What changes is where
+// the contractions run: every hidden Dense layer is a 64 x Hout x Hin GEMM per batch tile
+// (batch rows x fan-out x fan-in), issued as tcgen05.mma.cta_group::1.kind::f16 with M = 64 by
+// one thread, operands in shared memory (no-swizzle core-block tiles, hi/lo BF16 halves),
+// accumulators in TMEM.  FP32 accuracy is kept by the 3-term split  a*b ~ ah*bh + ah*bl + al*bh
+// (|error| ~ 2^-17 per product, FP32 accumulate), which holds the 1e-4 gradient bar of the
+// FP32 gate path.  The 1-wide output layer, the likelihood and all activation work run in the
+// epilogues on the TMEM fragments.
+//
+// Reference arithmetic: Flux Dense forward called at src/likelihoods/feedforward.jl:35,91, the
+// Zygote pullbacks of it (src/model/BNN.jl:66), likelihood deltas of SURVEY.md rows a8/a9.
+// Descriptor / fragment conventions were pinned on a B200 by tools/umma_probe*.cu
+// (profiles/r01_umma_probe_conventions.log).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "bfx_chain.cuh"
+
+namespace bfx {
+namespace tc {
+
+BFX_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, SWIZZLE_NONE, descriptor version 1
+BFX_DEV uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = F32, A = B = BF16, M = 64
+BFX_DEV uint32_t make_idesc(int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+}
+BFX_DEV void mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+BFX_DEV void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+BFX_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+BFX_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+BFX_DEV void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+BFX_DEV void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+BFX_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+BFX_DEV void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 lanes x 32 columns of a warp's lane quadrant: thread t gets, for j = 0..3,
+//   v[4j+0], v[4j+1] = (row t/4,     cols 8j + 2(t%4) + {0,1})
+//   v[4j+2], v[4j+3] = (row t/4 + 8, same columns)
+BFX_DEV void ld_16x256b_x4(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+BFX_DEV void ld_16x256b_x1(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// BF16 split of two adjacent values: hi word = {bf16(a), bf16(b)}, lo word = the residuals
+BFX_DEV void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+BFX_DEV float bf16lo_to_f(uint32_t w) { return __uint_as_float(w << 16); }
+BFX_DEV float bf16hi_to_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+struct Region {
+  unsigned char* base;  // 128-byte aligned tensor-core region
+  uint32_t tmem;        // TMEM base address (lane 0, column 0)
+  float* yh;            // [2][64] partial network outputs of the two column halves
+  float* glast;         // [72]    gradient of the output layer (weights, then bias at [64])
+  uint64_t* bar;        // [4]
+  uint32_t* tmem_slot;
+  uint32_t par[3];      // phase parity of bar[0..2]
+};
+
+BFX_DEV Region region_of(const ModelDev& M, const ChainSmem& s) {
+  Region R;
+  R.base = s.tc;
+  float* f = reinterpret_cast<float*>(s.tc + M.tc.misc_off);
+  R.yh = f;
+  R.glast = f + 128;
+  R.bar = reinterpret_cast<uint64_t*>(f + 200);
+  R.tmem_slot = reinterpret_cast<uint32_t*>(f + 208);
+  R.tmem = 0;
+  R.par[0] = R.par[1] = R.par[2] = 0;
+  return R;
+}
+
+// kernel prologue: TMEM allocation, barriers, constant parts of the tiles.  All threads call it.
+template <int NT>
+BFX_DEV void setup(const ModelDev& M, Region& R) {
+  const TcDesc& T = M.tc;
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(R.tmem_slot)),
+                 "r"((uint32_t)T.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < 3) mbar_init(&R.bar[threadIdx.x], 1);
+  // zero every tile, then the constant-one column of the activation tiles
+  uint4* z = reinterpret_cast<uint4*>(R.base);
+  for (int i = threadIdx.x; i < T.misc_off / 16; i += NT) z[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int l = 0; l < T.nh; ++l) {
+    const TcLayer& L = T.L[l];
+    const int sbo = (L.ccols >> 3) * 128;
+    for (int b = threadIdx.x; b < 64; b += NT) {
+      const int off = (b >> 3) * sbo + (L.kpad >> 3) * 128 + (b & 7) * 16;
+      *reinterpret_cast<unsigned short*>(R.base + L.a_off + off) = 0x3F80;  // bf16(1), hi tile only
+    }
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  R.tmem = *R.tmem_slot;
+}
+
+template <int NT>
+BFX_DEV void teardown(const ModelDev& M, Region& R) {
+  fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(R.tmem), "r"((uint32_t)M.tc.tmem_cols)
+                 : "memory");
+}
+
+// theta (FP32 master copy in s.th) -> hi/lo BF16 weight tiles.  Tile element (r = fan-in i, c = fan-out o).
+template <int NT>
+BFX_DEV void pack_weights(const ModelDev& M, const ChainSmem& s, const Region& R) {
+  const TcDesc& T = M.tc;
+  for (int l = 0; l < T.nh; ++l) {
+    const TcLayer& L = T.L[l];
+    const LayerDev& D = M.L[l];
+    const int noc = L.hout >> 3;           // 8-wide fan-out chunks
+    const int items = ((D.nin + 7) >> 3) * 8 * noc;  // rows i >= nin stay zero
+    unsigned char* hi = R.base + L.w_off;
+    unsigned char* lo = hi + L.w_bytes;
+    for (int e = threadIdx.x; e < items; e += NT) {
+      // lanes walk i%8 fastest: 8 lanes x 16 B = one conflict-free 128-byte row of the core block
+      const int il = e & 7, rest = e >> 3, oc = rest % noc, ih = rest / noc;
+      const int i = ih * 8 + il;
+      if (i >= D.nin) continue;
+      const float* src = s.th + D.w_s + i * D.ldw + 8 * oc;
+      float4 a = ld4(src), b = ld4(src + 4);
+      uint4 h, q;
+      split2(a.x, a.y, h.x, q.x);
+      split2(a.z, a.w, h.y, q.y);
+      split2(b.x, b.y, h.z, q.z);
+      split2(b.z, b.w, h.w, q.w);
+      const int off = ih * (noc * 128) + oc * 128 + il * 16;
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = q;
+    }
+  }
+}
+
+// one k-step = the three MMAs of the split product
+BFX_DEV void mma3(uint32_t d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc, uint32_t acc) {
+  mma(d, ahi, bhi, idesc, acc);
+  mma(d, ahi, blo, idesc, 1u);
+  mma(d, alo, bhi, idesc, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// value / gradient over a minibatch (loop over 64-row tiles).  NT must be 256.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, const float* __restrict__ x,
+                             const float* __restrict__ y, const BatchSrc& bs, long long B, float nb, bool want_grad,
+                             float& gn2) {
+  static_assert(NT == 256, "the tensor-core path uses 8 warps: 4 lane quadrants x 2 column halves");
+  const TcDesc& T = M.tc;
+  const int nh = T.nh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, h = warp >> 2;
+  const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8;  // the two batch rows of this thread's fragment
+  const uint32_t zaddr = R.tmem + ((uint32_t)(32 * q) << 16);
+  const LayerDev& LO = M.L[M.nlayers - 1];  // the 1-wide output layer
+  const float sl = s.th[M.like_s];
+  const float inv_sigma = 1.f / expf(sl);
+  double ds0 = 0.0, ds1 = 0.0;
+
+  pack_weights<NT>(M, s, R);
+  if (want_grad)
+    for (int k = tid; k < 72; k += NT) R.glast[k] = 0.f;
+  // (made visible to the async proxy by the fence + barrier after the first tile is staged)
+
+  const int d = M.d_in;
+  for (long long t0 = 0; t0 < B; t0 += 64) {
+    const int nvalid = (int)((B - t0) < 64 ? (B - t0) : 64);
+    const bool first_tile = t0 == 0;
+    // ---- stage the tile: indices, targets, X as hi/lo BF16 (rows >= nvalid are zero) ----------
+    if (tid < 64) {
+      long long o = (tid < nvalid) ? batch_obs(bs, t0 + tid) : -1;
+      s.idx[tid] = (int)o;
+      s.ys[tid] = (o >= 0) ? __ldg(y + o) : 0.f;
+    }
+    __syncthreads();
+    {
+      const TcLayer& L0 = T.L[0];
+      const int nch = L0.kpad >> 3;
+      const int sbo = (L0.ccols >> 3) * 128;
+      unsigned char* hi = R.base + L0.a_off;
+      unsigned char* lo = hi + L0.a_bytes;
+      for (int e = tid; e < 64 * nch; e += NT) {
+        const int bl = e & 7, rest = e >> 3, ch = rest % nch, bh = rest / nch;
+        const int b = bh * 8 + bl;
+        const int o = s.idx[b];
+        float v[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+          const int ff = 8 * ch + f;
+          v[f] = (o >= 0 && ff < d) ? __ldg(x + (long long)o * d + ff) : 0.f;
+        }
+        uint4 hh, ll;
+        split2(v[0], v[1], hh.x, ll.x);
+        split2(v[2], v[3], hh.y, ll.y);
+        split2(v[4], v[5], hh.z, ll.z);
+        split2(v[6], v[7], hh.w, ll.w);
+        const int off = bh * sbo + ch * 128 + bl * 16;
+        *reinterpret_cast<uint4*>(hi + off) = hh;
+        *reinterpret_cast<uint4*>(lo + off) = ll;
+      }
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+
+    // ---- forward ---------------------------------------------------------------------------------
+    float a[16];       // activations of the last hidden layer (this thread's fragment)
+    float dl0 = 0.f, dl1 = 0.f;
+    for (int l = 0; l < nh; ++l) {
+      const TcLayer& L = T.L[l];
+      const LayerDev& D = M.L[l];
+      if (tid == 0) {
+        fence_after();
+        const uint32_t a_sbo = (L.ccols >> 3) * 128, b_lbo = (L.hout >> 3) * 128;
+        const uint32_t ahi = smem_u32(R.base + L.a_off), alo = ahi + L.a_bytes;
+        const uint32_t bhi = smem_u32(R.base + L.w_off), blo = bhi + L.w_bytes;
+        const uint32_t idesc = make_idesc(L.hout, 0, 1);
+        for (int k = 0; k < (L.kpad >> 4); ++k) {
+          // A: K-major (rows = batch): LBO = next 16-byte K chunk, SBO = next 8 rows; 16 k = 2 chunks
+          // B: MN-major (rows = fan-in k, cols = fan-out n): SBO = next 8 n, LBO = next 8 k rows
+          mma3(R.tmem, make_desc(ahi + k * 256, 128, a_sbo), make_desc(alo + k * 256, 128, a_sbo),
+               make_desc(bhi + k * 2 * b_lbo, b_lbo, 128), make_desc(blo + k * 2 * b_lbo, b_lbo, 128), idesc,
+               k ? 1u : 0u);
+        }
+        commit(&R.bar[0]);
+      }
+      mbar_wait(&R.bar[0], R.par[0]);
+      R.par[0] ^= 1;
+      fence_after();
+      // epilogue of layer l on the fragment: rows r0/r1, columns 32h + 8j + 2(lane%4) + {0,1}
+      const bool active = 32 * h < L.hout;
+      if (active) ld_16x256b_x4(zaddr + (uint32_t)(32 * h), a);
+      const int cbase = 32 * h + 2 * (lane & 3);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = cbase + 8 * j;
+        if (active && c < L.hout) {
+          const float2 bb = *reinterpret_cast<const float2*>(s.th + D.b_s + c);
+          a[4 * j + 0] = act_apply(D.act, a[4 * j + 0] + bb.x);
+          a[4 * j + 1] = act_apply(D.act, a[4 * j + 1] + bb.y);
+          a[4 * j + 2] = act_apply(D.act, a[4 * j + 2] + bb.x);
+          a[4 * j + 3] = act_apply(D.act, a[4 * j + 3] + bb.y);
+        } else {
+          a[4 * j + 0] = a[4 * j + 1] = a[4 * j + 2] = a[4 * j + 3] = 0.f;
+        }
+      }
+      if (l + 1 < nh) {
+        // next layer's input tile
+        const TcLayer& Ln = T.L[l + 1];
+        const int sbo = (Ln.ccols >> 3) * 128;
+        unsigned char* hi = R.base + Ln.a_off;
+        unsigned char* lo = hi + Ln.a_bytes;
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = cbase + 8 * j;
+            if (c < L.hout) {
+              uint32_t h0, l0, h1, l1;
+              split2(a[4 * j + 0], a[4 * j + 1], h0, l0);
+              split2(a[4 * j + 2], a[4 * j + 3], h1, l1);
+              const int off0 = (r0 >> 3) * sbo + (c >> 3) * 128 + (r0 & 7) * 16 + (c & 7) * 2;
+              const int off1 = off0 + sbo;  // r1 = r0 + 8
+              *reinterpret_cast<uint32_t*>(hi + off0) = h0;
+              *reinterpret_cast<uint32_t*>(lo + off0) = l0;
+              *reinterpret_cast<uint32_t*>(hi + off1) = h1;
+              *reinterpret_cast<uint32_t*>(lo + off1) = l1;
+            }
+          }
+        }
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+      }
+    }
+    // ---- output layer (fan-out 1) + likelihood on the fragment of the last hidden layer -----------
+    const int hl = T.L[nh - 1].hout;
+    const int cbase = 32 * h + 2 * (lane & 3);
+    float wl[8];
+    {
+      float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = cbase + 8 * j;
+        wl[2 * j] = (c < hl) ? s.th[LO.w_s + c * LO.ldw] : 0.f;
+        wl[2 * j + 1] = (c + 1 < hl) ? s.th[LO.w_s + (c + 1) * LO.ldw] : 0.f;
+        p0 = fmaf(a[4 * j + 0], wl[2 * j], fmaf(a[4 * j + 1], wl[2 * j + 1], p0));
+        p1 = fmaf(a[4 * j + 2], wl[2 * j], fmaf(a[4 * j + 3], wl[2 * j + 1], p1));
+      }
+      p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+      p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+      p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+      p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+      if ((lane & 3) == 0) {
+        R.yh[64 * h + r0] = p0;
+        R.yh[64 * h + r1] = p1;
+      }
+    }
+    __syncthreads();
+    {
+      const float bl = s.th[LO.b_s];
+      const bool owner = (lane & 3) == 0 && h == 0;
+      float sm0 = 0.f, sm1 = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = rr ? r1 : r0;
+        float dl = 0.f;
+        if (r < nvalid) {
+          const float yh = act_apply(LO.act, R.yh[r] + R.yh[64 + r] + bl);
+          const float z = (s.ys[r] - yh) * inv_sigma;
+          if (M.like_kind == LK_NORMAL) {
+            sm0 += z * z;
+            dl = nb * z * inv_sigma;
+          } else {
+            const float zz = z * z;
+            const float w = (M.nu + 1.f) * z / (M.nu + zz);
+            sm0 += log1pf(zz / M.nu);
+            sm1 += w * z;
+            dl = nb * w * inv_sigma;
+          }
+          dl *= act_deriv_from_out(LO.act, yh);
+        }
+        if (rr) dl1 = dl; else dl0 = dl;
+      }
+      if (owner) {
+        ds0 += (double)sm0;
+        ds1 += (double)sm1;
+      }
+    }
+    if (want_grad) {
+      // output-layer gradient: dW[c] = sum_b dl[b] a[b][c], db = sum_b dl[b]
+      {
+        float pc[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pc[2 * j] = dl0 * a[4 * j + 0] + dl1 * a[4 * j + 2];
+          pc[2 * j + 1] = dl0 * a[4 * j + 1] + dl1 * a[4 * j + 3];
+        }
+        float pb = dl0 + dl1;
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pc[i] += __shfl_xor_sync(0xffffffffu, pc[i], o);
+          pb += __shfl_xor_sync(0xffffffffu, pb, o);
+        }
+        if (lane < 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = cbase + 8 * j;
+            if (c < hl) atomicAdd(&R.glast[c], pc[2 * j]);
+            if (c + 1 < hl) atomicAdd(&R.glast[c + 1], pc[2 * j + 1]);
+          }
+          if (lane == 0 && h == 0) atomicAdd(&R.glast[64], pb);
+        }
+      }
+      // delta of the last hidden layer -> D tile (64 x 64, zero beyond hl)
+      {
+        const int act_l = M.L[nh - 1].act;
+        unsigned char* hi = R.base + T.d_off;
+        unsigned char* lo = hi + T.d_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = cbase + 8 * j;
+          const float d00 = dl0 * wl[2 * j] * act_deriv_from_out(act_l, a[4 * j + 0]);
+          const float d01 = dl0 * wl[2 * j + 1] * act_deriv_from_out(act_l, a[4 * j + 1]);
+          const float d10 = dl1 * wl[2 * j] * act_deriv_from_out(act_l, a[4 * j + 2]);
+          const float d11 = dl1 * wl[2 * j + 1] * act_deriv_from_out(act_l, a[4 * j + 3]);
+          uint32_t h0, l0, h1, l1;
+          split2(d00, d01, h0, l0);
+          split2(d10, d11, h1, l1);
+          const int off0 = (r0 >> 3) * 1024 + (c >> 3) * 128 + (r0 & 7) * 16 + (c & 7) * 2;
+          *reinterpret_cast<uint32_t*>(hi + off0) = h0;
+          *reinterpret_cast<uint32_t*>(lo + off0) = l0;
+          *reinterpret_cast<uint32_t*>(hi + off0 + 1024) = h1;
+          *reinterpret_cast<uint32_t*>(lo + off0 + 1024) = l1;
+        }
+      }
+      fence_async_smem();
+      fence_before();
+      __syncthreads();
+      // ---- backward ------------------------------------------------------------------------------
+      for (int l = nh - 1; l >= 0; --l) {
+        const TcLayer& L = T.L[l];
+        if (tid == 0) {
+          fence_after();
+          const uint32_t dhi = smem_u32(R.base + T.d_off), dlo = dhi + T.d_bytes;
+          const uint32_t whi = smem_u32(R.base + L.w_off), wlo = whi + L.w_bytes;
+          const uint32_t xhi = smem_u32(R.base + L.a_off), xlo = xhi + L.a_bytes;
+          if (l > 0) {
+            // dA[b][i] = sum_o D[b][o] W[o][i]:  A = D tile K-major (K = fan-out), B = W tile K-major (rows n = fan-in)
+            const uint32_t w_sbo = (L.hout >> 3) * 128;
+            const uint32_t idesc = make_idesc(L.kpad, 0, 0);
+            for (int k = 0; k < (L.hout >> 4); ++k)
+              mma3(R.tmem, make_desc(dhi + k * 256, 128, 1024), make_desc(dlo + k * 256, 128, 1024),
+                   make_desc(whi + k * 256, 128, w_sbo), make_desc(wlo + k * 256, 128, w_sbo), idesc, k ? 1u : 0u);
+            commit(&R.bar[1]);
+          }
+          // dW[o][c] += sum_b D[b][o] Ain[b][c]:  A = D tile MN-major (M = fan-out), B = Ain tile MN-major, K = batch
+          const uint32_t x_lbo = (L.ccols >> 3) * 128;
+          const uint32_t idesc = make_idesc(L.ccols, 1, 1);
+          for (int k = 0; k < 4; ++k)
+            mma3(R.tmem + (uint32_t)L.dw_col, make_desc(dhi + k * 2048, 1024, 128), make_desc(dlo + k * 2048, 1024, 128),
+                 make_desc(xhi + k * 2 * x_lbo, x_lbo, 128), make_desc(xlo + k * 2 * x_lbo, x_lbo, 128), idesc,
+                 (k || !first_tile) ? 1u : 0u);
+          commit(&R.bar[2]);
+        }
+        if (l > 0) {
+          mbar_wait(&R.bar[1], R.par[1]);
+          R.par[1] ^= 1;
+          fence_after();
+          // delta of layer l-1 = dA * act'(A_{l-1}); A_{l-1} is the input tile of layer l
+          const int hp = L.kpad;  // = fan-out of layer l-1
+          const int act_p = M.L[l - 1].act;
+          const bool active = 32 * h < hp;
+          float da[16];
+          if (active) ld_16x256b_x4(zaddr + (uint32_t)(32 * h), da);
+          const int sbo = (L.ccols >> 3) * 128;
+          const unsigned char* ahi = R.base + L.a_off;
+          const unsigned char* alo = ahi + L.a_bytes;
+          uint32_t oh[8], ol[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = cbase + 8 * j;
+            oh[2 * j] = ol[2 * j] = oh[2 * j + 1] = ol[2 * j + 1] = 0u;
+            if (active && c < hp) {
+              const int off0 = (r0 >> 3) * sbo + (c >> 3) * 128 + (r0 & 7) * 16 + (c & 7) * 2;
+              const uint32_t h0 = *reinterpret_cast<const uint32_t*>(ahi + off0);
+              const uint32_t l0 = *reinterpret_cast<const uint32_t*>(alo + off0);
+              const uint32_t h1 = *reinterpret_cast<const uint32_t*>(ahi + off0 + sbo);
+              const uint32_t l1 = *reinterpret_cast<const uint32_t*>(alo + off0 + sbo);
+              const float a00 = bf16lo_to_f(h0) + bf16lo_to_f(l0), a01 = bf16hi_to_f(h0) + bf16hi_to_f(l0);
+              const float a10 = bf16lo_to_f(h1) + bf16lo_to_f(l1), a11 = bf16hi_to_f(h1) + bf16hi_to_f(l1);
+              split2(da[4 * j + 0] * act_deriv_from_out(act_p, a00), da[4 * j + 1] * act_deriv_from_out(act_p, a01),
+                     oh[2 * j], ol[2 * j]);
+              split2(da[4 * j + 2] * act_deriv_from_out(act_p, a10), da[4 * j + 3] * act_deriv_from_out(act_p, a11),
+                     oh[2 * j + 1], ol[2 * j + 1]);
+            }
+          }
+          // the dW MMAs of layer l still read the D tile: wait for them before overwriting it
+          mbar_wait(&R.bar[2], R.par[2]);
+          R.par[2] ^= 1;
+          unsigned char* hi = R.base + T.d_off;
+          unsigned char* lo = hi + T.d_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = cbase + 8 * j;
+            const int off0 = (r0 >> 3) * 1024 + (c >> 3) * 128 + (r0 & 7) * 16 + (c & 7) * 2;
+            *reinterpret_cast<uint32_t*>(hi + off0) = oh[2 * j];
+            *reinterpret_cast<uint32_t*>(lo + off0) = ol[2 * j];
+            *reinterpret_cast<uint32_t*>(hi + off0 + 1024) = oh[2 * j + 1];
+            *reinterpret_cast<uint32_t*>(lo + off0 + 1024) = ol[2 * j + 1];
+          }
+          fence_async_smem();
+          fence_before();
+          __syncthreads();
+        } else {
+          mbar_wait(&R.bar[2], R.par[2]);
+          R.par[2] ^= 1;
+          fence_after();
+        }
+      }
+    }
+    fence_before();
+    __syncthreads();  // tile buffers, yh and the Z accumulator are free again
+  }
+
+  if (want_grad) {
+    // ---- dW accumulators (TMEM) -> s.g in the padded parameter layout ---------------------------------
+    fence_after();
+    for (int l = 0; l < nh; ++l) {
+      const TcLayer& L = T.L[l];
+      const LayerDev& D = M.L[l];
+      const int ngroups = L.ccols >> 3;
+      for (int gq = h; gq < ngroups; gq += 2) {
+        float v[4];
+        ld_16x256b_x1(zaddr + (uint32_t)(L.dw_col + 8 * gq), v);
+        const int c = 8 * gq + 2 * (lane & 3);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int o = (e & 2) ? r1 : r0, cc = c + (e & 1);
+          if (o < D.nout) {
+            if (cc < D.nin) s.g[D.w_s + cc * D.ldw + o] = v[e];
+            else if (cc == L.kpad) s.g[D.b_s + o] = v[e];
+          }
+        }
+      }
+    }
+    const int hl = T.L[nh - 1].hout;
+    for (int k = tid; k < hl; k += NT) s.g[LO.w_s + k * LO.ldw] = R.glast[k];
+    if (tid == 0) s.g[LO.b_s] = R.glast[64];
+    fence_before();
+  }
+  __syncthreads();
+  return eval_finish<NT>(M, s, B, nb, ds0, ds1, want_grad, gn2);
+}
+
+}  // namespace tc
+}  // namespace bfx

@@ -204,7 +204,7 @@ def run_ours(args):
     nc = bf.destruct(net)
     like = bf.FeedforwardNormal(nc, bf.Gamma(2.0, 0.5))
     prior = bf.GaussianPrior(nc, 1.0)
-    bnn = bf.BNN(x, y, like, prior, device=local)
+    bnn = bf.BNN(x, y, like, prior, device=local, compute=args.compute)
     P = bnn.num_total_params
     assert P == P_TOTAL
     rng_c = np.random.default_rng(SEED + 1 + rank)
@@ -344,6 +344,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_DATA)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--compute", default="tc", choices=["fp32", "tc", "auto"],
+                    help="contraction arithmetic: tc = tcgen05 tensor cores (3-term BF16 split), fp32 = CUDA-core gate path")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

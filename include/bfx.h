@@ -183,6 +183,16 @@ int32_t bfx_model_set_data(bfx_model* m, const float* x, const int64_t* dims, in
 int32_t bfx_model_set_data_device(bfx_model* m, const float* x_dev, const int64_t* dims, int32_t ndims,
                                   const float* y_dev, int64_t n);
 
+/* Arithmetic of the contractions (no reference counterpart: the reference has one Float32 path).
+ *   BFX_COMPUTE_FP32      FP32 FMA on the CUDA cores -- the correctness gate, every model
+ *   BFX_COMPUTE_TC_BF16X3 tcgen05 tensor cores, 3-term BF16 split with FP32 accumulation in TMEM
+ *                         (same 1e-4 gradient bar); MLPs whose hidden widths are multiples of 16
+ *                         and <= 64, input dimension <= 64; otherwise BFX_ERR_UNSUPPORTED and the
+ *                         model stays on the FP32 path. */
+enum { BFX_COMPUTE_FP32 = 0, BFX_COMPUTE_TC_BF16X3 = 1 };
+int32_t bfx_model_set_compute(bfx_model* m, int32_t mode);
+int32_t bfx_model_get_compute(const bfx_model* m, int32_t* mode);
+
 /* ---- log posterior and its gradient (parity entries) -------------------- *
  * loglikeprior(bnn, θ, x, y; num_batches)   src/model/BNN.jl:50-56
  * ∇loglikeprior(bnn, θ, x, y; num_batches)  src/model/BNN.jl:61-69
