@@ -52,6 +52,12 @@ struct bfx_model {
   float* y = nullptr;
   int64_t n = 0;
   cudaStream_t stream = nullptr;
+  // flat (ABI) <-> padded (engine) parameter layout
+  std::vector<int> flat_pad, pad_flat;
+  std::vector<unsigned char> pad_mask;
+  int* d_flat_pad = nullptr;
+  int* d_pad_flat = nullptr;
+  unsigned char* d_pad_mask = nullptr;
 };
 
 struct bfx_sampler {
@@ -142,6 +148,19 @@ static int32_t build_model_dev(bfx_model* m, const bfx_like_desc* like, const bf
   M.P = flat + 1;
   M.S = s_off;
   M.nsegs = nseg;
+  m->flat_pad.assign(M.P, 0);
+  m->pad_flat.assign(M.S, -1);
+  m->pad_mask.assign(M.S / 4, 0);
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    const SegDesc& sg = M.seg[sgi];
+    for (int j = 0; j < sg.count; ++j) {
+      const int col = j / sg.rows, row = j - col * sg.rows;
+      const int k = sg.s_off + col * sg.ld + row;
+      m->flat_pad[sg.flat_off + j] = k;
+      m->pad_flat[k] = sg.flat_off + j;
+      m->pad_mask[k >> 2] |= (unsigned char)(1u << (k & 3));
+    }
+  }
   M.d_in = m->layers[0].in;
   // likelihood
   if (like->kind != BFX_LIKE_NORMAL && like->kind != BFX_LIKE_TDIST) return fail(BFX_ERR_BAD_ARG, "unknown likelihood");
@@ -324,6 +343,12 @@ int32_t bfx_model_destroy(bfx_model* m) {
     if (m->y) cudaFree(m->y);
     if (m->stream) cudaStreamDestroy(m->stream);
   }
+  if (m->d_flat_pad) {
+    cudaSetDevice(m->device);
+    cudaFree(m->d_flat_pad);
+    cudaFree(m->d_pad_flat);
+    cudaFree(m->d_pad_mask);
+  }
   delete m;
   return BFX_OK;
 }
@@ -345,7 +370,31 @@ int32_t bfx_model_layer_bounds(const bfx_model* m, int32_t layer, int64_t* start
 static int32_t ensure_stream(bfx_model* m) {
   CK(cudaSetDevice(m->device));
   if (!m->stream) CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  if (!m->d_flat_pad) {
+    CK(cudaMalloc(&m->d_flat_pad, m->flat_pad.size() * sizeof(int)));
+    CK(cudaMalloc(&m->d_pad_flat, m->pad_flat.size() * sizeof(int)));
+    CK(cudaMalloc(&m->d_pad_mask, m->pad_mask.size()));
+    CK(cudaMemcpy(m->d_flat_pad, m->flat_pad.data(), m->flat_pad.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m->d_pad_flat, m->pad_flat.data(), m->pad_flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m->d_pad_mask, m->pad_mask.data(), m->pad_mask.size(), cudaMemcpyHostToDevice));
+    m->M.flat_pad = m->d_flat_pad;
+    m->M.pad_flat = m->d_pad_flat;
+    m->M.pad_mask = m->d_pad_mask;
+  }
   return BFX_OK;
+}
+
+// host-side layout conversion of per-parameter state: flat P x C (ABI)  <->  padded C rows of S floats
+static void flat_to_padded(const bfx_model* m, const float* flat, int C, float fill, std::vector<float>& out) {
+  const int P = m->M.P, S = m->M.S;
+  out.assign((size_t)S * C, fill);
+  for (int c = 0; c < C; ++c)
+    for (int J = 0; J < P; ++J) out[(size_t)c * S + m->flat_pad[J]] = flat[(size_t)c * P + J];
+}
+static void padded_to_flat(const bfx_model* m, const std::vector<float>& pad, int C, float* flat) {
+  const int P = m->M.P, S = m->M.S;
+  for (int c = 0; c < C; ++c)
+    for (int J = 0; J < P; ++J) flat[(size_t)c * P + J] = pad[(size_t)c * S + m->flat_pad[J]];
 }
 
 static int32_t set_data_impl(bfx_model* m, const float* x, const int64_t* dims, int32_t ndims, const float* y,
@@ -501,7 +550,7 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
   s->m = m;
   s->d = *d;
   s->C = nchains;
-  s->Ps = round4(m->M.P);
+  s->Ps = m->M.S;
   SamplerDev& S = s->S;
   S.kind = d->kind;
   S.steps = d->kind == BFX_GGMC ? d->steps : 1;
@@ -557,22 +606,18 @@ int32_t bfx_sampler_destroy(bfx_sampler* s) {
   return BFX_OK;
 }
 
-// rows of P floats (host, dense) <-> rows of Ps floats (device)
-static cudaError_t copy_rows_h2d(float* dst, int Ps, const float* src, int P, int C, cudaStream_t st) {
-  return cudaMemcpy2DAsync(dst, (size_t)Ps * 4, src, (size_t)P * 4, (size_t)P * 4, C, cudaMemcpyHostToDevice, st);
-}
-static cudaError_t copy_rows_d2h(float* dst, int P, const float* src, int Ps, int C, cudaStream_t st) {
-  return cudaMemcpy2DAsync(dst, (size_t)P * 4, src, (size_t)Ps * 4, (size_t)P * 4, C, cudaMemcpyDeviceToHost, st);
-}
-
 int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) {
   if (!s || !theta_start) return fail(BFX_ERR_BAD_ARG, "NULL argument");
   bfx_model* m = s->m;
   int32_t st = ensure_stream(m);
   if (st) return st;
   const size_t all = (size_t)s->Ps * sizeof(float) * (size_t)s->C;
-  CK(cudaMemsetAsync(s->theta, 0, all, m->stream));
-  CK(copy_rows_h2d(s->theta, s->Ps, theta_start, m->M.P, s->C, m->stream));
+  {
+    std::vector<float> pad;
+    flat_to_padded(m, theta_start, s->C, 0.f, pad);
+    CK(cudaMemcpyAsync(s->theta, pad.data(), all, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
   if (s->mom) CK(cudaMemsetAsync(s->mom, 0, all, m->stream));
   if (s->theta_old) CK(cudaMemsetAsync(s->theta_old, 0, all, m->stream));
   if (s->minv) {
@@ -632,8 +677,10 @@ int32_t bfx_sampler_get_state(bfx_sampler* s, int32_t field, void* out, int64_t 
       for (int64_t i = 0; i < (int64_t)P * C; ++i) o[i] = field == BFX_STATE_MINV ? 1.f : 0.f;
       return BFX_OK;
     }
-    CK(copy_rows_d2h(o, P, src, s->Ps, C, m->stream));
+    std::vector<float> pad((size_t)s->Ps * C);
+    CK(cudaMemcpyAsync(pad.data(), src, pad.size() * 4, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
+    padded_to_flat(m, pad, C, o);
     return BFX_OK;
   }
   std::vector<ChainScalars> sc;
@@ -671,7 +718,9 @@ int32_t bfx_sampler_set_state(bfx_sampler* s, int32_t field, const void* in, int
     float* dst = field == BFX_STATE_THETA ? s->theta : field == BFX_STATE_MOMENTUM ? s->mom : s->minv;
     if (!dst) return fail(BFX_ERR_STATE, "this sampler does not carry that state");
     if (nbytes != (int64_t)P * C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold P x C floats");
-    CK(copy_rows_h2d(dst, s->Ps, static_cast<const float*>(in), P, C, m->stream));
+    std::vector<float> pad;
+    flat_to_padded(m, static_cast<const float*>(in), C, field == BFX_STATE_MINV ? 1.f : 0.f, pad);
+    CK(cudaMemcpyAsync(dst, pad.data(), pad.size() * 4, cudaMemcpyHostToDevice, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     return BFX_OK;
   }
@@ -782,8 +831,12 @@ int32_t bfx_sampler_step_injected(bfx_sampler* s, const int64_t* idx, int64_t B,
   CKC(launch_mcmc(R, m->cfg, m->stream));
   s->launches += 1;
   s->gstep += 1;
-  if (theta_out) CKC(copy_rows_d2h(theta_out, P, s->theta, s->Ps, C, m->stream));
   CKC(cudaStreamSynchronize(m->stream));
+  if (theta_out) {
+    std::vector<float> pad((size_t)s->Ps * C);
+    CKC(cudaMemcpy(pad.data(), s->theta, pad.size() * 4, cudaMemcpyDeviceToHost));
+    padded_to_flat(m, pad, C, theta_out);
+  }
   cleanup();
   return status_after(s);
 }
@@ -1036,7 +1089,8 @@ int32_t bfx_debug_noise(const bfx_sampler* s, const bfx_run_desc* run, int64_t c
   };
   CKC(cudaMalloc(&d_n, (size_t)P * 4));
   CKC(cudaMalloc(&d_u, 4));
-  CKC(launch_debug_noise(run->seed, (unsigned)(run->chain_offset + chain), (unsigned long long)step, (unsigned)slot, P, d_n, d_u, m->stream));
+  CKC(launch_debug_noise(run->seed, (unsigned)(run->chain_offset + chain), (unsigned long long)step, (unsigned)slot, P,
+                         m->d_flat_pad, d_n, d_u, m->stream));
   CKC(cudaMemcpyAsync(normals_out, d_n, (size_t)P * 4, cudaMemcpyDeviceToHost, m->stream));
   CKC(cudaMemcpyAsync(uniform_out, d_u, 4, cudaMemcpyDeviceToHost, m->stream));
   CKC(cudaStreamSynchronize(m->stream));

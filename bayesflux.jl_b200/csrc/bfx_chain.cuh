@@ -17,9 +17,7 @@ template <int NT, int BT>
 BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
                           const float* __restrict__ y, const BatchSrc& bs, long long B, float nb, bool want_grad,
                           float& gn2) {
-  if (want_grad) {
-    for (int k = threadIdx.x; k < M.S; k += NT) s.g[k] = 0.f;
-  }
+  if (want_grad) for_each_quad<NT>(M, [&](int k) { st4(s.g + k, make_float4(0.f, 0.f, 0.f, 0.f)); });
   const float sl = s.th[M.like_s];
   const float sigma = expf(sl);
   LikeCoef lc;
@@ -90,19 +88,18 @@ BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, f
   float acc[2] = {0.f, 0.f};  // sum theta_net^2, sum g^2
   const float c2 = M.prior_c2;
   const float glike = (float)((double)nb * dlike_ds);
-  const int Pnet = M.Pnet;
-  for_each_param<NT>(M, [&](int J, int k) {
-    float th = s.th[k];
-    float g;
-    if (J < Pnet) {
-      acc[0] += th * th;
-      g = s.g[k] - c2 * th;
-    } else {
-      g = glike;
-    }
+  const int like_q = M.like_s;  // a multiple of 4 by construction: theta_like is element 0 of its own quad
+  for_each_quad<NT>(M, [&](int k) {
+    const unsigned m = s.mask[k >> 2];
+    float4 th = ld4(s.th + k);
+    if (k == like_q) th.x = 0.f;  // theta_like is not a network parameter: no prior term, its gradient is glike
+    acc[0] += th.x * th.x + th.y * th.y + th.z * th.z + th.w * th.w;
     if (want_grad) {
-      s.g[k] = g;
-      acc[1] += g * g;
+      float4 g = mask4(ld4(s.g + k), m);
+      g.x -= c2 * th.x; g.y -= c2 * th.y; g.z -= c2 * th.z; g.w -= c2 * th.w;
+      if (k == like_q) g.x = glike;
+      st4(s.g + k, g);
+      acc[1] += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
     }
   });
   block_sum<NT, 2>(acc, s.red);

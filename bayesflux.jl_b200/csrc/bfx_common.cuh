@@ -92,6 +92,11 @@ struct ModelDev {
   LayerDev L[BFX_MAX_LAYERS];
   SegDesc seg[BFX_MAX_SEGS];
   TcDesc tc;
+  // device tables (uploaded once per model): flat index J -> padded slot, padded slot -> J (-1 = padding),
+  // 4 validity bits per padded quad
+  const int* flat_pad;          // [P]
+  const int* pad_flat;          // [S]
+  const unsigned char* pad_mask;  // [S/4]
 };
 
 // sampler hyper-parameters (device copy of bfx_sampler_desc, see include/bfx.h)
@@ -133,7 +138,7 @@ struct RunDev {
   long long n;
   int C;
   unsigned chain0;  // global id of local chain 0 (noise / permutation keys)
-  // per-chain state, flat layout, row stride Ps floats
+  // per-chain state in the PADDED layout, row stride Ps = M.S floats
   int Ps;
   float* theta;
   float* mom;
@@ -173,7 +178,7 @@ struct EvalDev {
   const float* y;
   long long n;
   int C;
-  const float* theta;  // [C][P]
+  const float* theta;  // [C][P] flat (ABI layout)
   const long long* idx;
   long long idx_chain_stride;
   long long B;

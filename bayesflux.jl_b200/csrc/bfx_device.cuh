@@ -333,52 +333,38 @@ BFX_DEV void rowsum_acc(const float* __restrict__ D, int ldd, float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------
-// flat <-> padded parameter mapping
+// Parameter passes.  Inside the engine every per-parameter vector (theta, g, momentum, Minv, ...)
+// uses the PADDED layout of ModelDev (S floats, a multiple of 4), in shared memory and in HBM
+// alike, so that every element-wise pass is a float4 stream over k = 0, 4, 8, ... < S.
+// Padding slots hold 0 and are kept at 0 through the 4-bit validity mask of each quad
+// (M.pad_mask).  The reference's flat order (the ABI layout) is only touched where values
+// enter or leave the engine, through the tables M.flat_pad / M.pad_flat.
 // ---------------------------------------------------------------------------------
-BFX_DEV int seg_map(const SegDesc& sg, int j /* index inside the segment */) {
-  if (sg.ld == sg.rows) return sg.s_off + j;
-  int i = __float2int_rz(((float)j + 0.5f) * sg.rcp_rows);
-  return sg.s_off + i * sg.ld + (j - i * sg.rows);
-}
-
-// call f(flat index, smem index) for every parameter of the chain
 template <int NT, class F>
-BFX_DEV void for_each_param(const ModelDev& M, F f) {
-  for (int s = 0; s < M.nsegs; ++s) {
-    const SegDesc sg = M.seg[s];
-    for (int j = threadIdx.x; j < sg.count; j += NT) f(sg.flat_off + j, seg_map(sg, j));
-  }
+BFX_DEV void for_each_quad(const ModelDev& M, F f) {
+  for (int k = 4 * threadIdx.x; k < M.S; k += 4 * NT) f(k);
 }
 
-// find the smem index of flat index J, remembering the segment in `hint`
-BFX_DEV int map_flat(const ModelDev& M, int J, int& hint) {
-  while (J >= M.seg[hint].flat_off + M.seg[hint].count) ++hint;
-  while (J < M.seg[hint].flat_off) --hint;
-  return seg_map(M.seg[hint], J - M.seg[hint].flat_off);
-}
-
-// call f(flat index J, smem index k, standard normal z) for every parameter; the normals are
-// either injected (inj[J]) or Philox draws of (key, step, slot)
+// call f(flat index J, padded index k) for every parameter (boundary code only: one table load each)
 template <int NT, class F>
-BFX_DEV void for_each_param_noise(const ModelDev& M, const NoiseKey& key, unsigned long long step, unsigned slot,
-                                  const float* __restrict__ inj, F f) {
-  const int nq = (M.P + 3) >> 2;
-  int hint = 0;
-  for (int q = threadIdx.x; q < nq; q += NT) {
-    float z[4];
-    if (inj) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) z[e] = (4 * q + e < M.P) ? inj[4 * q + e] : 0.f;
-    } else {
-      float4 zz = normal_quad(key, step, slot, (unsigned)q);
-      z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      int J = 4 * q + e;
-      if (J < M.P) f(J, map_flat(M, J, hint), z[e]);
-    }
+BFX_DEV void for_each_flat(const ModelDev& M, F f) {
+  for (int J = threadIdx.x; J < M.P; J += NT) f(J, __ldg(M.flat_pad + J));
+}
+
+BFX_DEV float4 mask4(float4 v, unsigned m) {
+  return make_float4((m & 1u) ? v.x : 0.f, (m & 2u) ? v.y : 0.f, (m & 4u) ? v.z : 0.f, (m & 8u) ? v.w : 0.f);
+}
+
+// the 4 standard normals of padded quad k: Philox draws of (key, step, slot, k/4), or the injected
+// flat-indexed normals inj[J] (parity entry)
+BFX_DEV float4 noise_quad(const ModelDev& M, const NoiseKey& key, unsigned long long step, unsigned slot,
+                          const float* __restrict__ inj, int k) {
+  if (inj) {
+    const int4 J = __ldg(reinterpret_cast<const int4*>(M.pad_flat + k));
+    return make_float4(J.x >= 0 ? inj[J.x] : 0.f, J.y >= 0 ? inj[J.y] : 0.f, J.z >= 0 ? inj[J.z] : 0.f,
+                       J.w >= 0 ? inj[J.w] : 0.f);
   }
+  return normal_quad(key, step, slot, (unsigned)(k >> 2));
 }
 
 // ---------------------------------------------------------------------------------
@@ -397,13 +383,15 @@ struct ChainSmem {
   int* idx;     // [BT]  observation indices of the tile (-1 = masked)
   float* red;   // [32*4] reduction scratch
   double* dacc; // [4]   double accumulators (thread 0)
+  unsigned char* mask;  // [S/4] validity bits of each padded quad (copy of M.pad_mask)
   unsigned char* tc;  // tensor-core region (128-byte aligned) or nullptr
 };
 
 // floats of the CTA working set that precede the tensor-core region
 template <int BT>
 __host__ __device__ inline size_t chain_smem_floats(const ModelDev& M) {
-  return (size_t)2 * M.S + (M.tc.enabled ? 0 : M.act_total) + BT /*ys*/ + BT /*idx*/ + 32 * 4 /*red*/;
+  return (size_t)2 * M.S + (M.tc.enabled ? 0 : M.act_total) + BT /*ys*/ + BT /*idx*/ + 32 * 4 /*red*/ +
+         (size_t)((M.S / 4 + 15) & ~15) / 4 /*mask*/;
 }
 
 template <int BT>
@@ -425,6 +413,7 @@ BFX_DEV ChainSmem carve_smem(const ModelDev& M, unsigned char* base) {
   s.ys = f; f += BT;
   s.idx = reinterpret_cast<int*>(f); f += BT;
   s.red = f; f += 32 * 4;
+  s.mask = reinterpret_cast<unsigned char*>(f); f += ((M.S / 4 + 15) & ~15) / 4;
   s.tc = nullptr;
   if (M.tc.enabled) {
     unsigned long long a = reinterpret_cast<unsigned long long>(f);

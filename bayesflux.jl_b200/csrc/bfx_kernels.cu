@@ -40,6 +40,11 @@ BFX_DEV void make_batch(const RunDev& R, int c, unsigned long long gstep, BatchS
   perm_keys(R.seed, chainkey, epoch, bs.k0, bs.k1);
 }
 
+template <int NT>
+BFX_DEV void load_mask(const ModelDev& M, const ChainSmem& s) {
+  for (int i = threadIdx.x; i < M.S / 4; i += NT) s.mask[i] = __ldg(M.pad_mask + i);
+}
+
 template <int NT, int BT, bool TC>
 __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -51,10 +56,11 @@ __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) 
     tr = tc::region_of(M, s);
     tc::setup<NT>(M, tr);
   }
+  load_mask<NT>(M, s);
   for (int k = threadIdx.x; k < M.S; k += NT) s.th[k] = 0.f;
   __syncthreads();
   const float* th_in = E.theta + (long long)c * M.P;
-  for_each_param<NT>(M, [&](int J, int k) { s.th[k] = th_in[J]; });
+  for_each_flat<NT>(M, [&](int J, int k) { s.th[k] = th_in[J]; });
   __syncthreads();
   BatchSrc bs;
   bs.n = E.n;
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) 
   if (threadIdx.x == 0) E.v_out[c] = v;
   if (E.want_grad) {
     float* g_out = E.g_out + (long long)c * M.P;
-    for_each_param<NT>(M, [&](int J, int k) { g_out[J] = s.g[k]; });
+    for_each_flat<NT>(M, [&](int J, int k) { g_out[J] = s.g[k]; });
   }
   if constexpr (TC) tc::teardown<NT>(M, tr);
 }
@@ -99,9 +105,8 @@ __global__ void __launch_bounds__(NT) k_mcmc(const __grid_constant__ RunDev R) {
   X.thold = R.theta_old ? R.theta_old + row : nullptr;
   X.rmsv = R.rms_v ? R.rms_v + row : nullptr;
   X.ring = R.ring ? R.ring + (long long)c * R.S.ma_windowlength * R.Ps : nullptr;
-  for (int k = threadIdx.x; k < M.S; k += NT) s.th[k] = 0.f;
-  __syncthreads();
-  for_each_param<NT>(M, [&](int J, int k) { s.th[k] = X.th_g[J]; });
+  load_mask<NT>(M, s);
+  for_each_quad<NT>(M, [&](int k) { st4(s.th + k, ld4(X.th_g + k)); });
   __syncthreads();
   for (int it = 0; it < R.nsteps; ++it) {
     if (X.sc.status != 0) break;  // a NaN guard fired: this chain is frozen
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(NT) k_mcmc(const __grid_constant__ RunDev R) {
     if (R.progress && c == 0 && threadIdx.x == 0) *(volatile unsigned long long*)R.progress = X.gstep + 1ull;
   }
   __syncthreads();
-  for_each_param<NT>(M, [&](int J, int k) { X.th_g[J] = s.th[k]; });
+  for_each_quad<NT>(M, [&](int k) { st4(X.th_g + k, ld4(s.th + k)); });
   if (threadIdx.x == 0) R.sc[c] = X.sc;
   if constexpr (TC) tc::teardown<NT>(M, tr);
 }
@@ -131,17 +136,18 @@ __global__ void k_debug_batch(RunDev R, int c, unsigned long long gstep, long lo
     out[j] = batch_obs(bs, j);
 }
 
+// the normal parameter J receives = component (k % 4) of the Philox quad of its padded slot k
 __global__ void k_debug_noise(unsigned long long seed, unsigned chain, unsigned long long gstep, unsigned slot, int P,
-                              float* normals, float* uni) {
+                              const int* flat_pad, float* normals, float* uni) {
   NoiseKey key{seed, chain};
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (4 * q < P) {
-    float4 z = normal_quad(key, gstep, slot, (unsigned)q);
-    float zz[4] = {z.x, z.y, z.z, z.w};
-    for (int e = 0; e < 4; ++e)
-      if (4 * q + e < P) normals[4 * q + e] = z.x * 0.f + zz[e];
+  int J = blockIdx.x * blockDim.x + threadIdx.x;
+  if (J < P) {
+    const int k = flat_pad[J];
+    float4 z = normal_quad(key, gstep, slot, (unsigned)(k >> 2));
+    const int e = k & 3;
+    normals[J] = e == 0 ? z.x : e == 1 ? z.y : e == 2 ? z.z : z.w;
   }
-  if (q == 0) *uni = uniform_draw(key, gstep);
+  if (J == 0) *uni = uniform_draw(key, gstep);
 }
 
 // ---- launchers --------------------------------------------------------------------
@@ -202,9 +208,8 @@ cudaError_t launch_debug_batch(const RunDev& R, int c, unsigned long long gstep,
 }
 
 cudaError_t launch_debug_noise(unsigned long long seed, unsigned chain, unsigned long long gstep, unsigned slot, int P,
-                               float* normals, float* uni, cudaStream_t st) {
-  int nq = (P + 3) / 4;
-  k_debug_noise<<<(nq + 127) / 128, 128, 0, st>>>(seed, chain, gstep, slot, P, normals, uni);
+                               const int* flat_pad, float* normals, float* uni, cudaStream_t st) {
+  k_debug_noise<<<(P + 127) / 128, 128, 0, st>>>(seed, chain, gstep, slot, P, flat_pad, normals, uni);
   return cudaGetLastError();
 }
 

@@ -17,6 +17,6 @@ cudaError_t launch_mcmc(const RunDev& R, const LaunchCfg& cfg, cudaStream_t st);
 cudaError_t launch_debug_batch(const RunDev& R, int c, unsigned long long gstep, long long* out, long long* Bout,
                                cudaStream_t st);
 cudaError_t launch_debug_noise(unsigned long long seed, unsigned chain, unsigned long long gstep, unsigned slot, int P,
-                               float* normals, float* uni, cudaStream_t st);
+                               const int* flat_pad, float* normals, float* uni, cudaStream_t st);
 
 }  // namespace bfx

@@ -15,7 +15,7 @@ struct Ctx {
   int c;  // local chain
   NoiseKey key;
   ChainScalars sc;
-  float* th_g;  // HBM rows of this chain
+  float* th_g;  // HBM rows of this chain (padded layout, S floats each)
   float* mom;
   float* minv;
   float* thold;
@@ -57,23 +57,21 @@ BFX_DEV bool block_any(bool f, float* red) {
 }
 
 // s.samples[:, t] = copy(θ)  (+ DiagCov window ring).  ns = nsampled AFTER the increment.
+// Recorded samples leave the engine in the reference's flat order; the window ring is internal (padded).
 template <int NT, int BT, bool TC>
-BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns, const float* src_global /* nullptr: smem theta */) {
+BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns) {
   const RunDev& R = X.R;
-  float* dst = nullptr;
   if (R.samples && (ns % R.keep_every) == 0) {
     long long slot = ns / R.keep_every - 1 - R.kept_origin;
     if (R.ring_slots > 0) slot %= R.ring_slots;
-    dst = R.samples + (long long)X.c * R.samples_chain_stride + slot * R.M.P;
+    float* dst = R.samples + (long long)X.c * R.samples_chain_stride + slot * R.M.P;
+    const float* th = X.s.th;
+    for_each_flat<NT>(R.M, [&](int J, int k) { dst[J] = th[k]; });
   }
-  float* rdst = nullptr;
-  if (X.ring) rdst = X.ring + ((ns - 1) % R.S.ma_windowlength) * (long long)R.Ps;
-  if (!dst && !rdst) return;
-  for_each_param<NT>(R.M, [&](int J, int k) {
-    float v = src_global ? src_global[J] : X.s.th[k];
-    if (dst) dst[J] = v;
-    if (rdst) rdst[J] = v;
-  });
+  if (X.ring) {
+    float* rdst = X.ring + ((ns - 1) % R.S.ma_windowlength) * (long long)R.Ps;
+    for_each_quad<NT>(R.M, [&](int k) { st4(rdst + k, ld4(X.s.th + k)); });
+  }
 }
 
 // DualAveragingStepSize / ConstantStepsize  (adapters/stepsize/*.jl)
@@ -91,6 +89,24 @@ BFX_DEV float stepsize_adapt(ChainScalars& sc, const SamplerDev& S, float mh_pro
 
 BFX_DEV float mh_prob_of(float lMH) { return (lMH != lMH) ? lMH : fminf(expf(lMH), 1.f); }
 
+#define BFX_Q4(EXPR_X, EXPR_Y, EXPR_Z, EXPR_W) make_float4(EXPR_X, EXPR_Y, EXPR_Z, EXPR_W)
+// apply `expr` (written in terms of component c) to the four components
+#define BFX_MAP4(OUT, expr)            \
+  {                                    \
+    { constexpr int c = 0; OUT.x = expr; } \
+    { constexpr int c = 1; OUT.y = expr; } \
+    { constexpr int c = 2; OUT.z = expr; } \
+    { constexpr int c = 3; OUT.w = expr; } \
+  }
+BFX_DEV float comp(const float4& v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; }
+BFX_DEV float hsum(const float4& v) { return (v.x + v.y) + (v.z + v.w); }
+BFX_DEV float4 ones4() { return make_float4(1.f, 1.f, 1.f, 1.f); }
+// padding slots of an inverse mass vector hold 1 (never 0: they are divided by)
+BFX_DEV float4 mask4_one(float4 v, unsigned m) {
+  return make_float4((m & 1u) ? v.x : 1.f, (m & 2u) ? v.y : 1.f, (m & 4u) ? v.z : 1.f, (m & 8u) ? v.w : 1.f);
+}
+BFX_DEV bool any_nan(const float4& v) { return v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w; }
+
 // madapter(s, θ, bnn, ∇θ) -> Minv (diagonal).  The gradient RMSProp asks for is the one
 // of the current minibatch at the current θ, which is what s.g already holds.
 template <int NT, int BT, bool TC>
@@ -102,12 +118,15 @@ BFX_DEV void mass_adapt(Ctx<NT, BT, TC>& X, float gn2) {
     if (X.sc.ma_t > S.ma_adapt_steps) return;
     const bool first = X.sc.ma_t == 1;
     const float inv_ng = 1.f / sqrtf(gn2);
-    for_each_param<NT>(R.M, [&](int J, int k) {
-      float g = X.s.g[k] * inv_ng;
-      float V = first ? 1.f : X.rmsv[J];
-      V = S.ma_alpha * V + (1.f - S.ma_alpha) * g * g;
-      X.rmsv[J] = V;
-      X.minv[J] = 1.f / (S.ma_lambda + sqrtf(V));
+    for_each_quad<NT>(R.M, [&](int k) {
+      const unsigned m = X.s.mask[k >> 2];
+      const float4 g = ld4(X.s.g + k);
+      const float4 V0 = first ? ones4() : ld4(X.rmsv + k);
+      float4 V, mi;
+      BFX_MAP4(V, S.ma_alpha * comp(V0, c) + (1.f - S.ma_alpha) * (comp(g, c) * inv_ng) * (comp(g, c) * inv_ng));
+      BFX_MAP4(mi, 1.f / (S.ma_lambda + sqrtf(comp(V, c))));
+      st4(X.rmsv + k, mask4(V, m));
+      st4(X.minv + k, mask4_one(mi, m));
     });
     X.sc.ma_t += 1;
   } else if (S.madapter_kind == MA_DIAGCOV) {
@@ -115,21 +134,29 @@ BFX_DEV void mass_adapt(Ctx<NT, BT, TC>& X, float gn2) {
     if (X.sc.ma_t > S.ma_adapt_steps) return;
     const int w = S.ma_windowlength;
     if ((long long)w > X.sc.nsampled) return;
-    for (int J = threadIdx.x; J < R.M.P; J += NT) {
-      float m = 0.f;
-      for (int i = 0; i < w; ++i) m += X.ring[(long long)i * R.Ps + J];
-      m /= (float)w;
-      float v = 0.f;
+    for_each_quad<NT>(R.M, [&](int k) {
+      const unsigned m = X.s.mask[k >> 2];
+      float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int i = 0; i < w; ++i) {
-        float dlt = X.ring[(long long)i * R.Ps + J] - m;
-        v += dlt * dlt;
+        const float4 v = ld4(X.ring + (long long)i * R.Ps + k);
+        mean.x += v.x; mean.y += v.y; mean.z += v.z; mean.w += v.w;
       }
-      v /= (float)(w - 1);
-      X.minv[J] = (1.f - S.ma_kappa) * v + S.ma_kappa + S.ma_epsilon;
-    }
+      const float rw = 1.f / (float)w;
+      mean.x *= rw; mean.y *= rw; mean.z *= rw; mean.w *= rw;
+      float4 var = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < w; ++i) {
+        const float4 v = ld4(X.ring + (long long)i * R.Ps + k);
+        var.x += (v.x - mean.x) * (v.x - mean.x); var.y += (v.y - mean.y) * (v.y - mean.y);
+        var.z += (v.z - mean.z) * (v.z - mean.z); var.w += (v.w - mean.w) * (v.w - mean.w);
+      }
+      const float rv = 1.f / (float)(w - 1);
+      float4 mi;
+      BFX_MAP4(mi, (1.f - S.ma_kappa) * (comp(var, c) * rv) + S.ma_kappa + S.ma_epsilon);
+      st4(X.minv + k, mask4_one(mi, m));
+    });
     X.sc.ma_t += 1;
   }
-  __syncthreads();  // make Minv visible to later passes of this CTA (same-thread mapping differs)
+  __syncthreads();  // make Minv visible to later passes of this CTA
 }
 
 // --------------------------------------------------------------------------------
@@ -145,11 +172,19 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
   const float ha = 0.5f * alpha * clip_scale(gn2, S.maxnorm), sa = sqrtf(alpha);
   float* th = X.s.th;
   const float* g = X.s.g;
-  for_each_param_noise<NT>(X.R.M, X.key, X.gstep, 0, X.inj(0),
-                           [&](int J, int k, float z) { th[k] += ha * g[k] + sa * z; });
+  const float* inj = X.inj(0);
+  for_each_quad<NT>(X.R.M, [&](int k) {
+    const unsigned m = X.s.mask[k >> 2];
+    if (!m) return;
+    const float4 z = noise_quad(X.R.M, X.key, X.gstep, 0, inj, k);
+    const float4 t = ld4(th + k), gg = ld4(g + k);
+    float4 o;
+    BFX_MAP4(o, comp(t, c) + ha * comp(gg, c) + sa * comp(z, c));
+    st4(th + k, mask4(o, m));
+  });
   __syncthreads();
   X.sc.nsampled += 1;
-  record_sample(X, X.sc.t, nullptr);  // samples[:, t] = θ
+  record_sample(X, X.sc.t);  // samples[:, t] = θ
   X.sc.t += 1;
 }
 
@@ -169,15 +204,21 @@ BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
   const float l = S.l, xi = X.sc.xi, cn = sqrtf(l * 2.f * S.A);
   float* th = X.s.th;
   const float* g = X.s.g;
+  const float* inj = X.inj(0);
   float acc[2] = {0.f, 0.f};  // p'p, nan flag
-  for_each_param_noise<NT>(R.M, X.key, X.gstep, 0, X.inj(0), [&](int J, int k, float z) {
-    float p = X.mom[J];
-    p = p - xi * l * p + l * g[k] + cn * z;  // g here is +∇, the reference's g is -∇
-    X.mom[J] = p;
-    float t = th[k] + l * p;
-    th[k] = t;
-    acc[0] += p * p;
-    acc[1] += (t != t) ? 1.f : 0.f;
+  for_each_quad<NT>(R.M, [&](int k) {
+    const unsigned m = X.s.mask[k >> 2];
+    if (!m) return;
+    const float4 z = noise_quad(R.M, X.key, X.gstep, 0, inj, k);
+    const float4 p0 = ld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
+    float4 p, t;
+    BFX_MAP4(p, comp(p0, c) - xi * l * comp(p0, c) + l * comp(gg, c) + cn * comp(z, c));  // g here is +∇, the reference's g is -∇
+    p = mask4(p, m);
+    BFX_MAP4(t, comp(t0, c) + l * comp(p, c));
+    st4(X.mom + k, p);
+    st4(th + k, t);
+    acc[0] += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
+    acc[1] += any_nan(t) ? 1.f : 0.f;
   });
   block_sum<NT, 2>(acc, X.s.red);
   const float kin = acc[0] / (float)R.M.P;
@@ -190,7 +231,7 @@ BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
     return;
   }
   X.sc.nsampled += 1;
-  record_sample(X, X.sc.t, nullptr);
+  record_sample(X, X.sc.t);
   X.sc.t += 1;
 }
 
@@ -212,14 +253,21 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
   const float l = S.l, hl = 0.5f * l, n = (float)R.M.P;
   float* th = X.s.th;
   const float* g = X.s.g;
+  const float* inj = X.inj(0);
   float acc[2] = {0.f, 0.f};
   // B half kick + A half drift, accumulate p' Minv p   (:95-97)
-  for_each_param<NT>(R.M, [&](int J, int k) {
-    float mi = um ? X.minv[J] : 1.f;
-    float p = X.mom[J] + hl * g[k];
-    X.mom[J] = p;
-    th[k] += hl * mi * p;
-    acc[0] += p * p * mi;
+  for_each_quad<NT>(R.M, [&](int k) {
+    const unsigned m = X.s.mask[k >> 2];
+    if (!m) return;
+    const float4 mi = um ? ld4(X.minv + k) : ones4();
+    const float4 p0 = ld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
+    float4 p, t;
+    BFX_MAP4(p, comp(p0, c) + hl * comp(gg, c));
+    p = mask4(p, m);
+    BFX_MAP4(t, comp(t0, c) + hl * comp(mi, c) * comp(p, c));
+    st4(X.mom + k, p);
+    st4(th + k, t);
+    acc[0] += p.x * p.x * mi.x + p.y * p.y * mi.y + p.z * p.z * mi.z + p.w * p.w * mi.w;
   });
   block_sum<NT, 2>(acc, X.s.red);
   float xi = X.sc.xi + l / (2.f * S.mu) * (acc[0] - n);
@@ -234,14 +282,20 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
   acc[0] = 0.f;
   acc[1] = 0.f;
   // O step with noise ~ N(0, M), second A half drift  (:98-104)
-  for_each_param_noise<NT>(R.M, X.key, X.gstep, 0, X.inj(0), [&](int J, int k, float z) {
-    float mi = um ? X.minv[J] : 1.f;
-    float p = e1 * X.mom[J] + sc * rsqrtf(mi) * z;
-    X.mom[J] = p;
-    float t = th[k] + hl * mi * p;
-    th[k] = t;
-    acc[0] += p * p * mi;
-    acc[1] += (t != t) ? 1.f : 0.f;
+  for_each_quad<NT>(R.M, [&](int k) {
+    const unsigned m = X.s.mask[k >> 2];
+    if (!m) return;
+    const float4 z = noise_quad(R.M, X.key, X.gstep, 0, inj, k);
+    const float4 mi = um ? ld4(X.minv + k) : ones4();
+    const float4 p0 = ld4(X.mom + k), t0 = ld4(th + k);
+    float4 p, t;
+    BFX_MAP4(p, e1 * comp(p0, c) + sc * rsqrtf(comp(mi, c)) * comp(z, c));
+    p = mask4(p, m);
+    BFX_MAP4(t, comp(t0, c) + hl * comp(mi, c) * comp(p, c));
+    st4(X.mom + k, p);
+    st4(th + k, t);
+    acc[0] += p.x * p.x * mi.x + p.y * p.y * mi.y + p.z * p.z * mi.z + p.w * p.w * mi.w;
+    acc[1] += any_nan(t) ? 1.f : 0.f;
   });
   block_sum<NT, 2>(acc, X.s.red);
   X.sc.xi = xi + l / (2.f * S.mu) * (acc[0] - n);
@@ -252,7 +306,7 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
   if (R.kinetic_out && threadIdx.x == 0)
     R.kinetic_out[(long long)X.c * R.hist_stride + (X.sc.t - 1 - R.hist_origin)] = acc[0] / n;
   X.sc.nsampled += 1;
-  record_sample(X, X.sc.t, nullptr);
+  record_sample(X, X.sc.t);
   X.sc.t += 1;
 }
 
@@ -273,7 +327,7 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
   if (X.sc.current_step == 1) {
     X.sc.lMH = (float)(-X.full_lp());  // :146-148
     // θ at the start of the window = samples[:, nsampled - steps] on a later reject
-    for_each_param<NT>(R.M, [&](int J, int k) { X.thold[J] = th[k]; });
+    for_each_quad<NT>(R.M, [&](int k) { st4(X.thold + k, ld4(th + k)); });
   }
   float gn2;
   X.grad(gn2);
@@ -282,16 +336,26 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
   const float sa = sqrtf(a), s1a = sqrtf(1.f - a), hh = 0.5f * h;
   const bool um = X.uses_minv();
   float acc[2] = {0.f, 0.f};  // K(m14)*2, nan
-  for_each_param_noise<NT>(R.M, X.key, X.gstep, 0, X.inj(0), [&](int J, int k, float z) {
-    float mi = um ? X.minv[J] : 1.f;
-    float m14 = sa * X.mom[J] + s1a * rsqrtf(mi) * z;  // Mhalf = chol(inv(Minv)) = 1/sqrt(Minv)
-    float m12 = m14 + hh * cs * g[k];                  // reference g = -∇
-    X.mom[J] = m12;
-    float t = th[k] + h * mi * m12;
-    th[k] = t;
-    acc[0] += m14 * m14 * mi;
-    acc[1] += (t != t) ? 1.f : 0.f;
-  });
+  {
+    const float* inj = X.inj(0);
+    for_each_quad<NT>(R.M, [&](int k) {
+      const unsigned m = X.s.mask[k >> 2];
+      if (!m) return;
+      const float4 z = noise_quad(R.M, X.key, X.gstep, 0, inj, k);
+      const float4 mi = um ? ld4(X.minv + k) : ones4();
+      const float4 m0 = ld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
+      float4 m14, m12, t;
+      BFX_MAP4(m14, sa * comp(m0, c) + s1a * rsqrtf(comp(mi, c)) * comp(z, c));  // Mhalf = chol(inv(Minv)) = 1/sqrt(Minv)
+      m14 = mask4(m14, m);
+      BFX_MAP4(m12, comp(m14, c) + hh * cs * comp(gg, c));  // reference g = -∇
+      m12 = mask4(m12, m);
+      BFX_MAP4(t, comp(t0, c) + h * comp(mi, c) * comp(m12, c));
+      st4(X.mom + k, m12);
+      st4(th + k, t);
+      acc[0] += m14.x * m14.x * mi.x + m14.y * m14.y * mi.y + m14.z * m14.z * mi.z + m14.w * m14.w * mi.w;
+      acc[1] += any_nan(t) ? 1.f : 0.f;
+    });
+  }
   block_sum<NT, 2>(acc, X.s.red);
   if (acc[1] > 0.f) {
     X.sc.status = 5;
@@ -301,17 +365,27 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
   X.grad(gn2);  // same minibatch, new θ  (:164-166)
   cs = clip_scale(gn2, S.maxnorm);
   acc[0] = 0.f;
-  for_each_param_noise<NT>(R.M, X.key, X.gstep, 1, X.inj(1), [&](int J, int k, float z) {
-    float mi = um ? X.minv[J] : 1.f;
-    float m34 = X.mom[J] + hh * cs * g[k];
-    X.mom[J] = sa * m34 + s1a * rsqrtf(mi) * z;
-    acc[0] += m34 * m34 * mi;
-  });
+  {
+    const float* inj = X.inj(1);
+    for_each_quad<NT>(R.M, [&](int k) {
+      const unsigned m = X.s.mask[k >> 2];
+      if (!m) return;
+      const float4 z = noise_quad(R.M, X.key, X.gstep, 1, inj, k);
+      const float4 mi = um ? ld4(X.minv + k) : ones4();
+      const float4 m0 = ld4(X.mom + k), gg = ld4(g + k);
+      float4 m34, mn;
+      BFX_MAP4(m34, comp(m0, c) + hh * cs * comp(gg, c));
+      m34 = mask4(m34, m);
+      BFX_MAP4(mn, sa * comp(m34, c) + s1a * rsqrtf(comp(mi, c)) * comp(z, c));
+      st4(X.mom + k, mask4(mn, m));
+      acc[0] += m34.x * m34.x * mi.x + m34.y * m34.y * mi.y + m34.z * m34.z * mi.z + m34.w * m34.w * mi.w;
+    });
+  }
   block_sum<NT, 2>(acc, X.s.red);
   X.sc.lMH += 0.5f * acc[0] - K14;  // :171
   X.sc.nsampled += 1;
   const long long ns = X.sc.nsampled;
-  record_sample(X, ns, nullptr);  // samples[:, t] with t == nsampled for GGMC
+  record_sample(X, ns);  // samples[:, t] with t == nsampled for GGMC
   if (X.sc.current_step == S.steps && X.sc.t > S.steps) {
     __syncthreads();
     X.sc.lMH += (float)X.full_lp();  // :176
@@ -328,9 +402,9 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
       X.sc.accepted_total += S.steps;
     } else {
       __syncthreads();
-      for_each_param<NT>(R.M, [&](int J, int k) { th[k] = X.thold[J]; });
+      for_each_quad<NT>(R.M, [&](int k) { st4(th + k, ld4(X.thold + k)); });
       __syncthreads();
-      for (int j = 0; j < S.steps; ++j) record_sample(X, ns - j, nullptr);
+      for (int j = 0; j < S.steps; ++j) record_sample(X, ns - j);
     }
   }
   X.sc.t += 1;
@@ -354,17 +428,26 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
     // -loglikeprior(θold) and logpdf(moment_dist, pold) are evaluated here, while θ == θold.
     X.sc.start_lp = X.full_lp();
     float acc[1] = {0.f};
-    for_each_param_noise<NT>(R.M, X.key, X.gstep, 0, X.inj(0), [&](int J, int k, float z) {
-      float mi = um ? X.minv[J] : 1.f;
-      float p = sqrtf(mi) * z;
-      X.mom[J] = p;
-      X.thold[J] = th[k];
-      acc[0] += p * p / mi;
+    const float* inj = X.inj(0);
+    for_each_quad<NT>(R.M, [&](int k) {
+      const unsigned m = X.s.mask[k >> 2];
+      st4(X.thold + k, ld4(th + k));
+      if (!m) return;
+      const float4 z = noise_quad(R.M, X.key, X.gstep, 0, inj, k);
+      const float4 mi = um ? ld4(X.minv + k) : ones4();
+      float4 p;
+      BFX_MAP4(p, sqrtf(comp(mi, c)) * comp(z, c));
+      p = mask4(p, m);
+      st4(X.mom + k, p);
+      acc[0] += p.x * p.x / mi.x + p.y * p.y / mi.y + p.z * p.z / mi.z + p.w * p.w / mi.w;
     });
     block_sum<NT, 1>(acc, X.s.red);
     X.sc.lMH = 0.5f * acc[0];  // -logpdf(moment_dist, pold) up to the constant that cancels
   } else {
-    for_each_param<NT>(R.M, [&](int J, int k) { th[k] += l * X.mom[J]; });  // :124,128
+    for_each_quad<NT>(R.M, [&](int k) {  // :124,128
+      const float4 t0 = ld4(th + k), p = ld4(X.mom + k);
+      st4(th + k, make_float4(t0.x + l * p.x, t0.y + l * p.y, t0.z + l * p.z, t0.w + l * p.w));
+    });
   }
   __syncthreads();
   float gn2;
@@ -372,14 +455,19 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
   const float hk = 0.5f * l * clip_scale(gn2, S.maxnorm);
   const bool last = stage == S.path_len;
   float acc[1] = {0.f};
-  for_each_param<NT>(R.M, [&](int J, int k) {
-    float p = X.mom[J] + hk * g[k];  // momentum .-= l*(-∇)/2
+  for_each_quad<NT>(R.M, [&](int k) {
+    const unsigned m = X.s.mask[k >> 2];
+    if (!m) return;
+    const float4 p0 = ld4(X.mom + k), gg = ld4(g + k);
+    float4 p;
+    BFX_MAP4(p, comp(p0, c) + hk * comp(gg, c));  // momentum .-= l*(-∇)/2
+    p = mask4(p, m);
     if (last) {
-      p = -p;  // :133
-      float mi = um ? X.minv[J] : 1.f;
-      acc[0] += p * p / mi;
+      p = make_float4(-p.x, -p.y, -p.z, -p.w);  // :133
+      const float4 mi = um ? ld4(X.minv + k) : ones4();
+      acc[0] += p.x * p.x / mi.x + p.y * p.y / mi.y + p.z * p.z / mi.z + p.w * p.w / mi.w;
     }
-    X.mom[J] = p;
+    st4(X.mom + k, p);
   });
   if (last) {
     block_sum<NT, 1>(acc, X.s.red);
@@ -397,11 +485,11 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
       X.sc.accepted_total += 1;
     } else {
       __syncthreads();
-      for_each_param<NT>(R.M, [&](int J, int k) { th[k] = X.thold[J]; });
+      for_each_quad<NT>(R.M, [&](int k) { st4(th + k, ld4(X.thold + k)); });
       __syncthreads();
     }
     X.sc.nsampled = ns;
-    record_sample(X, ns, nullptr);
+    record_sample(X, ns);
   }
   X.sc.current_step = last ? 1 : stage + 1;
   X.sc.t += 1;
