@@ -17,6 +17,8 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "bfx_chain.cuh"
 
 namespace bfx {
@@ -89,14 +91,43 @@ BFX_DEV void ld_16x256b_x1(uint32_t taddr, float (&v)[4]) {
 }
 
 // BF16 split of two adjacent values: hi word = {bf16(a), bf16(b)}, lo word = the residuals
-BFX_DEV void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-}
 BFX_DEV float bf16lo_to_f(uint32_t w) { return __uint_as_float(w << 16); }
 BFX_DEV float bf16hi_to_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+BFX_DEV uint32_t pack_bf16x2(float lo_elem, float hi_elem) {  // one cvt.rn.bf16x2.f32
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+BFX_DEV void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  lo = pack_bf16x2(a - bf16lo_to_f(hi), b - bf16hi_to_f(hi));
+}
+
+// activation dispatch hoisted out of the element loops
+template <int A>
+struct ActT {
+  static BFX_DEV float f(float z) {
+    if (A == A_RELU) return fmaxf(z, 0.f);
+    if (A == A_TANH) return tanhf(z);
+    if (A == A_SIGMOID) return 1.f / (1.f + expf(-z));
+    return z;
+  }
+  static BFX_DEV float d(float o) {  // derivative from the output
+    if (A == A_RELU) return o > 0.f ? 1.f : 0.f;
+    if (A == A_TANH) return 1.f - o * o;
+    if (A == A_SIGMOID) return o * (1.f - o);
+    return 1.f;
+  }
+};
+template <class F>
+BFX_DEV void with_act(int act, F f) {
+  switch (act) {
+    case A_RELU: f(ActT<A_RELU>{}); break;
+    case A_TANH: f(ActT<A_TANH>{}); break;
+    case A_SIGMOID: f(ActT<A_SIGMOID>{}); break;
+    default: f(ActT<A_IDENTITY>{}); break;
+  }
+}
 
 struct Region {
   unsigned char* base;  // 128-byte aligned tensor-core region
@@ -291,19 +322,22 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       const bool active = 32 * h < L.hout;
       if (active) ld_16x256b_x4(zaddr + (uint32_t)(32 * h), a);
       const int cbase = 32 * h + 2 * (lane & 3);
+      with_act(D.act, [&](auto A) {
+        using AT = decltype(A);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = cbase + 8 * j;
-        if (active && c < L.hout) {
-          const float2 bb = *reinterpret_cast<const float2*>(s.th + D.b_s + c);
-          a[4 * j + 0] = act_apply(D.act, a[4 * j + 0] + bb.x);
-          a[4 * j + 1] = act_apply(D.act, a[4 * j + 1] + bb.y);
-          a[4 * j + 2] = act_apply(D.act, a[4 * j + 2] + bb.x);
-          a[4 * j + 3] = act_apply(D.act, a[4 * j + 3] + bb.y);
-        } else {
-          a[4 * j + 0] = a[4 * j + 1] = a[4 * j + 2] = a[4 * j + 3] = 0.f;
+        for (int j = 0; j < 4; ++j) {
+          const int c = cbase + 8 * j;
+          if (active && c < L.hout) {
+            const float2 bb = *reinterpret_cast<const float2*>(s.th + D.b_s + c);
+            a[4 * j + 0] = AT::f(a[4 * j + 0] + bb.x);
+            a[4 * j + 1] = AT::f(a[4 * j + 1] + bb.y);
+            a[4 * j + 2] = AT::f(a[4 * j + 2] + bb.x);
+            a[4 * j + 3] = AT::f(a[4 * j + 3] + bb.y);
+          } else {
+            a[4 * j + 0] = a[4 * j + 1] = a[4 * j + 2] = a[4 * j + 3] = 0.f;
+          }
         }
-      }
+      });
       if (l + 1 < nh) {
         // next layer's input tile
         const TcLayer& Ln = T.L[l + 1];
@@ -417,22 +451,25 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         const int act_l = M.L[nh - 1].act;
         unsigned char* hi = R.base + T.d_off;
         unsigned char* lo = hi + T.d_bytes;
+        const int offb = (r0 >> 3) * 1024 + (r0 & 7) * 16 + (lane & 3) * 4 + h * 512;
+        with_act(act_l, [&](auto A) {
+          using AT = decltype(A);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = cbase + 8 * j;
-          const float d00 = dl0 * wl[2 * j] * act_deriv_from_out(act_l, a[4 * j + 0]);
-          const float d01 = dl0 * wl[2 * j + 1] * act_deriv_from_out(act_l, a[4 * j + 1]);
-          const float d10 = dl1 * wl[2 * j] * act_deriv_from_out(act_l, a[4 * j + 2]);
-          const float d11 = dl1 * wl[2 * j + 1] * act_deriv_from_out(act_l, a[4 * j + 3]);
-          uint32_t h0, l0, h1, l1;
-          split2(d00, d01, h0, l0);
-          split2(d10, d11, h1, l1);
-          const int off0 = (r0 >> 3) * 1024 + (c >> 3) * 128 + (r0 & 7) * 16 + (c & 7) * 2;
-          *reinterpret_cast<uint32_t*>(hi + off0) = h0;
-          *reinterpret_cast<uint32_t*>(lo + off0) = l0;
-          *reinterpret_cast<uint32_t*>(hi + off0 + 1024) = h1;
-          *reinterpret_cast<uint32_t*>(lo + off0 + 1024) = l1;
-        }
+          for (int j = 0; j < 4; ++j) {
+            const float d00 = dl0 * wl[2 * j] * AT::d(a[4 * j + 0]);
+            const float d01 = dl0 * wl[2 * j + 1] * AT::d(a[4 * j + 1]);
+            const float d10 = dl1 * wl[2 * j] * AT::d(a[4 * j + 2]);
+            const float d11 = dl1 * wl[2 * j + 1] * AT::d(a[4 * j + 3]);
+            uint32_t h0, l0, h1, l1;
+            split2(d00, d01, h0, l0);
+            split2(d10, d11, h1, l1);
+            const int off0 = offb + j * 128;  // column 32h + 8j + 2(lane%4): chunk 4h + j, 2 bytes per column
+            *reinterpret_cast<uint32_t*>(hi + off0) = h0;
+            *reinterpret_cast<uint32_t*>(lo + off0) = l0;
+            *reinterpret_cast<uint32_t*>(hi + off0 + 1024) = h1;
+            *reinterpret_cast<uint32_t*>(lo + off0 + 1024) = l1;
+          }
+        });
       }
       fence_async_smem();
       fence_before();
@@ -477,33 +514,38 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           const unsigned char* ahi = R.base + L.a_off;
           const unsigned char* alo = ahi + L.a_bytes;
           uint32_t oh[8], ol[8];
+          const int offa = (r0 >> 3) * sbo + (r0 & 7) * 16 + (lane & 3) * 4 + h * 512;
+          with_act(act_p, [&](auto A) {
+            using AT = decltype(A);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = cbase + 8 * j;
-            oh[2 * j] = ol[2 * j] = oh[2 * j + 1] = ol[2 * j + 1] = 0u;
-            if (active && c < hp) {
-              const int off0 = (r0 >> 3) * sbo + (c >> 3) * 128 + (r0 & 7) * 16 + (c & 7) * 2;
-              const uint32_t h0 = *reinterpret_cast<const uint32_t*>(ahi + off0);
-              const uint32_t l0 = *reinterpret_cast<const uint32_t*>(alo + off0);
-              const uint32_t h1 = *reinterpret_cast<const uint32_t*>(ahi + off0 + sbo);
-              const uint32_t l1 = *reinterpret_cast<const uint32_t*>(alo + off0 + sbo);
-              const float a00 = bf16lo_to_f(h0) + bf16lo_to_f(l0), a01 = bf16hi_to_f(h0) + bf16hi_to_f(l0);
-              const float a10 = bf16lo_to_f(h1) + bf16lo_to_f(l1), a11 = bf16hi_to_f(h1) + bf16hi_to_f(l1);
-              split2(da[4 * j + 0] * act_deriv_from_out(act_p, a00), da[4 * j + 1] * act_deriv_from_out(act_p, a01),
-                     oh[2 * j], ol[2 * j]);
-              split2(da[4 * j + 2] * act_deriv_from_out(act_p, a10), da[4 * j + 3] * act_deriv_from_out(act_p, a11),
-                     oh[2 * j + 1], ol[2 * j + 1]);
+            for (int j = 0; j < 4; ++j) {
+              const int c = cbase + 8 * j;
+              oh[2 * j] = ol[2 * j] = oh[2 * j + 1] = ol[2 * j + 1] = 0u;
+              if (active && c < hp) {
+                const int off0 = offa + j * 128;
+                const uint32_t h0 = *reinterpret_cast<const uint32_t*>(ahi + off0);
+                const uint32_t h1 = *reinterpret_cast<const uint32_t*>(ahi + off0 + sbo);
+                float a00 = bf16lo_to_f(h0), a01 = bf16hi_to_f(h0), a10 = bf16lo_to_f(h1), a11 = bf16hi_to_f(h1);
+                if (!std::is_same<AT, ActT<A_RELU>>::value && !std::is_same<AT, ActT<A_IDENTITY>>::value) {
+                  // tanh / sigmoid derivatives need the full-precision output: add the lo half
+                  const uint32_t l0 = *reinterpret_cast<const uint32_t*>(alo + off0);
+                  const uint32_t l1 = *reinterpret_cast<const uint32_t*>(alo + off0 + sbo);
+                  a00 += bf16lo_to_f(l0); a01 += bf16hi_to_f(l0); a10 += bf16lo_to_f(l1); a11 += bf16hi_to_f(l1);
+                }
+                split2(da[4 * j + 0] * AT::d(a00), da[4 * j + 1] * AT::d(a01), oh[2 * j], ol[2 * j]);
+                split2(da[4 * j + 2] * AT::d(a10), da[4 * j + 3] * AT::d(a11), oh[2 * j + 1], ol[2 * j + 1]);
+              }
             }
-          }
+          });
           // the dW MMAs of layer l still read the D tile: wait for them before overwriting it
           mbar_wait(&R.bar[2], R.par[2]);
           R.par[2] ^= 1;
           unsigned char* hi = R.base + T.d_off;
           unsigned char* lo = hi + T.d_bytes;
+          const int offd = (r0 >> 3) * 1024 + (r0 & 7) * 16 + (lane & 3) * 4 + h * 512;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int c = cbase + 8 * j;
-            const int off0 = (r0 >> 3) * 1024 + (c >> 3) * 128 + (r0 & 7) * 16 + (c & 7) * 2;
+            const int off0 = offd + j * 128;
             *reinterpret_cast<uint32_t*>(hi + off0) = oh[2 * j];
             *reinterpret_cast<uint32_t*>(lo + off0) = ol[2 * j];
             *reinterpret_cast<uint32_t*>(hi + off0 + 1024) = oh[2 * j + 1];
@@ -534,12 +576,20 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         float v[4];
         ld_16x256b_x1(zaddr + (uint32_t)(L.dw_col + 8 * gq), v);
         const int c = 8 * gq + 2 * (lane & 3);
+        if (8 * gq + 8 <= D.nin && D.nout == 64) {  // group fully inside the weight matrix: no bounds checks
+          float* gp = s.g + D.w_s + c * D.ldw + r0;
+          gp[0] = v[0];
+          gp[D.ldw] = v[1];
+          gp[8] = v[2];
+          gp[D.ldw + 8] = v[3];
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int o = (e & 2) ? r1 : r0, cc = c + (e & 1);
-          if (o < D.nout) {
-            if (cc < D.nin) s.g[D.w_s + cc * D.ldw + o] = v[e];
-            else if (cc == L.kpad) s.g[D.b_s + o] = v[e];
+          for (int e = 0; e < 4; ++e) {
+            const int o = (e & 2) ? r1 : r0, cc = c + (e & 1);
+            if (o < D.nout) {
+              if (cc < D.nin) s.g[D.w_s + cc * D.ldw + o] = v[e];
+              else if (cc == L.kpad) s.g[D.b_s + o] = v[e];
+            }
           }
         }
       }
