@@ -55,6 +55,8 @@ struct bfx_model {
   // flat (ABI) <-> padded (engine) parameter layout
   std::vector<int> flat_pad, pad_flat;
   std::vector<unsigned char> pad_mask;
+  float* scratch = nullptr;  // recurrent path: per-CTA per-step records
+  size_t scratch_ctas = 0;
   int* d_flat_pad = nullptr;
   int* d_pad_flat = nullptr;
   unsigned char* d_pad_mask = nullptr;
@@ -200,8 +202,11 @@ static int32_t build_model_dev(bfx_model* m, const bfx_like_desc* like, const bf
   // launch shape: tiny nets get one warp per chain, wide ones 256 threads
   int max_rows = 0;
   for (int l = 0; l < nl; ++l) max_rows = std::max(max_rows, M.L[l].nout_pad);
-  if (M.rec_layer >= 0) return fail(BFX_ERR_UNSUPPORTED, "recurrent layers: kernel not built in this version");
-  if (max_rows >= 48)
+  if (M.rec_layer >= 0) {
+    if (nl < 2 || M.L[1].kind != L_DENSE)
+      return fail(BFX_ERR_UNSUPPORTED, "a recurrent layer must be followed by a Dense head");
+    m->cfg = LaunchCfg{256, 16};  // 16 sequences per tile: the per-step records of a tile stay small (L2 resident)
+  } else if (max_rows >= 48)
     m->cfg = LaunchCfg{256, 64};
   else if (max_rows >= 16)
     m->cfg = LaunchCfg{128, 64};
@@ -213,9 +218,20 @@ static int32_t build_model_dev(bfx_model* m, const bfx_like_desc* like, const bf
   M.act_off[0] = 0;
   off = M.act_rows[0] * LDB;
   for (int l = 0; l < nl; ++l) {
-    M.act_rows[l + 1] = M.L[l].nout_pad;
+    // the output of a recurrent layer is h (H rows), not its gate block
+    const int rows = M.L[l].kind == L_DENSE ? M.L[l].nout_pad : round4(M.L[l].H);
+    M.act_rows[l + 1] = rows;
     M.act_off[l + 1] = off;
-    off += M.L[l].nout_pad * LDB;
+    off += rows * LDB;
+  }
+  if (M.rec_layer >= 0) {
+    const int hp = round4(M.L[0].H) * LDB;
+    M.rec_hp = off; off += hp;
+    M.rec_c = off; off += hp;
+    M.rec_dc = off; off += hp;
+    M.rec_cp = off; off += hp;
+    M.rec_g = off; off += M.L[0].nout_pad * LDB;
+    M.rec_rows = M.L[0].kind == L_LSTM ? 6 * M.L[0].H : M.L[0].H;
   }
   M.act_total = off;
   if (smallp_smem_bytes(M, m->cfg.bt) > kMaxSmem)
@@ -343,6 +359,10 @@ int32_t bfx_model_destroy(bfx_model* m) {
     if (m->y) cudaFree(m->y);
     if (m->stream) cudaStreamDestroy(m->stream);
   }
+  if (m->scratch) {
+    cudaSetDevice(m->device);
+    cudaFree(m->scratch);
+  }
   if (m->d_flat_pad) {
     cudaSetDevice(m->device);
     cudaFree(m->d_flat_pad);
@@ -384,6 +404,27 @@ static int32_t ensure_stream(bfx_model* m) {
   return BFX_OK;
 }
 
+// recurrent path: scratch for `ctas` concurrently launched CTAs (T per-step records of one tile each)
+static int32_t ensure_scratch(bfx_model* m, size_t ctas, float** out, long long* stride) {
+  *out = nullptr;
+  *stride = 0;
+  if (m->M.rec_layer < 0) return BFX_OK;
+  const long long st = (long long)m->M.T * m->M.rec_rows * m->cfg.bt;
+  if (ctas > m->scratch_ctas) {
+    if (m->scratch) {
+      CK(cudaStreamSynchronize(m->stream));
+      CK(cudaFree(m->scratch));
+      m->scratch = nullptr;
+      m->scratch_ctas = 0;
+    }
+    CK(cudaMalloc(&m->scratch, (size_t)st * ctas * sizeof(float)));
+    m->scratch_ctas = ctas;
+  }
+  *out = m->scratch;
+  *stride = st;
+  return BFX_OK;
+}
+
 // host-side layout conversion of per-parameter state: flat P x C (ABI)  <->  padded C rows of S floats
 static void flat_to_padded(const bfx_model* m, const float* flat, int C, float fill, std::vector<float>& out) {
   const int P = m->M.P, S = m->M.S;
@@ -421,6 +462,11 @@ static int32_t set_data_impl(bfx_model* m, const float* x, const int64_t* dims, 
   m->n = n;
   m->M.seq = ndims == 3;
   m->M.T = ndims == 3 ? (int)dims[0] : 1;
+  m->scratch_ctas = 0;  // the scratch stride depends on T: force a re-allocation
+  if (m->scratch) {
+    cudaFree(m->scratch);
+    m->scratch = nullptr;
+  }
   return BFX_OK;
 }
 
@@ -490,6 +536,13 @@ static int32_t eval_impl(bfx_model* m, const float* theta, int32_t C, const int6
   E.want_grad = g_out ? 1 : 0;
   E.v_out = d_v;
   E.g_out = d_g;
+  {
+    int32_t sst = ensure_scratch(m, (size_t)C, &E.scratch, &E.scratch_stride);
+    if (sst) {
+      cleanup();
+      return sst;
+    }
+  }
   CKC(launch_eval(E, m->cfg, m->stream));
   CKC(cudaMemcpyAsync(v_out, d_v, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   if (g_out) CKC(cudaMemcpyAsync(g_out, d_g, (size_t)C * P * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
@@ -747,8 +800,14 @@ int32_t bfx_sampler_set_state(bfx_sampler* s, int32_t field, const void* in, int
   return BFX_OK;
 }
 
-static void fill_run_common(bfx_sampler* s, RunDev& R) {
+static int32_t fill_run_common(bfx_sampler* s, RunDev& R) {
   bfx_model* m = s->m;
+  {
+    float* scr;
+    long long stride;
+    int32_t st = ensure_scratch(m, (size_t)s->C, &scr, &stride);
+    if (st) return st;
+  }
   R.M = m->M;
   R.S = s->S;
   R.x = m->x;
@@ -766,6 +825,9 @@ static void fill_run_common(bfx_sampler* s, RunDev& R) {
   R.sc = s->sc;
   R.keep_every = 1;
   R.progress = nullptr;
+  R.scratch = m->scratch;
+  R.scratch_stride = (long long)m->M.T * m->M.rec_rows * m->cfg.bt;
+  return BFX_OK;
 }
 
 static int ndraws_of(int kind) { return kind == BFX_GGMC ? 2 : 1; }
@@ -816,7 +878,13 @@ int32_t bfx_sampler_step_injected(bfx_sampler* s, const int64_t* idx, int64_t B,
     CKC(cudaMemcpyAsync(d_u, uniforms, (size_t)C * 4, cudaMemcpyHostToDevice, m->stream));
   }
   RunDev R{};
-  fill_run_common(s, R);
+  {
+    int32_t fst = fill_run_common(s, R);
+    if (fst) {
+      cleanup();
+      return fst;
+    }
+  }
   R.B = B;
   R.nb = 1;
   R.num_batches = num_batches;
@@ -861,7 +929,10 @@ int32_t bfx_mcmc_num_kept(const bfx_sampler* s, const bfx_run_desc* run, int64_t
 static int32_t prepare_schedule(bfx_sampler* s, const bfx_run_desc* run, RunDev& R) {
   bfx_model* m = s->m;
   if (!m->x) return fail(BFX_ERR_NO_DATA, "bfx_model_set_data has not been called");
-  fill_run_common(s, R);
+  {
+    int32_t fst = fill_run_common(s, R);
+    if (fst) return fst;
+  }
   R.B = run->batchsize < m->n ? run->batchsize : m->n;
   R.nb = run->partial ? (m->n + R.B - 1) / R.B : m->n / R.B;  // length(DataLoader)
   if (R.nb < 1) R.nb = 1;

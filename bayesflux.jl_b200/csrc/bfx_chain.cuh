@@ -28,7 +28,8 @@ BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __
   for (long long t0 = 0; t0 < B; t0 += BT) {
     int nvalid = (int)((B - t0) < (long long)BT ? (B - t0) : (long long)BT);
     float sums[2] = {0.f, 0.f};
-    mlp_tile<NT, BT>(M, s, x, y, bs, t0, nvalid, lc, want_grad, sums);
+    if (M.rec_layer >= 0) rec_tile<NT, BT>(M, s, x, y, bs, t0, nvalid, lc, want_grad, sums);
+    else mlp_tile<NT, BT>(M, s, x, y, bs, t0, nvalid, lc, want_grad, sums);
     ds0 += (double)sums[0];
     ds1 += (double)sums[1];
     __syncthreads();

@@ -89,6 +89,8 @@ struct ModelDev {
   int act_off[BFX_MAX_LAYERS + 1];   // float offsets of the activation buffers in smem
   int act_rows[BFX_MAX_LAYERS + 1];  // padded row counts
   int act_total;                     // floats of activation smem for one batch tile
+  int rec_hp, rec_c, rec_dc, rec_cp, rec_g;  // recurrent path: float offsets of h_{t-1}, c_t, dc, c_{t-1}, gates
+  int rec_rows;                      // rows of one per-step scratch record (LSTM 6H, RNN H)
   LayerDev L[BFX_MAX_LAYERS];
   SegDesc seg[BFX_MAX_SEGS];
   TcDesc tc;
@@ -169,6 +171,8 @@ struct RunDev {
   int* accepted_out;         // [C][hist_stride]
   long long hist_stride, hist_origin;
   unsigned long long* progress;
+  float* scratch;              // recurrent path: per-CTA scratch, scratch_stride floats each
+  long long scratch_stride;
 };
 
 // evaluation-only launch (bfx_loglikeprior / bfx_grad_loglikeprior)
@@ -186,6 +190,8 @@ struct EvalDev {
   int want_grad;
   double* v_out;  // [C]
   float* g_out;   // [C][P]
+  float* scratch;
+  long long scratch_stride;
 };
 
 }  // namespace bfx

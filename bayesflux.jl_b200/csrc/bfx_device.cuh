@@ -384,6 +384,7 @@ struct ChainSmem {
   float* red;   // [32*4] reduction scratch
   double* dacc; // [4]   double accumulators (thread 0)
   unsigned char* mask;  // [S/4] validity bits of each padded quad (copy of M.pad_mask)
+  float* scr;   // per-CTA HBM scratch of the recurrent path (per-step records) or nullptr
   unsigned char* tc;  // tensor-core region (128-byte aligned) or nullptr
 };
 
@@ -415,6 +416,7 @@ BFX_DEV ChainSmem carve_smem(const ModelDev& M, unsigned char* base) {
   s.red = f; f += 32 * 4;
   s.mask = reinterpret_cast<unsigned char*>(f); f += ((M.S / 4 + 15) & ~15) / 4;
   s.tc = nullptr;
+  s.scr = nullptr;
   if (M.tc.enabled) {
     unsigned long long a = reinterpret_cast<unsigned long long>(f);
     s.tc = reinterpret_cast<unsigned char*>((a + 127ull) & ~127ull);
@@ -451,37 +453,34 @@ struct LikeCoef {
   float nb;  // num_batches (scales the delta; src/model/BNN.jl:55)
 };
 
+// indices and targets of the tile
 template <int NT, int BT>
-BFX_DEV void mlp_tile(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
-                      const float* __restrict__ y, const BatchSrc& bs, long long tile0, int nvalid,
-                      const LikeCoef& lc, bool want_grad, float (&sums)[2]) {
-  constexpr int LDB = TileCfg<BT>::LDB;
-  const int d = M.d_in;
-  // ---- stage the tile: indices, targets, transposed inputs ------------------
+BFX_DEV void stage_targets(const ChainSmem& s, const float* __restrict__ y, const BatchSrc& bs, long long tile0,
+                           int nvalid) {
   for (int b = threadIdx.x; b < BT; b += NT) {
     long long o = (b < nvalid) ? batch_obs(bs, tile0 + b) : -1;
     s.idx[b] = (int)o;
     s.ys[b] = (o >= 0) ? __ldg(y + o) : 0.f;
   }
-  __syncthreads();
-  {
-    float* X = s.act + M.act_off[0];
-    const int dpad = M.act_rows[0];
-    for (int e = threadIdx.x; e < dpad * BT; e += NT) {
-      int b = e / dpad, f = e - b * dpad;
-      int o = s.idx[b];
-      X[f * LDB + b] = (o >= 0 && f < d) ? __ldg(x + (long long)o * d + f) : 0.f;
-    }
-  }
-  __syncthreads();
-  // ---- forward ----------------------------------------------------------------
-  for (int l = 0; l < M.nlayers; ++l) {
+}
+
+// Dense layers l0 .. nlayers-1 forward; the input of layer l0 is already in its activation buffer
+template <int NT, int BT>
+BFX_DEV void dense_forward(const ModelDev& M, const ChainSmem& s, int l0) {
+  constexpr int LDB = TileCfg<BT>::LDB;
+  for (int l = l0; l < M.nlayers; ++l) {
     const LayerDev& L = M.L[l];
     gemm_fwd<NT, BT>(s.th + L.w_s, L.ldw, s.act + M.act_off[l], LDB, s.th + L.b_s, s.act + M.act_off[l + 1], LDB,
                      L.nout_pad, L.nin, L.act);
     __syncthreads();
   }
-  // ---- likelihood epilogue ------------------------------------------------------
+}
+
+// likelihood epilogue on the network output; leaves dl[b] (scaled by num_batches) in the output buffer
+template <int NT, int BT>
+BFX_DEV void like_epilogue(const ModelDev& M, const ChainSmem& s, int nvalid, const LikeCoef& lc, bool want_grad,
+                           float (&sums)[2]) {
+  constexpr int LDB = TileCfg<BT>::LDB;
   float* out = s.act + M.act_off[M.nlayers];
   const int out_act = M.L[M.nlayers - 1].act;
   for (int b = threadIdx.x; b < BT; b += NT) {
@@ -508,10 +507,14 @@ BFX_DEV void mlp_tile(const ModelDev& M, const ChainSmem& s, const float* __rest
       out[3 * LDB + b] = 0.f;
     }
   }
-  if (!want_grad) return;
-  __syncthreads();
-  // ---- backward -------------------------------------------------------------------
-  for (int l = M.nlayers - 1; l >= 0; --l) {
+}
+
+// Dense layers nlayers-1 .. l0 backward.  For l0 > 0 the raw gradient w.r.t. the input of layer l0 (not
+// multiplied by any activation derivative) is left in that layer's input buffer.
+template <int NT, int BT>
+BFX_DEV void dense_backward(const ModelDev& M, const ChainSmem& s, int l0) {
+  constexpr int LDB = TileCfg<BT>::LDB;
+  for (int l = M.nlayers - 1; l >= l0; --l) {
     const LayerDev& L = M.L[l];
     const float* D = s.act + M.act_off[l + 1];
     float* A = s.act + M.act_off[l];
@@ -519,9 +522,163 @@ BFX_DEV void mlp_tile(const ModelDev& M, const ChainSmem& s, const float* __rest
     rowsum_acc<NT, BT>(D, LDB, s.g + L.b_s, L.nout);
     if (l > 0) {
       __syncthreads();
-      gemm_dx<NT, BT>(s.th + L.w_s, L.ldw, D, LDB, A, LDB, L.nin_pad, L.nout_pad, M.L[l - 1].act);
+      gemm_dx<NT, BT>(s.th + L.w_s, L.ldw, D, LDB, A, LDB, L.nin_pad, L.nout_pad,
+                      l > l0 ? M.L[l - 1].act : A_IDENTITY);
       __syncthreads();
     }
+  }
+}
+
+template <int NT, int BT>
+BFX_DEV void mlp_tile(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
+                      const float* __restrict__ y, const BatchSrc& bs, long long tile0, int nvalid,
+                      const LikeCoef& lc, bool want_grad, float (&sums)[2]) {
+  constexpr int LDB = TileCfg<BT>::LDB;
+  const int d = M.d_in;
+  stage_targets<NT, BT>(s, y, bs, tile0, nvalid);
+  __syncthreads();
+  {
+    float* X = s.act + M.act_off[0];
+    const int dpad = M.act_rows[0];
+    for (int e = threadIdx.x; e < dpad * BT; e += NT) {
+      int b = e / dpad, f = e - b * dpad;
+      int o = s.idx[b];
+      X[f * LDB + b] = (o >= 0 && f < d) ? __ldg(x + (long long)o * d + f) : 0.f;
+    }
+  }
+  __syncthreads();
+  dense_forward<NT, BT>(M, s, 0);
+  like_epilogue<NT, BT>(M, s, nvalid, lc, want_grad, sums);
+  if (!want_grad) return;
+  __syncthreads();
+  dense_backward<NT, BT>(M, s, 0);
+}
+
+// ---------------------------------------------------------------------------------
+// Seq-to-one networks: Chain(RNN | LSTM, Dense..., Dense(., 1)) on x of shape T x d x n.
+// src/likelihoods/seq_to_one.jl:31-44,89-100: the chain is applied to every time slice with the
+// recurrent state carried over (zero initial state, src/layers/recurrent.jl:30,60,64) and only the
+// last output is used -- the Dense head therefore only matters at t = T.  Flux cells (third party):
+//   RNNCell   h' = act(Wi x + Wh h + b)
+//   LSTMCell  g = Wi x + Wh h + b, rows [i; f; c~; o];  c' = sig(f) c + sig(i) tanh(c~);  h' = sig(o) tanh(c')
+// Backward = BPTT, hand-derived (oracle/bfx_oracle.py net_backward).  The per-step records the backward
+// needs (gate outputs, c_t, h_t) go to a per-CTA scratch in HBM (L2 resident); weights, gradient and the
+// working tiles stay in shared memory.
+// ---------------------------------------------------------------------------------
+BFX_DEV float sigm(float z) { return 1.f / (1.f + expf(-z)); }
+
+template <int NT, int BT>
+BFX_DEV void rec_stage_x(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x, int t) {
+  constexpr int LDB = TileCfg<BT>::LDB;
+  float* X = s.act + M.act_off[0];
+  const int dpad = M.act_rows[0], d = M.d_in, T = M.T;
+  for (int e = threadIdx.x; e < dpad * BT; e += NT) {
+    int f = e / BT, b = e - f * BT;
+    int o = s.idx[b];
+    X[f * LDB + b] = (o >= 0 && f < d) ? __ldg(x + ((long long)o * d + f) * T + t) : 0.f;
+  }
+}
+
+template <int NT, int BT>
+BFX_DEV void rec_tile(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
+                      const float* __restrict__ y, const BatchSrc& bs, long long tile0, int nvalid,
+                      const LikeCoef& lc, bool want_grad, float (&sums)[2]) {
+  constexpr int LDB = TileCfg<BT>::LDB;
+  const LayerDev& L = M.L[0];
+  const int H = L.H, T = M.T;
+  const bool lstm = L.kind == L_LSTM;
+  const int GR = lstm ? 4 * H : H;   // gate rows
+  const int GRp = L.nout_pad, Hp4 = M.act_rows[1];
+  const int RR = lstm ? 6 * H : H;   // rows of one per-step record in the scratch
+  float* Hc = s.act + M.act_off[1];  // h_t (input of the Dense head); dh during the backward sweep
+  float* Hp = s.act + M.rec_hp;      // h_{t-1}
+  float* Cc = s.act + M.rec_c;       // c_t
+  float* DC = s.act + M.rec_dc;      // dL/dc flowing to the past
+  float* G = s.act + M.rec_g;        // gate pre-activations / dz
+  float* scr = s.scr;
+  stage_targets<NT, BT>(s, y, bs, tile0, nvalid);
+  for (int e = threadIdx.x; e < Hp4 * LDB; e += NT) {
+    Hc[e] = 0.f;
+    Cc[e] = 0.f;
+  }
+  __syncthreads();
+  // ---- forward over time -----------------------------------------------------------------
+  for (int t = 0; t < T; ++t) {
+    for (int e = threadIdx.x; e < Hp4 * LDB; e += NT) Hp[e] = Hc[e];
+    rec_stage_x<NT, BT>(M, s, x, t);
+    __syncthreads();
+    gemm_fwd<NT, BT>(s.th + L.w_s, L.ldw, s.act + M.act_off[0], LDB, s.th + L.b_s, G, LDB, GRp, L.nin, A_IDENTITY);
+    __syncthreads();
+    gemm_fwd<NT, BT>(s.th + L.wh_s, L.ldh, Hp, LDB, nullptr, G, LDB, GRp, H, lstm ? A_IDENTITY : L.act, true);
+    __syncthreads();
+    float* rec = scr + (long long)t * RR * BT;
+    for (int e = threadIdx.x; e < H * BT; e += NT) {
+      const int r = e / BT, b = e - r * BT;
+      if (lstm) {
+        const float ig = sigm(G[r * LDB + b]), fg = sigm(G[(H + r) * LDB + b]);
+        const float cg = tanhf(G[(2 * H + r) * LDB + b]), og = sigm(G[(3 * H + r) * LDB + b]);
+        const float c = fg * Cc[r * LDB + b] + ig * cg;
+        const float h = og * tanhf(c);
+        Cc[r * LDB + b] = c;
+        Hc[r * LDB + b] = h;
+        if (want_grad) {
+          rec[r * BT + b] = ig;
+          rec[(H + r) * BT + b] = fg;
+          rec[(2 * H + r) * BT + b] = cg;
+          rec[(3 * H + r) * BT + b] = og;
+          rec[(4 * H + r) * BT + b] = c;
+          rec[(5 * H + r) * BT + b] = h;
+        }
+      } else {
+        const float h = G[r * LDB + b];
+        Hc[r * LDB + b] = h;
+        if (want_grad) rec[r * BT + b] = h;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- Dense head on h_T, likelihood, head backward (leaves dL/dh_T in Hc) ---------------------
+  dense_forward<NT, BT>(M, s, 1);
+  like_epilogue<NT, BT>(M, s, nvalid, lc, want_grad, sums);
+  if (!want_grad) return;
+  __syncthreads();
+  dense_backward<NT, BT>(M, s, 1);
+  for (int e = threadIdx.x; e < Hp4 * LDB; e += NT) DC[e] = 0.f;
+  for (int e = threadIdx.x; e < GRp * LDB; e += NT) G[e] = 0.f;
+  __syncthreads();
+  // ---- backward through time -------------------------------------------------------------------
+  for (int t = T - 1; t >= 0; --t) {
+    const float* rec = scr + (long long)t * RR * BT;
+    const float* recp = scr + (long long)(t - 1) * RR * BT;
+    for (int e = threadIdx.x; e < H * BT; e += NT) {
+      const int r = e / BT, b = e - r * BT;
+      const float dh = Hc[r * LDB + b];
+      if (lstm) {
+        const float ig = rec[r * BT + b], fg = rec[(H + r) * BT + b], cg = rec[(2 * H + r) * BT + b];
+        const float og = rec[(3 * H + r) * BT + b], c = rec[(4 * H + r) * BT + b];
+        const float cprev = t > 0 ? recp[(4 * H + r) * BT + b] : 0.f;
+        Hp[r * LDB + b] = t > 0 ? recp[(5 * H + r) * BT + b] : 0.f;
+        const float tc = tanhf(c);
+        const float dgo = dh * tc;
+        const float dc = dh * og * (1.f - tc * tc) + DC[r * LDB + b];
+        G[r * LDB + b] = dc * cg * ig * (1.f - ig);
+        G[(H + r) * LDB + b] = dc * cprev * fg * (1.f - fg);
+        G[(2 * H + r) * LDB + b] = dc * ig * (1.f - cg * cg);
+        G[(3 * H + r) * LDB + b] = dgo * og * (1.f - og);
+        DC[r * LDB + b] = dc * fg;
+      } else {
+        const float h = rec[r * BT + b];
+        Hp[r * LDB + b] = t > 0 ? recp[r * BT + b] : 0.f;
+        G[r * LDB + b] = dh * act_deriv_from_out(L.act, h);
+      }
+    }
+    rec_stage_x<NT, BT>(M, s, x, t);
+    __syncthreads();
+    gemm_dw<NT, BT>(G, LDB, s.act + M.act_off[0], LDB, s.g + L.w_s, L.ldw, GRp, L.nin_pad);
+    gemm_dw<NT, BT>(G, LDB, Hp, LDB, s.g + L.wh_s, L.ldh, GRp, Hp4);
+    rowsum_acc<NT, BT>(G, LDB, s.g + L.b_s, GR);
+    if (t > 0) gemm_dx<NT, BT>(s.th + L.wh_s, L.ldh, G, LDB, Hc, LDB, Hp4, GRp, A_IDENTITY);
+    __syncthreads();
   }
 }
 

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) 
   const ModelDev& M = E.M;
   ChainSmem s = carve_smem<BT>(M, smem_raw);
   const int c = blockIdx.x;
+  s.scr = E.scratch ? E.scratch + (long long)c * E.scratch_stride : nullptr;
   tc::Region tr{};
   if constexpr (TC) {
     tr = tc::region_of(M, s);
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(NT) k_mcmc(const __grid_constant__ RunDev R) {
     tr = tc::region_of(M, s);
     tc::setup<NT>(M, tr);
   }
+  s.scr = R.scratch ? R.scratch + (long long)c * R.scratch_stride : nullptr;
   Ctx<NT, BT, TC> X(R, s);
   X.tcr = &tr;
   X.c = c;
@@ -184,11 +186,12 @@ static cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
 }
 
 size_t smallp_smem_bytes(const ModelDev& M, int bt) {
-  return bt == 32 ? chain_smem_bytes<32>(M) : chain_smem_bytes<64>(M);
+  return bt == 16 ? chain_smem_bytes<16>(M) : bt == 32 ? chain_smem_bytes<32>(M) : chain_smem_bytes<64>(M);
 }
 
 cudaError_t launch_eval(const EvalDev& E, const LaunchCfg& cfg, cudaStream_t st) {
   if (E.M.tc.enabled) return launch_eval_t<256, 64, true>(E, st);
+  if (cfg.bt == 16) return launch_eval_t<256, 16>(E, st);
   if (cfg.nt == 32) return launch_eval_t<32, 32>(E, st);
   if (cfg.nt == 128) return launch_eval_t<128, 64>(E, st);
   return launch_eval_t<256, 64>(E, st);
@@ -196,6 +199,7 @@ cudaError_t launch_eval(const EvalDev& E, const LaunchCfg& cfg, cudaStream_t st)
 
 cudaError_t launch_mcmc(const RunDev& R, const LaunchCfg& cfg, cudaStream_t st) {
   if (R.M.tc.enabled) return launch_mcmc_t<256, 64, true>(R, st);
+  if (cfg.bt == 16) return launch_mcmc_t<256, 16>(R, st);
   if (cfg.nt == 32) return launch_mcmc_t<32, 32>(R, st);
   if (cfg.nt == 128) return launch_mcmc_t<128, 64>(R, st);
   return launch_mcmc_t<256, 64>(R, st);
