@@ -14,3 +14,5 @@ from .api import (BNN, Chain, Dense, LSTM, RNN, NetConstructor, destruct, Gamma,
                   RMSPropMassAdapter, FullCovMassAdapter, MCMCState, SGLD, SGNHT, SGNHTS, GGMC, HMC, mcmc,
                   advance, launch_count,
                   identity, relu, tanh, sigmoid)
+from .sharded import (shard_chains, shard_data, global_num_batches, model_regime, ShardedChain,  # noqa: F401,E402
+                      mcmc_sharded)

@@ -20,6 +20,7 @@ MASS_FIXED, MASS_DIAGCOV, MASS_RMSPROP, MASS_FULLCOV = range(4)
  STATE_STATUS) = range(8)
 BATCH_PER_CHAIN, BATCH_SHARED = 0, 1
 COMPUTE_FP32, COMPUTE_TC_BF16X3 = 0, 1
+REGIME_SMEM, REGIME_STREAM = 0, 1
 
 
 class LayerDesc(C.Structure):
@@ -85,6 +86,9 @@ SYMBOLS = {
     "bfx_progress": [_vp, _pi64],
     "bfx_mcmc_advance": [_vp, C.POINTER(RunDesc), _i64, _vp, _vp, _i64],
     "bfx_sampler_launch_count": [_vp, _pi64],
+    "bfx_model_regime": [_vp, _pi32],
+    "bfx_stream_grad_local": [_vp, C.POINTER(RunDesc), _f32, _vp, _vp, _i64],
+    "bfx_stream_apply_update": [_vp, C.POINTER(RunDesc), _f32, _vp, _vp, _vp],
     "bfx_debug_batch_indices": [_vp, C.POINTER(RunDesc), _i64, _i64, _vp, _pi64],
     "bfx_debug_noise": [_vp, C.POINTER(RunDesc), _i64, _i64, _i32, _vp, _vp],
 }

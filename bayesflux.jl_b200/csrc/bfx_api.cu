@@ -12,6 +12,7 @@
 #include "../../include/bfx.h"
 #include "bfx_common.cuh"
 #include "bfx_kernels.h"
+#include "bfx_stream.cuh"
 
 using namespace bfx;
 
@@ -55,6 +56,10 @@ struct bfx_model {
   // flat (ABI) <-> padded (engine) parameter layout
   std::vector<int> flat_pad, pad_flat;
   std::vector<unsigned char> pad_mask;
+  // large-P ("stream") regime, bfx_stream.cuh
+  bool stream_regime = false;
+  StreamModel SM{};
+  StreamWork W{};
   float* scratch = nullptr;  // recurrent path: per-CTA per-step records
   size_t scratch_ctas = 0;
   int* d_flat_pad = nullptr;
@@ -70,6 +75,8 @@ struct bfx_sampler {
   int Ps = 0;
   float *theta = nullptr, *mom = nullptr, *minv = nullptr, *theta_old = nullptr, *rms_v = nullptr, *ring = nullptr;
   ChainScalars* sc = nullptr;
+  StreamScalars* ssc = nullptr;  // stream regime: per-chain device scalars
+  float* gbuf = nullptr;         // stream regime: [P + 3] gradient + likelihood sums (the all-reduce payload)
   unsigned long long* progress_host = nullptr;  // mapped pinned
   unsigned long long* progress_dev = nullptr;
   long long gstep = 0;     // update! calls done since init
@@ -234,9 +241,45 @@ static int32_t build_model_dev(bfx_model* m, const bfx_like_desc* like, const bf
     M.rec_rows = M.L[0].kind == L_LSTM ? 6 * M.L[0].H : M.L[0].H;
   }
   M.act_total = off;
-  if (smallp_smem_bytes(M, m->cfg.bt) > kMaxSmem)
-    return fail(BFX_ERR_UNSUPPORTED,
-                "network does not fit the shared-memory regime (theta + gradient + one batch tile > 227 KB)");
+  if (smallp_smem_bytes(M, m->cfg.bt) > kMaxSmem) {
+    if (M.rec_layer >= 0)
+      return fail(BFX_ERR_UNSUPPORTED,
+                  "recurrent network does not fit the shared-memory regime (theta + gradient + one batch tile > 227 KB)");
+    // large-P regime: theta in HBM in the flat order, layer-wise GEMMs (bfx_stream.cuh)
+    m->stream_regime = true;
+    StreamModel& SMd = m->SM;
+    SMd = StreamModel{};
+    SMd.nlayers = nl;
+    SMd.P = M.P;
+    SMd.Pnet = M.Pnet;
+    SMd.d_in = M.d_in;
+    SMd.like_kind = M.like_kind;
+    SMd.sprior_kind = M.sprior_kind;
+    SMd.nu = M.nu;
+    SMd.sprior_a = M.sprior_a;
+    SMd.sprior_b = M.sprior_b;
+    SMd.prior_c2 = M.prior_c2;
+    SMd.prior_c0n = M.prior_c0n;
+    SMd.tdist_const = M.tdist_const;
+    SMd.sprior_const = M.sprior_const;
+    for (int l = 0; l < nl; ++l) {
+      SMd.L[l].nin = M.L[l].nin;
+      SMd.L[l].nout = M.L[l].nout;
+      SMd.L[l].act = M.L[l].act;
+      SMd.L[l].w_off = m->starts[l];
+      SMd.L[l].b_off = m->starts[l] + (long long)M.L[l].nin * M.L[l].nout;
+    }
+    // the engine-internal layout of this regime IS the flat order (rows padded to a multiple of 4)
+    M.S = round4(M.P);
+    m->flat_pad.resize(M.P);
+    m->pad_flat.assign(M.S, -1);
+    m->pad_mask.assign(M.S / 4, 0);
+    for (int J = 0; J < M.P; ++J) {
+      m->flat_pad[J] = J;
+      m->pad_flat[J] = J;
+      m->pad_mask[J >> 2] |= (unsigned char)(1u << (J & 3));
+    }
+  }
   return BFX_OK;
 }
 
@@ -363,6 +406,10 @@ int32_t bfx_model_destroy(bfx_model* m) {
     cudaSetDevice(m->device);
     cudaFree(m->scratch);
   }
+  if (m->W.Bc) {
+    cudaSetDevice(m->device);
+    stream_work_free(m->W);
+  }
   if (m->d_flat_pad) {
     cudaSetDevice(m->device);
     cudaFree(m->d_flat_pad);
@@ -480,6 +527,119 @@ int32_t bfx_model_set_data_device(bfx_model* m, const float* x_dev, const int64_
   return set_data_impl(m, x_dev, dims, ndims, y_dev, n, cudaMemcpyDeviceToDevice);
 }
 
+
+// ---------------------------------------------------------------------------------
+// stream regime helpers
+// ---------------------------------------------------------------------------------
+static void philox_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0;
+    k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// the minibatch of global step gstep for chain `chainkey` (same schedule as make_batch in bfx_kernels.cu)
+static StreamBatch stream_batch(const bfx_model* m, const bfx_run_desc* run, unsigned chainkey, long long gstep) {
+  StreamBatch b{};
+  b.idx = nullptr;
+  b.n = m->n;
+  long long B = run->batchsize < m->n ? run->batchsize : m->n;
+  long long nb = run->partial ? (m->n + B - 1) / B : m->n / B;
+  if (nb < 1) nb = 1;
+  const unsigned long long epoch = (unsigned long long)gstep / (unsigned long long)nb, k = (unsigned long long)gstep % (unsigned long long)nb;
+  b.first = (long long)k * B;
+  const long long rem = m->n - b.first;
+  b.B = rem < B ? rem : B;
+  b.shuffle = run->shuffle ? 1 : 0;
+  b.full = 0;
+  uint32_t o[4];
+  philox_host((uint32_t)epoch, (uint32_t)(epoch >> 32), run->batch_mode == BFX_BATCH_SHARED ? 0xFFFFFFFFu : chainkey,
+              0x5eedba7cu, (uint32_t)run->seed, (uint32_t)(run->seed >> 32), o);
+  b.k0 = o[0];
+  b.k1 = o[1];
+  return b;
+}
+
+static int32_t ensure_work(bfx_model* m, long long B) {
+  long long Bc = B < 8192 ? B : 8192;
+  if (Bc < 1) Bc = 1;
+  if (m->W.Bc >= Bc) return BFX_OK;
+  if (m->W.Bc) {
+    CK(cudaStreamSynchronize(m->stream));
+    stream_work_free(m->W);
+  }
+  CK(stream_work_alloc(m->SM, Bc, m->W));
+  return BFX_OK;
+}
+
+// one evaluation in the stream regime: g (P floats, device) and the scalars of `ssc`; single rank
+static int32_t stream_eval_full(bfx_model* m, const float* theta_dev, const StreamBatch& b, float nb, bool want_grad,
+                                float* g_dev, StreamScalars* ssc, cudaStream_t st) {
+  int32_t rc = ensure_work(m, b.B);
+  if (rc) return rc;
+  CK(stream_zero(g_dev, m->M.P, ssc, st));
+  CK(stream_eval_like(m->SM, m->W, theta_dev, m->x, m->y, b, nb, want_grad, g_dev, ssc, st));
+  CK(stream_finish(m->SM, theta_dev, g_dev, ssc, nb, want_grad, st));
+  return BFX_OK;
+}
+
+static int32_t stream_eval_api(bfx_model* m, const float* theta, int32_t C, const int64_t* idx, int64_t B, int64_t stride,
+                               float num_batches, double* v_out, float* g_out) {
+  const long long P = m->M.P;
+  float *d_theta = nullptr, *d_g = nullptr;
+  StreamScalars* d_sc = nullptr;
+  long long* d_idx = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_theta);
+    cudaFree(d_g);
+    cudaFree(d_sc);
+    cudaFree(d_idx);
+  };
+#define CKS(call)                                                                     \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      cleanup();                                                                      \
+      return fail(BFX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    }                                                                                 \
+  } while (0)
+  CKS(cudaMalloc(&d_theta, (size_t)P * 4));
+  CKS(cudaMalloc(&d_g, (size_t)(P + 4) * 4));
+  CKS(cudaMalloc(&d_sc, sizeof(StreamScalars)));
+  CKS(cudaMemsetAsync(d_sc, 0, sizeof(StreamScalars), m->stream));
+  const int64_t nidx = idx ? (stride ? (int64_t)(C - 1) * stride + B : B) : 0;
+  if (idx) {
+    CKS(cudaMalloc(&d_idx, (size_t)nidx * 8));
+    CKS(cudaMemcpyAsync(d_idx, idx, (size_t)nidx * 8, cudaMemcpyHostToDevice, m->stream));
+  }
+  for (int c = 0; c < C; ++c) {
+    CKS(cudaMemcpyAsync(d_theta, theta + (size_t)c * P, (size_t)P * 4, cudaMemcpyHostToDevice, m->stream));
+    StreamBatch b{};
+    b.n = m->n;
+    b.full = idx ? 0 : 1;
+    b.idx = idx ? d_idx + (long long)c * stride : nullptr;
+    b.B = idx ? B : m->n;
+    int32_t rc = stream_eval_full(m, d_theta, b, num_batches, g_out != nullptr, d_g, d_sc, m->stream);
+    if (rc) {
+      cleanup();
+      return rc;
+    }
+    StreamScalars h;
+    CKS(cudaMemcpyAsync(&h, d_sc, sizeof h, cudaMemcpyDeviceToHost, m->stream));
+    if (g_out) CKS(cudaMemcpyAsync(g_out + (size_t)c * P, d_g, (size_t)P * 4, cudaMemcpyDeviceToHost, m->stream));
+    CKS(cudaStreamSynchronize(m->stream));
+    v_out[c] = h.value;
+  }
+  cleanup();
+  return BFX_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // loglikeprior / ∇loglikeprior
 // ---------------------------------------------------------------------------------
@@ -496,6 +656,7 @@ static int32_t eval_impl(bfx_model* m, const float* theta, int32_t C, const int6
   if (idx)
     for (int64_t i = 0; i < nidx; ++i)
       if (idx[i] < 0 || idx[i] >= m->n) return fail(BFX_ERR_BAD_ARG, "batch index out of range");
+  if (m->stream_regime) return stream_eval_api(m, theta, C, idx, B, stride, num_batches, v_out, g_out);
   float *d_theta = nullptr, *d_g = nullptr;
   double* d_v = nullptr;
   long long* d_idx = nullptr;
@@ -575,6 +736,8 @@ static void free_sampler(bfx_sampler* s) {
   cudaFree(s->rms_v);
   cudaFree(s->ring);
   cudaFree(s->sc);
+  cudaFree(s->ssc);
+  cudaFree(s->gbuf);
   if (s->progress_host) cudaFreeHost(s->progress_host);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   delete s;
@@ -596,6 +759,12 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
   if (d->kind != BFX_SGLD && !(d->l > 0)) return fail(BFX_ERR_BAD_ARG, "stepsize l must be > 0");
   if (d->madapter_kind == BFX_MASS_DIAGCOV && d->ma_windowlength < 2)
     return fail(BFX_ERR_BAD_ARG, "DiagCov windowlength must be >= 2");
+  if (m->stream_regime) {
+    if (d->kind == BFX_GGMC || d->kind == BFX_HMC)
+      return fail(BFX_ERR_UNSUPPORTED, "large-P (stream) regime: SGLD, SGNHT and SGNHTS are available; GGMC / HMC are not");
+    if (d->kind == BFX_SGNHTS && d->madapter_kind == BFX_MASS_DIAGCOV)
+      return fail(BFX_ERR_UNSUPPORTED, "large-P (stream) regime: DiagCovMassAdapter is not available");
+  }
   int32_t st = ensure_stream(m);
   if (st) return st;
   bfx_sampler* s = new (std::nothrow) bfx_sampler();
@@ -642,6 +811,8 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
   if (e == cudaSuccess && S.madapter_kind != MA_FIXED) e = cudaMalloc(&s->minv, all);
   if (e == cudaSuccess && S.madapter_kind == MA_RMSPROP) e = cudaMalloc(&s->rms_v, all);
   if (e == cudaSuccess && S.madapter_kind == MA_DIAGCOV) e = cudaMalloc(&s->ring, all * (size_t)S.ma_windowlength);
+  if (e == cudaSuccess && m->stream_regime) e = cudaMalloc(&s->ssc, sizeof(StreamScalars) * (size_t)nchains);
+  if (e == cudaSuccess && m->stream_regime) e = cudaMalloc(&s->gbuf, ((size_t)m->M.P + 4) * sizeof(float));
   if (e == cudaSuccess) e = cudaHostAlloc(&s->progress_host, sizeof(unsigned long long), cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostGetDevicePointer(&s->progress_dev, s->progress_host, 0);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
@@ -694,6 +865,15 @@ int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) {
   z.status = 0;
   std::vector<ChainScalars> sc((size_t)s->C, z);
   CK(cudaMemcpyAsync(s->sc, sc.data(), sizeof(ChainScalars) * sc.size(), cudaMemcpyHostToDevice, m->stream));
+  if (s->ssc) {
+    StreamScalars zs{};
+    zs.t = 1;
+    zs.xi = s->S.xi;
+    zs.l = s->S.l;
+    zs.ma_t = 1;
+    std::vector<StreamScalars> ssc((size_t)s->C, zs);
+    CK(cudaMemcpyAsync(s->ssc, ssc.data(), sizeof(StreamScalars) * ssc.size(), cudaMemcpyHostToDevice, m->stream));
+  }
   CK(cudaStreamSynchronize(m->stream));
   s->gstep = 0;
   s->nsampled = 0;
@@ -706,6 +886,36 @@ static int32_t fetch_scalars(bfx_sampler* s, std::vector<ChainScalars>& sc) {
   sc.resize((size_t)s->C);
   CK(cudaSetDevice(s->m->device));
   CK(cudaMemcpy(sc.data(), s->sc, sizeof(ChainScalars) * sc.size(), cudaMemcpyDeviceToHost));
+  if (s->ssc) {  // stream regime keeps its own scalars: mirror them
+    std::vector<StreamScalars> ss((size_t)s->C);
+    CK(cudaMemcpy(ss.data(), s->ssc, sizeof(StreamScalars) * ss.size(), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < s->C; ++c) {
+      sc[c].t = ss[c].t;
+      sc[c].nsampled = ss[c].nsampled;
+      sc[c].xi = ss[c].xi;
+      sc[c].l = ss[c].l;
+      sc[c].status = ss[c].status;
+      sc[c].ma_t = ss[c].ma_t;
+    }
+  }
+  return BFX_OK;
+}
+
+static int32_t store_scalars(bfx_sampler* s, const std::vector<ChainScalars>& sc) {
+  CK(cudaMemcpy(s->sc, sc.data(), sizeof(ChainScalars) * sc.size(), cudaMemcpyHostToDevice));
+  if (s->ssc) {
+    std::vector<StreamScalars> ss((size_t)s->C);
+    CK(cudaMemcpy(ss.data(), s->ssc, sizeof(StreamScalars) * ss.size(), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < s->C; ++c) {
+      ss[c].t = sc[c].t;
+      ss[c].nsampled = sc[c].nsampled;
+      ss[c].xi = sc[c].xi;
+      ss[c].l = sc[c].l;
+      ss[c].status = sc[c].status;
+      ss[c].ma_t = sc[c].ma_t;
+    }
+    CK(cudaMemcpy(s->ssc, ss.data(), sizeof(StreamScalars) * ss.size(), cudaMemcpyHostToDevice));
+  }
   return BFX_OK;
 }
 
@@ -796,8 +1006,7 @@ int32_t bfx_sampler_set_state(bfx_sampler* s, int32_t field, const void* in, int
   } else {
     return fail(BFX_ERR_BAD_ARG, "unknown state field");
   }
-  CK(cudaMemcpy(s->sc, sc.data(), sizeof(ChainScalars) * sc.size(), cudaMemcpyHostToDevice));
-  return BFX_OK;
+  return store_scalars(s, sc);
 }
 
 static int32_t fill_run_common(bfx_sampler* s, RunDev& R) {
@@ -846,6 +1055,101 @@ static int32_t status_after(bfx_sampler* s) {
   return BFX_OK;
 }
 
+
+// ---------------------------------------------------------------------------------
+// stream regime: one update! of chain c (grad on the local minibatch, optional hand-off for the
+// caller's all-reduce, update).  Everything is enqueued on `st`; nothing synchronises.
+// ---------------------------------------------------------------------------------
+static int32_t stream_grad_local(bfx_sampler* s, int c, const StreamBatch& b, float nb, bool pack, cudaStream_t st,
+                                 float* gb = nullptr) {
+  if (!gb) gb = s->gbuf;
+  bfx_model* m = s->m;
+  int32_t rc = ensure_work(m, b.B);
+  if (rc) return rc;
+  const float* th = s->theta + (size_t)c * s->Ps;
+  CK(stream_zero(gb, m->M.P, s->ssc + c, st));
+  CK(stream_eval_like(m->SM, m->W, th, m->x, m->y, b, nb, true, gb, s->ssc + c, st));
+  if (pack) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, true, st));
+  return BFX_OK;
+}
+
+static int32_t stream_apply(bfx_sampler* s, int c, float nb, bool unpack, unsigned long long seed, unsigned chainkey,
+                            const float* inj, float* sample_dev, float* kinetic_dev, cudaStream_t st, float* gb = nullptr) {
+  bfx_model* m = s->m;
+  if (!gb) gb = s->gbuf;
+  float* th = s->theta + (size_t)c * s->Ps;
+  if (unpack) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, false, st));
+  CK(stream_finish(m->SM, th, gb, s->ssc + c, nb, true, st));
+  StreamUpdate U{};
+  U.S = &s->S;
+  U.P = m->M.P;
+  U.theta = th;
+  U.mom = s->mom ? s->mom + (size_t)c * s->Ps : nullptr;
+  U.minv = s->minv ? s->minv + (size_t)c * s->Ps : nullptr;
+  U.rmsv = s->rms_v ? s->rms_v + (size_t)c * s->Ps : nullptr;
+  U.g = gb;
+  U.sc = s->ssc + c;
+  U.seed = seed;
+  U.chain = chainkey;
+  U.gstep = (unsigned long long)s->gstep;
+  U.inj = inj;
+  U.sample_out = sample_dev;
+  U.kinetic_out = kinetic_dev;
+  cudaError_t e = stream_update(U, st);
+  if (e != cudaSuccess) return fail(BFX_ERR_CUDA, std::string("stream_update: ") + cudaGetErrorString(e));
+  return BFX_OK;
+}
+
+static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, int64_t base, float* samples_host,
+                          int64_t nkept, float* kinetic_host, int64_t nnew, float* samples_dev, int64_t ring_slots,
+                          cudaStream_t st) {
+  bfx_model* m = s->m;
+  const long long P = m->M.P;
+  const int C = s->C;
+  const int64_t ke = run->keep_every > 0 ? run->keep_every : 1;
+  long long B = run->batchsize < m->n ? run->batchsize : m->n;
+  long long nbat = run->partial ? (m->n + B - 1) / B : m->n / B;
+  if (nbat < 1) nbat = 1;
+  float* d_kin = nullptr;
+  if (kinetic_host) {
+    CK(cudaMalloc(&d_kin, (size_t)C * nnew * 4));
+    CK(cudaMemsetAsync(d_kin, 0, (size_t)C * nnew * 4, st));
+  }
+  for (int64_t it = 0; it < nsteps; ++it) {
+    const int64_t ns = base + it + 1;  // nsampled after this update (SGLD / SGNHT / SGNHTS: one sample per update)
+    for (int c = 0; c < C; ++c) {
+      const unsigned chainkey = (unsigned)(run->chain_offset + c);
+      StreamBatch b = stream_batch(m, run, chainkey, s->gstep);
+      int32_t rc = stream_grad_local(s, c, b, (float)nbat, false, st);
+      if (rc) return rc;
+      float* sdev = nullptr;
+      if (samples_dev && ns % ke == 0) {
+        int64_t slot = ns / ke - 1;
+        if (ring_slots > 0) slot %= ring_slots;
+        sdev = samples_dev + ((size_t)c * (ring_slots > 0 ? ring_slots : 1) + slot) * P;
+      }
+      rc = stream_apply(s, c, (float)nbat, false, run->seed, chainkey, nullptr, sdev,
+                        d_kin ? d_kin + (size_t)c * nnew + it : nullptr, st);
+      if (rc) return rc;
+      if (samples_host && ns % ke == 0) {
+        const int64_t col = ns / ke - 1 - base / ke;
+        CK(cudaMemcpyAsync(samples_host + ((size_t)c * nkept + col) * P, s->theta + (size_t)c * s->Ps, (size_t)P * 4,
+                           cudaMemcpyDeviceToHost, st));
+      }
+    }
+    s->gstep += 1;
+    s->launches += 12;
+    if ((it & 63) == 63) CK(cudaStreamSynchronize(st));  // bound the launch queue; also paces the progress counter
+    *s->progress_host = (unsigned long long)s->gstep;
+  }
+  if (d_kin) {
+    CK(cudaMemcpyAsync(kinetic_host, d_kin, (size_t)C * nnew * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_kin);
+  }
+  return BFX_OK;
+}
+
 int32_t bfx_sampler_step_injected(bfx_sampler* s, const int64_t* idx, int64_t B, int64_t stride, float num_batches,
                                   const float* normals, const float* uniforms, float* theta_out) {
   if (!s || !idx || !normals) return fail(BFX_ERR_BAD_ARG, "NULL argument");
@@ -876,6 +1180,30 @@ int32_t bfx_sampler_step_injected(bfx_sampler* s, const int64_t* idx, int64_t B,
   if (uniforms) {
     CKC(cudaMalloc(&d_u, (size_t)C * 4));
     CKC(cudaMemcpyAsync(d_u, uniforms, (size_t)C * 4, cudaMemcpyHostToDevice, m->stream));
+  }
+  if (m->stream_regime) {
+    for (int c = 0; c < C; ++c) {
+      StreamBatch b{};
+      b.n = m->n;
+      b.idx = d_idx + (long long)c * stride;
+      b.B = B;
+      int32_t rc = stream_grad_local(s, c, b, num_batches, false, m->stream);
+      if (!rc) rc = stream_apply(s, c, num_batches, false, 0, (unsigned)c, d_n + (size_t)c * P, nullptr, nullptr, m->stream);
+      if (rc) {
+        cleanup();
+        return rc;
+      }
+    }
+    s->gstep += 1;
+    s->launches += 12;
+    CKC(cudaStreamSynchronize(m->stream));
+    if (theta_out) {
+      std::vector<float> pad((size_t)s->Ps * C);
+      CKC(cudaMemcpy(pad.data(), s->theta, pad.size() * 4, cudaMemcpyDeviceToHost));
+      padded_to_flat(m, pad, C, theta_out);
+    }
+    cleanup();
+    return status_after(s);
   }
   RunDev R{};
   {
@@ -969,8 +1297,16 @@ int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta
       st = fetch_scalars(s, sc);
       if (st) return st;
       for (auto& c : sc) c.current_step = 1;
-      CK(cudaMemcpy(s->sc, sc.data(), sizeof(ChainScalars) * sc.size(), cudaMemcpyHostToDevice));
+      st = store_scalars(s, sc);
+      if (st) return st;
     }
+  }
+  if (m->stream_regime) {
+    if (!m->x) return fail(BFX_ERR_NO_DATA, "bfx_model_set_data has not been called");
+    st = stream_run(s, run, nnew, s->nsampled, samples_out, nkept, kinetic_out, nnew, nullptr, 0, m->stream);
+    if (st) return st;
+    CK(cudaStreamSynchronize(m->stream));
+    return status_after(s);
   }
   RunDev R{};
   st = prepare_schedule(s, run, R);
@@ -1089,6 +1425,11 @@ int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps
   bfx_model* m = s->m;
   int32_t st = ensure_stream(m);
   if (st) return st;
+  if (m->stream_regime) {
+    if (!m->x) return fail(BFX_ERR_NO_DATA, "bfx_model_set_data has not been called");
+    cudaStream_t sst = stream_handle ? (cudaStream_t)stream_handle : m->stream;
+    return stream_run(s, run, nsteps, s->gstep, nullptr, 0, nullptr, 0, samples_dev, ring_slots, sst);
+  }
   RunDev R{};
   st = prepare_schedule(s, run, R);
   if (st) return st;
@@ -1117,6 +1458,45 @@ int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps
 int32_t bfx_sampler_launch_count(const bfx_sampler* s, int64_t* n) {
   if (!s || !n) return fail(BFX_ERR_BAD_ARG, "NULL argument");
   *n = s->launches;
+  return BFX_OK;
+}
+
+// ---- minibatch-sharded single chain (SURVEY.md section 8e, configs[2]) -------------------------------
+int32_t bfx_stream_grad_local(bfx_sampler* s, const bfx_run_desc* run, float num_batches, void* stream_handle,
+                              float* buf_dev, int64_t count) {
+  if (!s || !run || !buf_dev) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (count != (int64_t)s->m->M.P + 3) return fail(BFX_ERR_BAD_ARG, "the exchange buffer must hold P + 3 floats");
+  bfx_model* m = s->m;
+  if (!m->stream_regime) return fail(BFX_ERR_UNSUPPORTED, "bfx_stream_*: the model is in the shared-memory regime");
+  if (s->C != 1) return fail(BFX_ERR_BAD_ARG, "a minibatch-sharded sampler carries exactly one chain");
+  if (!s->initialised) return fail(BFX_ERR_STATE, "sampler not initialised");
+  if (!m->x) return fail(BFX_ERR_NO_DATA, "bfx_model_set_data has not been called");
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  cudaStream_t cs = stream_handle ? (cudaStream_t)stream_handle : m->stream;
+  // the local minibatch of this update: this rank's slice of the schedule over ITS shard of the data
+  StreamBatch b = stream_batch(m, run, (unsigned)run->chain_offset, s->gstep);
+  return stream_grad_local(s, 0, b, num_batches, true, cs, buf_dev);
+}
+
+int32_t bfx_stream_apply_update(bfx_sampler* s, const bfx_run_desc* run, float num_batches, void* stream_handle,
+                                float* buf_dev, float* sample_dev) {
+  if (!s || !run || !buf_dev) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  bfx_model* m = s->m;
+  if (!m->stream_regime) return fail(BFX_ERR_UNSUPPORTED, "bfx_stream_*: the model is in the shared-memory regime");
+  if (s->C != 1) return fail(BFX_ERR_BAD_ARG, "a minibatch-sharded sampler carries exactly one chain");
+  cudaStream_t cs = stream_handle ? (cudaStream_t)stream_handle : m->stream;
+  // chain key 0 on every rank: identical Philox streams keep the replicated theta / p / xi bit-identical
+  int32_t st = stream_apply(s, 0, num_batches, true, run->seed, 0u, nullptr, sample_dev, nullptr, cs, buf_dev);
+  if (st) return st;
+  s->gstep += 1;
+  s->launches += 12;
+  return BFX_OK;
+}
+
+int32_t bfx_model_regime(const bfx_model* m, int32_t* regime) {
+  if (!m || !regime) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  *regime = m->stream_regime ? BFX_REGIME_STREAM : BFX_REGIME_SMEM;
   return BFX_OK;
 }
 

@@ -1,0 +1,7 @@
+// One launch shape of the small-P kernels (split so the shapes compile in parallel).
+#include "bfx_kernels_impl.cuh"
+
+namespace bfx {
+cudaError_t launch_eval_tc(const EvalDev& E, cudaStream_t st) { return launch_eval_t<256, 64, true>(E, st); }
+cudaError_t launch_mcmc_tc(const RunDev& R, cudaStream_t st) { return launch_mcmc_t<256, 64, true>(R, st); }
+}  // namespace bfx

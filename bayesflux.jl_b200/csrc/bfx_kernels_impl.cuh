@@ -1,0 +1,167 @@
+// Kernel templates of the small-P regime and their templated launchers (included by the bfx_k_*.cu
+// translation units, each of which instantiates one launch shape).
+//   k_eval  : loglikeprior / ∇loglikeprior for C chains on one (explicit or full) batch
+//   k_mcmc  : nsteps update! calls per chain, theta resident in shared memory
+//   k_debug_*: expose the engine's batch schedule / noise streams to the tests
+#pragma once
+#include <cstdio>
+
+#include "bfx_kernels.h"
+#include "bfx_samplers.cuh"
+
+namespace bfx {
+
+// permutation key of (seed, chain-or-shared, epoch)
+BFX_DEV void perm_keys(unsigned long long seed, unsigned chainkey, unsigned long long epoch, unsigned& k0,
+                       unsigned& k1) {
+  uint4 r = philox4x32_10(make_uint4((unsigned)epoch, (unsigned)(epoch >> 32), chainkey, 0x5eedba7cu),
+                          make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  k0 = r.x;
+  k1 = r.y;
+}
+
+// minibatch of global step `gstep` (0-based): epoch = gstep / nb, batch k = gstep % nb covers
+// positions [k*B, min(n, (k+1)*B)) of that epoch's permutation (abstract.jl:102-105,117-118)
+BFX_DEV void make_batch(const RunDev& R, int c, unsigned long long gstep, BatchSrc& bs, long long& Bk) {
+  bs.n = R.n;
+  bs.full = 0;
+  bs.shuffle = R.shuffle;
+  if (R.idx) {
+    bs.idx = R.idx + (long long)c * R.idx_chain_stride;
+    bs.first = 0;
+    bs.k0 = bs.k1 = 0;
+    Bk = R.B;
+    return;
+  }
+  bs.idx = nullptr;
+  unsigned long long epoch = gstep / (unsigned long long)R.nb, k = gstep % (unsigned long long)R.nb;
+  bs.first = (long long)k * R.B;
+  long long rem = R.n - bs.first;
+  Bk = rem < R.B ? rem : R.B;
+  unsigned chainkey = R.batch_shared ? 0xFFFFFFFFu : (R.chain0 + (unsigned)c);
+  perm_keys(R.seed, chainkey, epoch, bs.k0, bs.k1);
+}
+
+template <int NT>
+BFX_DEV void load_mask(const ModelDev& M, const ChainSmem& s) {
+  for (int i = threadIdx.x; i < M.S / 4; i += NT) s.mask[i] = __ldg(M.pad_mask + i);
+}
+
+template <int NT, int BT, bool TC>
+__global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const ModelDev& M = E.M;
+  ChainSmem s = carve_smem<BT>(M, smem_raw);
+  const int c = blockIdx.x;
+  s.scr = E.scratch ? E.scratch + (long long)c * E.scratch_stride : nullptr;
+  tc::Region tr{};
+  if constexpr (TC) {
+    tr = tc::region_of(M, s);
+    tc::setup<NT>(M, tr);
+  }
+  load_mask<NT>(M, s);
+  for (int k = threadIdx.x; k < M.S; k += NT) s.th[k] = 0.f;
+  __syncthreads();
+  const float* th_in = E.theta + (long long)c * M.P;
+  for_each_flat<NT>(M, [&](int J, int k) { s.th[k] = th_in[J]; });
+  __syncthreads();
+  BatchSrc bs;
+  bs.n = E.n;
+  bs.first = 0;
+  bs.k0 = bs.k1 = 0;
+  bs.shuffle = 0;
+  bs.full = E.idx ? 0 : 1;
+  bs.idx = E.idx ? E.idx + (long long)c * E.idx_chain_stride : nullptr;
+  float gn2;
+  double v;
+  if constexpr (TC) v = tc::chain_eval_tc<NT>(M, s, tr, E.x, E.y, bs, E.B, E.num_batches, E.want_grad != 0, gn2);
+  else v = chain_eval<NT, BT>(M, s, E.x, E.y, bs, E.B, E.num_batches, E.want_grad != 0, gn2);
+  if (threadIdx.x == 0) E.v_out[c] = v;
+  if (E.want_grad) {
+    float* g_out = E.g_out + (long long)c * M.P;
+    for_each_flat<NT>(M, [&](int J, int k) { g_out[J] = s.g[k]; });
+  }
+  if constexpr (TC) tc::teardown<NT>(M, tr);
+}
+
+template <int NT, int BT, int KIND, bool TC>
+__global__ void __launch_bounds__(NT) k_mcmc(const __grid_constant__ RunDev R) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const ModelDev& M = R.M;
+  ChainSmem s = carve_smem<BT>(M, smem_raw);
+  const int c = blockIdx.x;
+  tc::Region tr{};
+  if constexpr (TC) {
+    tr = tc::region_of(M, s);
+    tc::setup<NT>(M, tr);
+  }
+  s.scr = R.scratch ? R.scratch + (long long)c * R.scratch_stride : nullptr;
+  Ctx<NT, BT, TC> X(R, s);
+  X.tcr = &tr;
+  X.c = c;
+  X.key.seed = R.seed;
+  X.key.chain = R.chain0 + (unsigned)c;
+  X.sc = R.sc[c];
+  const long long row = (long long)c * R.Ps;
+  X.th_g = R.theta + row;
+  X.mom = R.mom ? R.mom + row : nullptr;
+  X.minv = R.minv ? R.minv + row : nullptr;
+  X.thold = R.theta_old ? R.theta_old + row : nullptr;
+  X.rmsv = R.rms_v ? R.rms_v + row : nullptr;
+  X.ring = R.ring ? R.ring + (long long)c * R.S.ma_windowlength * R.Ps : nullptr;
+  load_mask<NT>(M, s);
+  for_each_quad<NT>(M, [&](int k) { st4(s.th + k, ld4(X.th_g + k)); });
+  __syncthreads();
+  for (int it = 0; it < R.nsteps; ++it) {
+    if (X.sc.status != 0) break;  // a NaN guard fired: this chain is frozen
+    X.gstep = (unsigned long long)(R.gstep0 + it);
+    make_batch(R, c, X.gstep, X.bs, X.Bk);
+    if (KIND == S_SGLD) step_sgld(X);
+    else if (KIND == S_SGNHT) step_sgnht(X);
+    else if (KIND == S_SGNHTS) step_sgnhts(X);
+    else if (KIND == S_GGMC) step_ggmc(X);
+    else step_hmc(X);
+    __syncthreads();
+    if (R.progress && c == 0 && threadIdx.x == 0) *(volatile unsigned long long*)R.progress = X.gstep + 1ull;
+  }
+  __syncthreads();
+  for_each_quad<NT>(M, [&](int k) { st4(X.th_g + k, ld4(s.th + k)); });
+  if (threadIdx.x == 0) R.sc[c] = X.sc;
+  if constexpr (TC) tc::teardown<NT>(M, tr);
+}
+
+// ---- launchers --------------------------------------------------------------------
+template <int NT, int BT, bool TC = false>
+inline cudaError_t launch_eval_t(const EvalDev& E, cudaStream_t st) {
+  size_t smem = chain_smem_bytes<BT>(E.M) + (size_t)E.M.tc.smem_pad;
+  auto kern = k_eval<NT, BT, TC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<E.C, NT, smem, st>>>(E);
+  return cudaGetLastError();
+}
+
+template <int NT, int BT, bool TC = false>
+inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
+  size_t smem = chain_smem_bytes<BT>(R.M) + (size_t)R.M.tc.smem_pad;
+  cudaError_t e;
+#define BFX_LAUNCH(KIND)                                                                        \
+  {                                                                                             \
+    auto kern = k_mcmc<NT, BT, KIND, TC>;                                                           \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    if (e != cudaSuccess) return e;                                                             \
+    kern<<<R.C, NT, smem, st>>>(R);                                                             \
+  }
+  switch (R.S.kind) {
+    case S_SGLD: BFX_LAUNCH(S_SGLD); break;
+    case S_SGNHT: BFX_LAUNCH(S_SGNHT); break;
+    case S_SGNHTS: BFX_LAUNCH(S_SGNHTS); break;
+    case S_GGMC: BFX_LAUNCH(S_GGMC); break;
+    default: BFX_LAUNCH(S_HMC); break;
+  }
+#undef BFX_LAUNCH
+  return cudaGetLastError();
+}
+
+
+}  // namespace bfx

@@ -247,6 +247,26 @@ int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps
 /* number of kernel launches issued by this sampler handle so far */
 int32_t bfx_sampler_launch_count(const bfx_sampler* s, int64_t* n);
 
+/* ---- large-P regime and the minibatch-sharded single chain (SURVEY.md section 8e, configs[2]) ------------ *
+ * Models whose theta + gradient + one batch tile exceed a CTA's shared memory run in the "stream" regime:
+ * theta in HBM in the flat order, layer-wise GEMMs, SGLD / SGNHT / SGNHTS updates as fused passes with
+ * grid-wide reductions.  Every entry above works unchanged in that regime.  One chain can additionally be
+ * MINIBATCH-SHARDED over ranks (no reference counterpart: the reference is a single process): every rank
+ * holds its shard of the data and an identical copy of the sampler, and each update! is
+ *     bfx_stream_grad_local   -> this rank's likelihood part of the gradient into the CALLER's device buffer of
+ *                                count = P + 3 floats  [num_batches * dloglike/dtheta ; sum1 ; sum2 ; B_local]
+ *     (caller)                   all-reduce(sum) of that buffer over the ranks (NCCL over NVLink)
+ *     bfx_stream_apply_update -> prior and sigma-prior terms added once, update! with identical Philox
+ *                                streams on every rank, so theta / p / xi stay replicated without a broadcast
+ * Both calls only enqueue work on stream_handle (a cudaStream_t, 0 = the engine's stream).
+ * run->batchsize is the LOCAL batch size, num_batches the GLOBAL number of batches. */
+enum { BFX_REGIME_SMEM = 0, BFX_REGIME_STREAM = 1 };
+int32_t bfx_model_regime(const bfx_model* m, int32_t* regime);
+int32_t bfx_stream_grad_local(bfx_sampler* s, const bfx_run_desc* run, float num_batches, void* stream_handle,
+                              float* buf_dev, int64_t count);
+int32_t bfx_stream_apply_update(bfx_sampler* s, const bfx_run_desc* run, float num_batches, void* stream_handle,
+                                float* buf_dev, float* sample_dev /* P floats on the device, or NULL */);
+
 /* ---- test hooks: expose the engine's own random streams so the oracle can
  * replay a device run draw for draw -------------------------------------- */
 /* the minibatch (indices into the data set) chain `chain` uses at global step `step` */

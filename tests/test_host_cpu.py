@@ -70,8 +70,14 @@ def test_model_create_rejects_bad_descriptors():
     assert rc == L.ERR_BAD_ARG
     rc, _ = _mk([(L.DENSE, 5, 1, 0)], prior=L.PriorDesc(L.PRIOR_GAUSSIAN, 0, -1.0, 1.0, 1.0, 0.5))
     assert rc == L.ERR_BAD_ARG
-    # beyond the shared-memory regime -> unsupported, not a crash
-    rc, _ = _mk([(L.DENSE, 64, 512, L.RELU), (L.DENSE, 512, 512, L.RELU), (L.DENSE, 512, 1, 0)])
+    # beyond the shared-memory regime -> the large-P (stream) regime for Dense nets ...
+    rc, h = _mk([(L.DENSE, 64, 512, L.RELU), (L.DENSE, 512, 512, L.RELU), (L.DENSE, 512, 1, 0)])
+    assert rc == L.OK
+    reg = C.c_int32(-1)
+    assert L.lib.bfx_model_regime(h, C.byref(reg)) == L.OK and reg.value == L.REGIME_STREAM
+    L.lib.bfx_model_destroy(h)
+    # ... and unsupported (not a crash) for a recurrent net that large
+    rc, _ = _mk([(L.LSTM, 64, 256, L.TANH), (L.DENSE, 256, 1, 0)])
     assert rc == L.ERR_UNSUPPORTED
 
 
