@@ -70,24 +70,29 @@ class ShardedChain:
         # update with the shared noise key: see bfx_stream_apply_update
         self.run = A._run_desc(local_batchsize, 0, shuffle, partial, True, 1, seed, "per_chain", rank)
         self.nb = float(num_batches)
-        self.buf = torch.empty(self.P + 3, dtype=torch.float32, device=f"cuda:{bnn_local.device}")
+        dev = torch.device("cuda", bnn_local.device)
+        self.buf = torch.empty(self.P + 3, dtype=torch.float32, device=dev)
         self.allreduce = allreduce
+        # a dedicated (non-default) stream: the engine enqueues on it and the collective is ordered after it
+        # (stream handle 0 would mean "the engine's own stream" to the C ABI)
+        self.stream = torch.cuda.Stream(device=dev)
 
     def _reduce(self):
-        if self.allreduce is not None:
-            self.allreduce(self.buf)
-            return
-        dist = self.torch.distributed
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.buf)
+        with self.torch.cuda.stream(self.stream):
+            if self.allreduce is not None:
+                self.allreduce(self.buf)
+                return
+            dist = self.torch.distributed
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(self.buf)
 
     def grad_local(self):
-        st = self.torch.cuda.current_stream().cuda_stream
+        st = self.stream.cuda_stream
         L.check(L.lib.bfx_stream_grad_local(self.sampler._h, C.byref(self.run), self.nb, C.c_void_p(st),
                                             C.c_void_p(self.buf.data_ptr()), self.P + 3))
 
     def apply_update(self, sample_out=None):
-        st = self.torch.cuda.current_stream().cuda_stream
+        st = self.stream.cuda_stream
         ptr = C.c_void_p(sample_out.data_ptr()) if sample_out is not None else None
         L.check(L.lib.bfx_stream_apply_update(self.sampler._h, C.byref(self.run), self.nb, C.c_void_p(st),
                                               C.c_void_p(self.buf.data_ptr()), ptr))
