@@ -75,6 +75,7 @@ struct bfx_sampler {
   int Ps = 0;
   float *theta = nullptr, *mom = nullptr, *minv = nullptr, *theta_old = nullptr, *rms_v = nullptr, *ring = nullptr;
   ChainScalars* sc = nullptr;
+  int* work = nullptr;           // [1 + C] work-item counter and per-chain chunk counters of a launch
   StreamScalars* ssc = nullptr;  // stream regime: per-chain device scalars
   float* gbuf = nullptr;         // stream regime: [P + 3] gradient + likelihood sums (the all-reduce payload)
   unsigned long long* progress_host = nullptr;  // mapped pinned
@@ -736,6 +737,7 @@ static void free_sampler(bfx_sampler* s) {
   cudaFree(s->rms_v);
   cudaFree(s->ring);
   cudaFree(s->sc);
+  cudaFree(s->work);
   cudaFree(s->ssc);
   cudaFree(s->gbuf);
   if (s->progress_host) cudaFreeHost(s->progress_host);
@@ -811,6 +813,7 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
   if (e == cudaSuccess && S.madapter_kind != MA_FIXED) e = cudaMalloc(&s->minv, all);
   if (e == cudaSuccess && S.madapter_kind == MA_RMSPROP) e = cudaMalloc(&s->rms_v, all);
   if (e == cudaSuccess && S.madapter_kind == MA_DIAGCOV) e = cudaMalloc(&s->ring, all * (size_t)S.ma_windowlength);
+  if (e == cudaSuccess) e = cudaMalloc(&s->work, sizeof(int) * ((size_t)nchains + 1));
   if (e == cudaSuccess && m->stream_regime) e = cudaMalloc(&s->ssc, sizeof(StreamScalars) * (size_t)nchains);
   if (e == cudaSuccess && m->stream_regime) e = cudaMalloc(&s->gbuf, ((size_t)m->M.P + 4) * sizeof(float));
   if (e == cudaSuccess) e = cudaHostAlloc(&s->progress_host, sizeof(unsigned long long), cudaHostAllocMapped);
@@ -1039,6 +1042,17 @@ static int32_t fill_run_common(bfx_sampler* s, RunDev& R) {
   return BFX_OK;
 }
 
+// one launch of the persistent (chain, chunk) kernel: reset the work counters, pick the chunk length
+static cudaError_t launch_run(bfx_sampler* s, RunDev& R, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(s->work, 0, sizeof(int) * ((size_t)s->C + 1), st);
+  if (e != cudaSuccess) return e;
+  R.work = s->work;
+  int cl = R.nsteps / 16;
+  R.chunk_len = cl < 1 ? 1 : (cl > 16 ? 16 : cl);
+  R.grid_cap = s->C;
+  return launch_mcmc(R, s->m->cfg, st);
+}
+
 static int ndraws_of(int kind) { return kind == BFX_GGMC ? 2 : 1; }
 
 static int32_t status_after(bfx_sampler* s) {
@@ -1224,7 +1238,7 @@ int32_t bfx_sampler_step_injected(bfx_sampler* s, const int64_t* idx, int64_t B,
   R.nsteps = 1;
   R.inj_normals = d_n;
   R.inj_uniforms = d_u;
-  CKC(launch_mcmc(R, m->cfg, m->stream));
+  CKC(launch_run(s, R, m->stream));
   s->launches += 1;
   s->gstep += 1;
   CKC(cudaStreamSynchronize(m->stream));
@@ -1385,7 +1399,7 @@ int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta
     } else {
       R.samples = nullptr;
     }
-    CKC(launch_mcmc(R, m->cfg, m->stream));
+    CKC(launch_run(s, R, m->stream));
     s->launches += 1;
     s->gstep += R.nsteps;
     if (R.samples) {
@@ -1447,7 +1461,7 @@ int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps
     const int64_t cs = std::min<int64_t>(nsteps - done, 1 << 16);
     R.gstep0 = s->gstep;
     R.nsteps = (int)cs;
-    CK(launch_mcmc(R, m->cfg, stream));
+    CK(launch_run(s, R, stream));
     s->launches += 1;
     s->gstep += cs;
     done += cs;

@@ -173,6 +173,10 @@ struct RunDev {
   unsigned long long* progress;
   float* scratch;              // recurrent path: per-CTA scratch, scratch_stride floats each
   long long scratch_stride;
+  // dynamic (chain, chunk) scheduling of a launch: work[0] = item counter, work[1 + c] = finished chunks of chain c
+  int* work;
+  int chunk_len;               // update! calls per work item
+  long long grid_cap;          // upper bound of the CTA pool (recurrent scratch is sized by it)
 };
 
 // evaluation-only launch (bfx_loglikeprior / bfx_grad_loglikeprior)

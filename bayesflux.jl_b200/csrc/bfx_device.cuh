@@ -152,6 +152,9 @@ BFX_DEV float act_deriv_from_out(int a, float o) {
 }
 
 BFX_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// per-chain state in HBM: L2-coherent load (a chain may be continued by a CTA on another SM, whose L1 could
+// still hold the lines of an earlier chunk)
+BFX_DEV float4 gld4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 BFX_DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 #define BFX_FMA4x4(ACC, WV, AV) \

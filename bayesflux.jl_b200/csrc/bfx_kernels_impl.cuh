@@ -84,49 +84,85 @@ __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) 
   if constexpr (TC) tc::teardown<NT>(M, tr);
 }
 
+// L2-coherent copy of a chain's scalar state (see gld4)
+BFX_DEV ChainScalars load_scalars(const ChainScalars* p) {
+  static_assert(sizeof(ChainScalars) % 8 == 0, "ChainScalars is copied in 8-byte words");
+  ChainScalars out;
+  const long long* src = reinterpret_cast<const long long*>(p);
+  long long* dst = reinterpret_cast<long long*>(&out);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(ChainScalars) / 8); ++i) dst[i] = __ldcg(src + i);
+  return out;
+}
+
+// nsteps update! calls for every chain.  The launch is a pool of persistent CTAs (one or two per SM) that pull
+// (chain, chunk) work items from a counter: item i = chunk i / C of chain i % C, chunk_len updates each.  Chunks
+// of one chain run in order (the per-chain counter work[1 + c] is the hand-over), so a launch is balanced over
+// the SMs for any number of chains instead of running ceil(C / resident CTAs) full waves.
 template <int NT, int BT, int KIND, bool TC>
-__global__ void __launch_bounds__(NT) k_mcmc(const __grid_constant__ RunDev R) {
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_constant__ RunDev R) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_item;
   const ModelDev& M = R.M;
   ChainSmem s = carve_smem<BT>(M, smem_raw);
-  const int c = blockIdx.x;
   tc::Region tr{};
   if constexpr (TC) {
     tr = tc::region_of(M, s);
     tc::setup<NT>(M, tr);
   }
-  s.scr = R.scratch ? R.scratch + (long long)c * R.scratch_stride : nullptr;
+  s.scr = R.scratch ? R.scratch + (long long)blockIdx.x * R.scratch_stride : nullptr;
+  load_mask<NT>(M, s);
+  const int nchunks = (R.nsteps + R.chunk_len - 1) / R.chunk_len;
+  const int total = R.C * nchunks;
   Ctx<NT, BT, TC> X(R, s);
   X.tcr = &tr;
-  X.c = c;
   X.key.seed = R.seed;
-  X.key.chain = R.chain0 + (unsigned)c;
-  X.sc = R.sc[c];
-  const long long row = (long long)c * R.Ps;
-  X.th_g = R.theta + row;
-  X.mom = R.mom ? R.mom + row : nullptr;
-  X.minv = R.minv ? R.minv + row : nullptr;
-  X.thold = R.theta_old ? R.theta_old + row : nullptr;
-  X.rmsv = R.rms_v ? R.rms_v + row : nullptr;
-  X.ring = R.ring ? R.ring + (long long)c * R.S.ma_windowlength * R.Ps : nullptr;
-  load_mask<NT>(M, s);
-  for_each_quad<NT>(M, [&](int k) { st4(s.th + k, ld4(X.th_g + k)); });
-  __syncthreads();
-  for (int it = 0; it < R.nsteps; ++it) {
-    if (X.sc.status != 0) break;  // a NaN guard fired: this chain is frozen
-    X.gstep = (unsigned long long)(R.gstep0 + it);
-    make_batch(R, c, X.gstep, X.bs, X.Bk);
-    if (KIND == S_SGLD) step_sgld(X);
-    else if (KIND == S_SGNHT) step_sgnht(X);
-    else if (KIND == S_SGNHTS) step_sgnhts(X);
-    else if (KIND == S_GGMC) step_ggmc(X);
-    else step_hmc(X);
+  while (true) {
+    if (threadIdx.x == 0) s_item = atomicAdd(R.work, 1);
     __syncthreads();
-    if (R.progress && c == 0 && threadIdx.x == 0) *(volatile unsigned long long*)R.progress = X.gstep + 1ull;
+    const int item = s_item;
+    __syncthreads();
+    if (item >= total) break;
+    const int chunk = item / R.C, c = item - chunk * R.C;
+    if (threadIdx.x == 0) {
+      volatile int* done = R.work + 1 + c;
+      while (*done < chunk) __nanosleep(256);
+      __threadfence();
+    }
+    __syncthreads();
+    X.c = c;
+    X.key.chain = R.chain0 + (unsigned)c;
+    X.sc = load_scalars(R.sc + c);
+    const long long row = (long long)c * R.Ps;
+    X.th_g = R.theta + row;
+    X.mom = R.mom ? R.mom + row : nullptr;
+    X.minv = R.minv ? R.minv + row : nullptr;
+    X.thold = R.theta_old ? R.theta_old + row : nullptr;
+    X.rmsv = R.rms_v ? R.rms_v + row : nullptr;
+    X.ring = R.ring ? R.ring + (long long)c * R.S.ma_windowlength * R.Ps : nullptr;
+    for_each_quad<NT>(M, [&](int k) { st4(s.th + k, gld4(X.th_g + k)); });
+    __syncthreads();
+    const int it0 = chunk * R.chunk_len;
+    const int it1 = it0 + R.chunk_len < R.nsteps ? it0 + R.chunk_len : R.nsteps;
+    for (int it = it0; it < it1; ++it) {
+      if (X.sc.status != 0) break;  // a NaN guard fired: this chain is frozen
+      X.gstep = (unsigned long long)(R.gstep0 + it);
+      make_batch(R, c, X.gstep, X.bs, X.Bk);
+      if (KIND == S_SGLD) step_sgld(X);
+      else if (KIND == S_SGNHT) step_sgnht(X);
+      else if (KIND == S_SGNHTS) step_sgnhts(X);
+      else if (KIND == S_GGMC) step_ggmc(X);
+      else step_hmc(X);
+      __syncthreads();
+      if (R.progress && c == 0 && threadIdx.x == 0) *(volatile unsigned long long*)R.progress = X.gstep + 1ull;
+    }
+    __syncthreads();
+    for_each_quad<NT>(M, [&](int k) { st4(X.th_g + k, ld4(s.th + k)); });
+    if (threadIdx.x == 0) R.sc[c] = X.sc;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(R.work + 1 + c, chunk + 1);
   }
-  __syncthreads();
-  for_each_quad<NT>(M, [&](int k) { st4(X.th_g + k, ld4(s.th + k)); });
-  if (threadIdx.x == 0) R.sc[c] = X.sc;
   if constexpr (TC) tc::teardown<NT>(M, tr);
 }
 
@@ -150,7 +186,33 @@ inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
     auto kern = k_mcmc<NT, BT, KIND, TC>;                                                           \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     if (e != cudaSuccess) return e;                                                             \
-    kern<<<R.C, NT, smem, st>>>(R);                                                             \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+                             (int)cudaSharedmemCarveoutMaxShared);                              \
+    if (e != cudaSuccess) return e;                                                             \
+    int per_sm = 0, dev = 0, sms = 0;                                                           \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);                 \
+    if (e != cudaSuccess) return e;                                                             \
+    cudaGetDevice(&dev);                                                                        \
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                          \
+    {                                                                                           \
+      /* the occupancy query can under-report before the carve-out is applied: bound it by hand. */ \
+      /* Over-subscribing the pool is harmless (late CTAs find the work counter exhausted).     */ \
+      cudaFuncAttributes fa;                                                                    \
+      if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {                                    \
+        long long by_smem = 233472 / (long long)(smem + fa.sharedSizeBytes + 1024);             \
+        long long by_regs = 65536 / ((long long)(fa.numRegs > 0 ? fa.numRegs : 1) * NT);        \
+        long long by_thr = 2048 / NT;                                                           \
+        long long mn = by_smem < by_regs ? by_smem : by_regs;                                   \
+        mn = mn < by_thr ? mn : by_thr;                                                         \
+        mn = mn < 32 ? mn : 32;                                                                 \
+        if (mn > per_sm) per_sm = (int)mn;                                                      \
+      }                                                                                         \
+    }                                                                                           \
+    const long long items = (long long)R.C * ((R.nsteps + R.chunk_len - 1) / R.chunk_len);      \
+    long long grid = (long long)(per_sm > 0 ? per_sm : 1) * sms;                                \
+    if (grid > items) grid = items;                                                             \
+    if (grid > R.grid_cap) grid = R.grid_cap;                                                   \
+    kern<<<(unsigned)grid, NT, smem, st>>>(R);                                                  \
   }
   switch (R.S.kind) {
     case S_SGLD: BFX_LAUNCH(S_SGLD); break;

@@ -121,7 +121,7 @@ BFX_DEV void mass_adapt(Ctx<NT, BT, TC>& X, float gn2) {
     for_each_quad<NT>(R.M, [&](int k) {
       const unsigned m = X.s.mask[k >> 2];
       const float4 g = ld4(X.s.g + k);
-      const float4 V0 = first ? ones4() : ld4(X.rmsv + k);
+      const float4 V0 = first ? ones4() : gld4(X.rmsv + k);
       float4 V, mi;
       BFX_MAP4(V, S.ma_alpha * comp(V0, c) + (1.f - S.ma_alpha) * (comp(g, c) * inv_ng) * (comp(g, c) * inv_ng));
       BFX_MAP4(mi, 1.f / (S.ma_lambda + sqrtf(comp(V, c))));
@@ -138,14 +138,14 @@ BFX_DEV void mass_adapt(Ctx<NT, BT, TC>& X, float gn2) {
       const unsigned m = X.s.mask[k >> 2];
       float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int i = 0; i < w; ++i) {
-        const float4 v = ld4(X.ring + (long long)i * R.Ps + k);
+        const float4 v = gld4(X.ring + (long long)i * R.Ps + k);
         mean.x += v.x; mean.y += v.y; mean.z += v.z; mean.w += v.w;
       }
       const float rw = 1.f / (float)w;
       mean.x *= rw; mean.y *= rw; mean.z *= rw; mean.w *= rw;
       float4 var = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int i = 0; i < w; ++i) {
-        const float4 v = ld4(X.ring + (long long)i * R.Ps + k);
+        const float4 v = gld4(X.ring + (long long)i * R.Ps + k);
         var.x += (v.x - mean.x) * (v.x - mean.x); var.y += (v.y - mean.y) * (v.y - mean.y);
         var.z += (v.z - mean.z) * (v.z - mean.z); var.w += (v.w - mean.w) * (v.w - mean.w);
       }
@@ -210,7 +210,7 @@ BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
     const float4 z = noise_quad(R.M, X.key, X.gstep, 0, inj, k);
-    const float4 p0 = ld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
+    const float4 p0 = gld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
     float4 p, t;
     BFX_MAP4(p, comp(p0, c) - xi * l * comp(p0, c) + l * comp(gg, c) + cn * comp(z, c));  // g here is +∇, the reference's g is -∇
     p = mask4(p, m);
@@ -259,8 +259,8 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
   for_each_quad<NT>(R.M, [&](int k) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
-    const float4 mi = um ? ld4(X.minv + k) : ones4();
-    const float4 p0 = ld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
+    const float4 mi = um ? gld4(X.minv + k) : ones4();
+    const float4 p0 = gld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
     float4 p, t;
     BFX_MAP4(p, comp(p0, c) + hl * comp(gg, c));
     p = mask4(p, m);
@@ -286,8 +286,8 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
     const float4 z = noise_quad(R.M, X.key, X.gstep, 0, inj, k);
-    const float4 mi = um ? ld4(X.minv + k) : ones4();
-    const float4 p0 = ld4(X.mom + k), t0 = ld4(th + k);
+    const float4 mi = um ? gld4(X.minv + k) : ones4();
+    const float4 p0 = gld4(X.mom + k), t0 = ld4(th + k);
     float4 p, t;
     BFX_MAP4(p, e1 * comp(p0, c) + sc * rsqrtf(comp(mi, c)) * comp(z, c));
     p = mask4(p, m);
@@ -342,8 +342,8 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
       const unsigned m = X.s.mask[k >> 2];
       if (!m) return;
       const float4 z = noise_quad(R.M, X.key, X.gstep, 0, inj, k);
-      const float4 mi = um ? ld4(X.minv + k) : ones4();
-      const float4 m0 = ld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
+      const float4 mi = um ? gld4(X.minv + k) : ones4();
+      const float4 m0 = gld4(X.mom + k), gg = ld4(g + k), t0 = ld4(th + k);
       float4 m14, m12, t;
       BFX_MAP4(m14, sa * comp(m0, c) + s1a * rsqrtf(comp(mi, c)) * comp(z, c));  // Mhalf = chol(inv(Minv)) = 1/sqrt(Minv)
       m14 = mask4(m14, m);
@@ -371,8 +371,8 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
       const unsigned m = X.s.mask[k >> 2];
       if (!m) return;
       const float4 z = noise_quad(R.M, X.key, X.gstep, 1, inj, k);
-      const float4 mi = um ? ld4(X.minv + k) : ones4();
-      const float4 m0 = ld4(X.mom + k), gg = ld4(g + k);
+      const float4 mi = um ? gld4(X.minv + k) : ones4();
+      const float4 m0 = gld4(X.mom + k), gg = ld4(g + k);
       float4 m34, mn;
       BFX_MAP4(m34, comp(m0, c) + hh * cs * comp(gg, c));
       m34 = mask4(m34, m);
@@ -402,7 +402,7 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
       X.sc.accepted_total += S.steps;
     } else {
       __syncthreads();
-      for_each_quad<NT>(R.M, [&](int k) { st4(th + k, ld4(X.thold + k)); });
+      for_each_quad<NT>(R.M, [&](int k) { st4(th + k, gld4(X.thold + k)); });
       __syncthreads();
       for (int j = 0; j < S.steps; ++j) record_sample(X, ns - j);
     }
@@ -434,7 +434,7 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
       st4(X.thold + k, ld4(th + k));
       if (!m) return;
       const float4 z = noise_quad(R.M, X.key, X.gstep, 0, inj, k);
-      const float4 mi = um ? ld4(X.minv + k) : ones4();
+      const float4 mi = um ? gld4(X.minv + k) : ones4();
       float4 p;
       BFX_MAP4(p, sqrtf(comp(mi, c)) * comp(z, c));
       p = mask4(p, m);
@@ -445,7 +445,7 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
     X.sc.lMH = 0.5f * acc[0];  // -logpdf(moment_dist, pold) up to the constant that cancels
   } else {
     for_each_quad<NT>(R.M, [&](int k) {  // :124,128
-      const float4 t0 = ld4(th + k), p = ld4(X.mom + k);
+      const float4 t0 = ld4(th + k), p = gld4(X.mom + k);
       st4(th + k, make_float4(t0.x + l * p.x, t0.y + l * p.y, t0.z + l * p.z, t0.w + l * p.w));
     });
   }
@@ -458,13 +458,13 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
   for_each_quad<NT>(R.M, [&](int k) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
-    const float4 p0 = ld4(X.mom + k), gg = ld4(g + k);
+    const float4 p0 = gld4(X.mom + k), gg = ld4(g + k);
     float4 p;
     BFX_MAP4(p, comp(p0, c) + hk * comp(gg, c));  // momentum .-= l*(-∇)/2
     p = mask4(p, m);
     if (last) {
       p = make_float4(-p.x, -p.y, -p.z, -p.w);  // :133
-      const float4 mi = um ? ld4(X.minv + k) : ones4();
+      const float4 mi = um ? gld4(X.minv + k) : ones4();
       acc[0] += p.x * p.x / mi.x + p.y * p.y / mi.y + p.z * p.z / mi.z + p.w * p.w / mi.w;
     }
     st4(X.mom + k, p);
@@ -485,7 +485,7 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
       X.sc.accepted_total += 1;
     } else {
       __syncthreads();
-      for_each_quad<NT>(R.M, [&](int k) { st4(th + k, ld4(X.thold + k)); });
+      for_each_quad<NT>(R.M, [&](int k) { st4(th + k, gld4(X.thold + k)); });
       __syncthreads();
     }
     X.sc.nsampled = ns;
