@@ -13,11 +13,12 @@ IDENTITY, RELU, TANH, SIGMOID = 0, 1, 2, 3
 LIKE_NORMAL, LIKE_TDIST = 0, 1
 SIGMA_GAMMA, SIGMA_INVGAMMA = 0, 1
 PRIOR_GAUSSIAN, PRIOR_MIXTURE = 0, 1
-SGLD, SGNHT, SGNHTS, GGMC, HMC = range(5)
+SGLD, SGNHT, SGNHTS, GGMC, HMC, MODE = range(6)
+OPT_DESCENT, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADAM = range(4)
 STEP_CONSTANT, STEP_DUAL_AVERAGING = 0, 1
 MASS_FIXED, MASS_DIAGCOV, MASS_RMSPROP, MASS_FULLCOV = range(4)
 (STATE_THETA, STATE_MOMENTUM, STATE_MINV, STATE_XI, STATE_STEPSIZE, STATE_T, STATE_NSAMPLED,
- STATE_STATUS) = range(8)
+ STATE_STATUS, STATE_CONVERGED) = range(9)
 BATCH_PER_CHAIN, BATCH_SHARED = 0, 1
 COMPUTE_FP32, COMPUTE_TC_BF16X3 = 0, 1
 REGIME_SMEM, REGIME_STREAM = 0, 1
@@ -47,7 +48,10 @@ class SamplerDesc(C.Structure):
                 ("sigmaA", C.c_float), ("xi", C.c_float), ("mu", C.c_float), ("beta", C.c_float),
                 ("da_target_accept", C.c_float), ("da_gamma", C.c_float), ("da_kappa", C.c_float),
                 ("ma_kappa", C.c_float), ("ma_epsilon", C.c_float), ("ma_lambda", C.c_float),
-                ("ma_alpha", C.c_float)]
+                ("ma_alpha", C.c_float),
+                ("opt_kind", C.c_int32), ("mode_windowlength", C.c_int32), ("opt_eta", C.c_float),
+                ("opt_rho", C.c_float), ("opt_beta2", C.c_float), ("opt_eps", C.c_float),
+                ("mode_abstol", C.c_float), ("_pad2", C.c_float)]
 
 
 class RunDesc(C.Structure):

@@ -452,6 +452,10 @@ class MCMCState:
             d.madapter_kind = L.MASS_FULLCOV
         else:
             d.madapter_kind = L.MASS_FIXED
+        opt = getattr(self, "opt", None)
+        if opt is not None:
+            d.opt_kind, d.opt_eta, d.opt_rho, d.opt_beta2, d.opt_eps = opt.kind, opt.eta, opt.rho, opt.beta2, opt.eps
+            d.mode_windowlength, d.mode_abstol = self.windowlength, self.eps
         return d
 
     # -- device handle ------------------------------------------------------------
@@ -582,6 +586,69 @@ class HMC(MCMCState):
         self.l0, self.path_len, self.maxnorm = l, path_len, maxnorm
         self.sadapter = sadapter or DualAveragingStepSize(l)
         self.madapter = madapter if madapter is not None else FullCovMassAdapter(1000, 100)
+
+
+# ---------------------------------------------------------------- find_mode ---
+@dataclass
+class _FluxOpt:
+    kind: int
+    eta: float
+    rho: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+
+
+def Descent(eta=0.1):
+    """Flux.Optimise.Descent(η)"""
+    return _FluxOpt(L.OPT_DESCENT, eta)
+
+
+def Momentum(eta=0.01, rho=0.9):
+    """Flux.Optimise.Momentum(η, ρ)"""
+    return _FluxOpt(L.OPT_MOMENTUM, eta, rho)
+
+
+def RMSProp(eta=0.001, rho=0.9, eps=1e-8):
+    """Flux.Optimise.RMSProp(η, ρ, ϵ)"""
+    return _FluxOpt(L.OPT_RMSPROP, eta, rho, eps=eps)
+
+
+def ADAM(eta=0.001, beta=(0.9, 0.999), eps=1e-8):
+    """Flux.Optimise.ADAM(η, β, ϵ)"""
+    return _FluxOpt(L.OPT_ADAM, eta, beta[0], beta[1], eps)
+
+
+class FluxModeFinder(MCMCState):
+    """FluxModeFinder(bnn, opt; windowlength = 100, ϵ = 1e-6)  src/inference/mode/flux.jl:8-31"""
+    kind = L.MODE
+
+    def __init__(self, bnn, opt, windowlength=100, eps=1e-6):
+        super().__init__()
+        self.bnn, self.opt, self.windowlength, self.eps = bnn, opt, windowlength, eps
+        self.converged = None
+
+
+def find_mode(bnn: BNN, batchsize: int, epochs: int, optimiser: FluxModeFinder, shuffle=True, partial=True,
+              showprogress=False, theta_start=None, nchains: int = 1, seed: int = 0):
+    """find_mode(bnn, batchsize, epochs, optimiser; shuffle, partial)  src/inference/mode/abstract.jl:36-86, all
+    epochs on the device.  Engine extensions: theta_start (default: draws of bnn.init, one per chain), nchains
+    (many restarts at once), seed.  Returns θmode (P,) or (P, C); optimiser.converged tells which chains met the
+    convergence window (the reference logs "Converged!" / "Failed to converge.")."""
+    if theta_start is None:
+        if bnn.init is None:
+            raise ValueError("theta_start or bnn.init required")
+        theta_start = np.stack([np.concatenate(bnn.init()) for _ in range(nchains)], axis=1)
+    th, nc = _theta_cols(bnn, theta_start)
+    optimiser._bind(bnn, nc)
+    n = bnn.n
+    B = min(batchsize, n)
+    nb = -(-n // B) if partial else max(1, n // B)
+    run = _run_desc(batchsize, epochs * nb, shuffle, partial, False, 1, seed, "per_chain", 0)
+    code = L.lib.bfx_mcmc_run(optimiser._h, C.byref(run), _ptr(th), None, None, None)
+    L.check(code)
+    optimiser.converged = optimiser.get_state(L.STATE_CONVERGED, np.int32, False).astype(bool)
+    theta = optimiser.theta
+    return theta[:, 0] if np.ndim(theta_start) == 1 or nc == 1 and nchains == 1 else theta
 
 
 # --------------------------------------------------------------------- mcmc ---

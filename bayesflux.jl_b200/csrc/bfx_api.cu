@@ -74,6 +74,7 @@ struct bfx_sampler {
   int C = 0;
   int Ps = 0;
   float *theta = nullptr, *mom = nullptr, *minv = nullptr, *theta_old = nullptr, *rms_v = nullptr, *ring = nullptr;
+  float* mode_window = nullptr;
   ChainScalars* sc = nullptr;
   int* work = nullptr;           // [1 + C] work-item counter and per-chain chunk counters of a launch
   StreamScalars* ssc = nullptr;  // stream regime: per-chain device scalars
@@ -736,6 +737,7 @@ static void free_sampler(bfx_sampler* s) {
   cudaFree(s->theta_old);
   cudaFree(s->rms_v);
   cudaFree(s->ring);
+  cudaFree(s->mode_window);
   cudaFree(s->sc);
   cudaFree(s->work);
   cudaFree(s->ssc);
@@ -748,7 +750,13 @@ static void free_sampler(bfx_sampler* s) {
 int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t nchains, bfx_sampler** out) {
   if (!d || !m || !out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
   if (nchains <= 0) return fail(BFX_ERR_BAD_ARG, "nchains must be > 0");
-  if (d->kind < BFX_SGLD || d->kind > BFX_HMC) return fail(BFX_ERR_BAD_ARG, "unknown sampler kind");
+  if (d->kind < BFX_SGLD || d->kind > BFX_MODE) return fail(BFX_ERR_BAD_ARG, "unknown sampler kind");
+  if (d->kind == BFX_MODE) {
+    if (d->opt_kind < BFX_OPT_DESCENT || d->opt_kind > BFX_OPT_ADAM) return fail(BFX_ERR_BAD_ARG, "unknown optimiser");
+    if (d->mode_windowlength < 1) return fail(BFX_ERR_BAD_ARG, "windowlength must be >= 1");
+    if (!(d->opt_eta > 0)) return fail(BFX_ERR_BAD_ARG, "optimiser step size must be > 0");
+    if (m->stream_regime) return fail(BFX_ERR_UNSUPPORTED, "large-P (stream) regime: find_mode is not available");
+  }
   if (d->madapter_kind == BFX_MASS_FULLCOV)
     return fail(BFX_ERR_UNSUPPORTED,
                 "FullCovMassAdapter (dense P x P mass matrix) is outside the many-chain engine; use DiagCovMassAdapter");
@@ -758,7 +766,7 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
     return fail(BFX_ERR_BAD_ARG, "unknown stepsize adapter");
   if (d->kind == BFX_GGMC && d->steps < 1) return fail(BFX_ERR_BAD_ARG, "GGMC steps must be >= 1");
   if (d->kind == BFX_HMC && d->path_len < 1) return fail(BFX_ERR_BAD_ARG, "HMC path_len must be >= 1");
-  if (d->kind != BFX_SGLD && !(d->l > 0)) return fail(BFX_ERR_BAD_ARG, "stepsize l must be > 0");
+  if (d->kind != BFX_SGLD && d->kind != BFX_MODE && !(d->l > 0)) return fail(BFX_ERR_BAD_ARG, "stepsize l must be > 0");
   if (d->madapter_kind == BFX_MASS_DIAGCOV && d->ma_windowlength < 2)
     return fail(BFX_ERR_BAD_ARG, "DiagCov windowlength must be >= 2");
   if (m->stream_regime) {
@@ -781,7 +789,14 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
   S.path_len = d->kind == BFX_HMC ? d->path_len : 1;
   const bool mh = d->kind == BFX_GGMC || d->kind == BFX_HMC;
   S.sadapter_kind = mh ? d->sadapter_kind : SA_CONST;
-  S.madapter_kind = (d->kind == BFX_SGLD || d->kind == BFX_SGNHT) ? MA_FIXED : d->madapter_kind;
+  S.madapter_kind = (d->kind == BFX_SGLD || d->kind == BFX_SGNHT || d->kind == BFX_MODE) ? MA_FIXED : d->madapter_kind;
+  S.opt_kind = d->opt_kind;
+  S.mode_windowlength = d->kind == BFX_MODE ? d->mode_windowlength : 1;
+  S.opt_eta = d->opt_eta;
+  S.opt_rho = d->opt_rho;
+  S.opt_beta2 = d->opt_beta2;
+  S.opt_eps = d->opt_eps;
+  S.mode_abstol = d->mode_abstol;
   S.da_t0 = d->da_t0;
   S.da_adapt_steps = d->da_adapt_steps;
   S.ma_adapt_steps = d->ma_adapt_steps;
@@ -809,7 +824,10 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
   cudaError_t e = cudaMalloc(&s->theta, all);
   if (e == cudaSuccess) e = cudaMalloc(&s->sc, sizeof(ChainScalars) * (size_t)nchains);
   if (e == cudaSuccess && d->kind != BFX_SGLD) e = cudaMalloc(&s->mom, all);
-  if (e == cudaSuccess && mh) e = cudaMalloc(&s->theta_old, all);
+  const bool mode = d->kind == BFX_MODE;
+  if (e == cudaSuccess && (mh || mode)) e = cudaMalloc(&s->theta_old, all);
+  if (e == cudaSuccess && mode) e = cudaMalloc(&s->rms_v, all);
+  if (e == cudaSuccess && mode) e = cudaMalloc(&s->mode_window, sizeof(float) * (size_t)nchains * S.mode_windowlength);
   if (e == cudaSuccess && S.madapter_kind != MA_FIXED) e = cudaMalloc(&s->minv, all);
   if (e == cudaSuccess && S.madapter_kind == MA_RMSPROP) e = cudaMalloc(&s->rms_v, all);
   if (e == cudaSuccess && S.madapter_kind == MA_DIAGCOV) e = cudaMalloc(&s->ring, all * (size_t)S.ma_windowlength);
@@ -853,6 +871,14 @@ int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) {
     CK(cudaStreamSynchronize(m->stream));
   }
   if (s->rms_v) CK(cudaMemsetAsync(s->rms_v, 0, all, m->stream));
+  if (s->S.kind == S_MODE) {
+    // FluxModeFinder: window = fill(-Inf), prevθ = fill(Inf)  (flux.jl:26-27)
+    std::vector<float> inf((size_t)s->Ps * s->C, INFINITY);
+    CK(cudaMemcpyAsync(s->theta_old, inf.data(), all, cudaMemcpyHostToDevice, m->stream));
+    std::vector<float> ninf((size_t)s->C * s->S.mode_windowlength, -INFINITY);
+    CK(cudaMemcpyAsync(s->mode_window, ninf.data(), ninf.size() * 4, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
   if (s->ring) CK(cudaMemsetAsync(s->ring, 0, all * (size_t)s->S.ma_windowlength, m->stream));
   ChainScalars z{};
   z.t = 1;
@@ -866,6 +892,10 @@ int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) {
   z.da_log_avg = 0.f;
   z.ma_t = 1;
   z.status = 0;
+  z.mode_i = 1;
+  z.converged = 0;
+  z.bp1 = s->S.opt_rho;   // ADAM: βp = β  (Flux.Optimise.ADAM state)
+  z.bp2 = s->S.opt_beta2;
   std::vector<ChainScalars> sc((size_t)s->C, z);
   CK(cudaMemcpyAsync(s->sc, sc.data(), sizeof(ChainScalars) * sc.size(), cudaMemcpyHostToDevice, m->stream));
   if (s->ssc) {
@@ -964,10 +994,10 @@ int32_t bfx_sampler_get_state(bfx_sampler* s, int32_t field, void* out, int64_t 
     for (int c = 0; c < C; ++c) o[c] = field == BFX_STATE_T ? sc[c].t : sc[c].nsampled;
     return BFX_OK;
   }
-  if (field == BFX_STATE_STATUS) {
+  if (field == BFX_STATE_STATUS || field == BFX_STATE_CONVERGED) {
     if (nbytes != (int64_t)C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold C int32");
     int32_t* o = static_cast<int32_t*>(out);
-    for (int c = 0; c < C; ++c) o[c] = sc[c].status;
+    for (int c = 0; c < C; ++c) o[c] = field == BFX_STATE_STATUS ? sc[c].status : sc[c].converged;
     return BFX_OK;
   }
   return fail(BFX_ERR_BAD_ARG, "unknown state field");
@@ -1034,6 +1064,7 @@ static int32_t fill_run_common(bfx_sampler* s, RunDev& R) {
   R.theta_old = s->theta_old;
   R.rms_v = s->rms_v;
   R.ring = s->ring;
+  R.mode_window = s->mode_window;
   R.sc = s->sc;
   R.keep_every = 1;
   R.progress = nullptr;

@@ -21,7 +21,8 @@ enum { L_DENSE = 0, L_RNN = 1, L_LSTM = 2 };
 enum { A_IDENTITY = 0, A_RELU = 1, A_TANH = 2, A_SIGMOID = 3 };
 enum { LK_NORMAL = 0, LK_TDIST = 1 };
 enum { SP_GAMMA = 0, SP_INVGAMMA = 1 };
-enum { S_SGLD = 0, S_SGNHT = 1, S_SGNHTS = 2, S_GGMC = 3, S_HMC = 4 };
+enum { S_SGLD = 0, S_SGNHT = 1, S_SGNHTS = 2, S_GGMC = 3, S_HMC = 4, S_MODE = 5 };
+enum { OPT_DESCENT = 0, OPT_MOMENTUM = 1, OPT_RMSPROP = 2, OPT_ADAM = 3 };
 enum { SA_CONST = 0, SA_DUAL = 1 };
 enum { MA_FIXED = 0, MA_DIAGCOV = 1, MA_RMSPROP = 2 };
 
@@ -109,6 +110,9 @@ struct SamplerDev {
   float l, A, sigmaA, xi, mu, beta;
   float da_target_accept, da_gamma, da_kappa, da_mu;
   float ma_kappa, ma_epsilon, ma_lambda, ma_alpha;
+  // find_mode (src/inference/mode/flux.jl): Flux optimiser rule + convergence window
+  int opt_kind, mode_windowlength;
+  float opt_eta, opt_rho, opt_beta2, opt_eps, mode_abstol;
 };
 
 // per-chain scalar state kept in HBM between launches (mutable fields of the
@@ -129,6 +133,9 @@ struct ChainScalars {
   int status;           // 0 | BFX_ERR_NAN_G | BFX_ERR_NAN_THETA
   double start_lp;      // HMC: -loglikeprior(theta_old) cache is NOT used (reference recomputes)
   long long accepted_total;
+  // find_mode: FluxModeFinder.i, convergence flag, ADAM's running beta powers
+  int mode_i, converged;
+  float bp1, bp2;
 };
 
 // everything a launch needs (passed by value as a __grid_constant__ kernel parameter)
@@ -148,6 +155,7 @@ struct RunDev {
   float* theta_old;
   float* rms_v;
   float* ring;  // [C][w][Ps] DiagCov window
+  float* mode_window;  // [C][mode_windowlength] find_mode: max |theta change| of the last steps
   ChainScalars* sc;
   // batch schedule (src/inference/mcmc/abstract.jl:102-105,117-118)
   long long B, nb;

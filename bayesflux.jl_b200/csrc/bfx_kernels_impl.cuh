@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_c
     X.thold = R.theta_old ? R.theta_old + row : nullptr;
     X.rmsv = R.rms_v ? R.rms_v + row : nullptr;
     X.ring = R.ring ? R.ring + (long long)c * R.S.ma_windowlength * R.Ps : nullptr;
+    X.window = R.mode_window ? R.mode_window + (long long)c * R.S.mode_windowlength : nullptr;
     for_each_quad<NT>(M, [&](int k) { st4(s.th + k, gld4(X.th_g + k)); });
     __syncthreads();
     const int it0 = chunk * R.chunk_len;
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_c
       else if (KIND == S_SGNHT) step_sgnht(X);
       else if (KIND == S_SGNHTS) step_sgnhts(X);
       else if (KIND == S_GGMC) step_ggmc(X);
-      else step_hmc(X);
+      else if (KIND == S_HMC) step_hmc(X);
+      else step_mode(X);
       __syncthreads();
       if (R.progress && c == 0 && threadIdx.x == 0) *(volatile unsigned long long*)R.progress = X.gstep + 1ull;
     }
@@ -219,7 +221,8 @@ inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
     case S_SGNHT: BFX_LAUNCH(S_SGNHT); break;
     case S_SGNHTS: BFX_LAUNCH(S_SGNHTS); break;
     case S_GGMC: BFX_LAUNCH(S_GGMC); break;
-    default: BFX_LAUNCH(S_HMC); break;
+    case S_HMC: BFX_LAUNCH(S_HMC); break;
+    default: BFX_LAUNCH(S_MODE); break;
   }
 #undef BFX_LAUNCH
   return cudaGetLastError();

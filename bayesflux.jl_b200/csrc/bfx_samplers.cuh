@@ -21,6 +21,7 @@ struct Ctx {
   float* thold;
   float* rmsv;
   float* ring;
+  float* window;  // find_mode convergence window of this chain
   BatchSrc bs;   // minibatch of the current step
   long long Bk;  // its size
   unsigned long long gstep;
@@ -492,6 +493,97 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
     record_sample(X, ns);
   }
   X.sc.current_step = last ? 1 : stage + 1;
+  X.sc.t += 1;
+}
+
+// --------------------------------------------------------------------------------
+// find_mode: FluxModeFinder.step!  (src/inference/mode/flux.jl:33-54) with the Flux.Optimise rule
+// applied to -g (Flux minimises).  Optimiser state: m in the momentum vector, v in the RMSProp vector,
+// prevθ in the θold vector.  A converged chain is frozen (find_mode returns at that point,
+// src/inference/mode/abstract.jl:74-78).
+// --------------------------------------------------------------------------------
+template <int NT>
+BFX_DEV float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (NT > 32) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    v = red[0];
+#pragma unroll
+    for (int ww = 1; ww < NT / 32; ++ww) v = fmaxf(v, red[ww]);
+  }
+  return v;
+}
+
+template <int NT, int BT, bool TC>
+BFX_DEV void step_mode(Ctx<NT, BT, TC>& X) {
+  const RunDev& R = X.R;
+  const SamplerDev& S = R.S;
+  if (X.sc.converged) return;
+  const int w = S.mode_windowlength;
+  if (X.sc.mode_i == 1) {  // flux.jl:36-41
+    float mx = 0.f;
+    for (int i = threadIdx.x; i < w; i += NT) mx = fmaxf(mx, fabsf(__ldcg(X.window + i)));
+    mx = block_max<NT>(mx, X.s.red);
+    if (mx <= S.mode_abstol) {
+      X.sc.converged = 1;
+      return;
+    }
+  }
+  float gn2;
+  X.grad(gn2);
+  float* th = X.s.th;
+  const float* g = X.s.g;
+  const float eta = S.opt_eta, rho = S.opt_rho, b2 = S.opt_beta2, eps = S.opt_eps;
+  const float c1 = 1.f / (1.f - X.sc.bp1), c2 = 1.f / (1.f - X.sc.bp2);
+  float mx = 0.f;
+  for_each_quad<NT>(R.M, [&](int k) {
+    const unsigned m = X.s.mask[k >> 2];
+    if (!m) return;
+    const float4 t0 = ld4(th + k), gg = ld4(g + k), pv = gld4(X.thold + k);
+    const float4 ch = mask4(make_float4(fabsf(pv.x - t0.x), fabsf(pv.y - t0.y), fabsf(pv.z - t0.z), fabsf(pv.w - t0.w)), m);
+    mx = fmaxf(mx, fmaxf(fmaxf(ch.x, ch.y), fmaxf(ch.z, ch.w)));  // maximum(abs, prevθ - θ)   :44
+    st4(X.thold + k, t0);                                          // prevθ = copy(θ)            :46
+    float4 step;
+    if (S.opt_kind == OPT_DESCENT) {
+      BFX_MAP4(step, eta * -comp(gg, c));
+    } else if (S.opt_kind == OPT_MOMENTUM) {
+      const float4 v0 = gld4(X.mom + k);
+      float4 v;
+      BFX_MAP4(v, rho * comp(v0, c) - eta * -comp(gg, c));
+      st4(X.mom + k, mask4(v, m));
+      BFX_MAP4(step, -comp(v, c));
+    } else if (S.opt_kind == OPT_RMSPROP) {
+      const float4 a0 = gld4(X.rmsv + k);
+      float4 a;
+      BFX_MAP4(a, rho * comp(a0, c) + (1.f - rho) * comp(gg, c) * comp(gg, c));
+      st4(X.rmsv + k, mask4(a, m));
+      BFX_MAP4(step, -comp(gg, c) * (eta / (sqrtf(comp(a, c)) + eps)));
+    } else {  // ADAM
+      const float4 m0 = gld4(X.mom + k), v0 = gld4(X.rmsv + k);
+      float4 mt, vt;
+      BFX_MAP4(mt, rho * comp(m0, c) + (1.f - rho) * -comp(gg, c));
+      BFX_MAP4(vt, b2 * comp(v0, c) + (1.f - b2) * comp(gg, c) * comp(gg, c));
+      st4(X.mom + k, mask4(mt, m));
+      st4(X.rmsv + k, mask4(vt, m));
+      BFX_MAP4(step, comp(mt, c) * c1 / (sqrtf(comp(vt, c) * c2) + eps) * eta);
+    }
+    float4 o;
+    BFX_MAP4(o, comp(t0, c) - comp(step, c));                      // Flux.update!(opt, θ, -g)   :51
+    st4(th + k, mask4(o, m));
+  });
+  mx = block_max<NT>(mx, X.s.red);
+  if (threadIdx.x == 0) X.window[X.sc.mode_i - 1] = mx;            // :45
+  X.sc.mode_i = X.sc.mode_i == w ? 1 : X.sc.mode_i + 1;            // :47
+  if (S.opt_kind == OPT_ADAM) {
+    X.sc.bp1 *= rho;
+    X.sc.bp2 *= b2;
+  }
+  __syncthreads();
+  X.sc.nsampled += 1;
   X.sc.t += 1;
 }
 

@@ -92,7 +92,10 @@ typedef struct bfx_model bfx_model;     /* opaque: BNN (src/model/BNN.jl:5-38) o
 typedef struct bfx_sampler bfx_sampler; /* opaque: MCMCState for nchains chains            */
 
 /* ---- samplers ---------------------------------------------------------- */
-enum { BFX_SGLD = 0, BFX_SGNHT = 1, BFX_SGNHTS = 2, BFX_GGMC = 3, BFX_HMC = 4 };
+enum { BFX_SGLD = 0, BFX_SGNHT = 1, BFX_SGNHTS = 2, BFX_GGMC = 3, BFX_HMC = 4,
+       BFX_MODE = 5 /* find_mode: FluxModeFinder + a Flux optimiser, src/inference/mode/flux.jl:8-54 */ };
+/* Flux.Optimise rules usable by BFX_MODE (Flux 0.13 semantics, applied to -g) */
+enum { BFX_OPT_DESCENT = 0, BFX_OPT_MOMENTUM = 1, BFX_OPT_RMSPROP = 2, BFX_OPT_ADAM = 3 };
 enum { BFX_STEP_CONSTANT = 0, BFX_STEP_DUAL_AVERAGING = 1 };
 enum { BFX_MASS_FIXED = 0, BFX_MASS_DIAGCOV = 1, BFX_MASS_RMSPROP = 2, BFX_MASS_FULLCOV = 3 /* rejected */ };
 
@@ -102,6 +105,9 @@ enum { BFX_MASS_FIXED = 0, BFX_MASS_DIAGCOV = 1, BFX_MASS_RMSPROP = 2, BFX_MASS_
  *   SGNHTS sgnht-s.jl:41-47   l, sigmaA, xi, mu, madapter
  *   GGMC   ggmc.jl:59-67      beta, l, steps, maxnorm, sadapter, madapter
  *   HMC    hmc.jl:59-65       l, path_len, maxnorm, sadapter, madapter
+ *   MODE   mode/flux.jl:18-31 opt_*, mode_windowlength, mode_abstol  (find_mode = bfx_mcmc_run with
+ *                             numsamples = epochs * num_batches update steps and samples_out = NULL; the
+ *                             result is BFX_STATE_THETA, convergence per chain BFX_STATE_CONVERGED)
  *   DualAveragingStepSize dualaveragestepsize.jl:25-32; DiagCovMassAdapter
  *   diagcovariancemassadapter.jl:23-33; RMSPropMassAdapter rmspropmassadapter.jl:17-24 */
 typedef struct bfx_sampler_desc {
@@ -126,6 +132,13 @@ typedef struct bfx_sampler_desc {
   float da_target_accept, da_gamma, da_kappa;
   float ma_kappa, ma_epsilon; /* DiagCov */
   float ma_lambda, ma_alpha;  /* RMSProp */
+  /* BFX_MODE: FluxModeFinder(bnn, opt; windowlength, ϵ) flux.jl:18-31 and the optimiser's hyper-parameters
+   * (Descent η; Momentum η, ρ; RMSProp η, ρ, ϵ; ADAM η, β1 = opt_rho, β2, ϵ) */
+  int32_t opt_kind;
+  int32_t mode_windowlength;
+  float opt_eta, opt_rho, opt_beta2, opt_eps;
+  float mode_abstol;
+  float _pad2;
 } bfx_sampler_desc;
 
 /* state fields for bfx_sampler_get_state / set_state (checkpoint / resume,
@@ -138,7 +151,8 @@ enum {
   BFX_STATE_STEPSIZE = 4, /* float  C       l */
   BFX_STATE_T = 5,        /* int64  C       step counter t (1-based like the reference) */
   BFX_STATE_NSAMPLED = 6, /* int64  C */
-  BFX_STATE_STATUS = 7    /* int32  C       BFX_OK | BFX_ERR_NAN_G | BFX_ERR_NAN_THETA */
+  BFX_STATE_STATUS = 7,   /* int32  C       BFX_OK | BFX_ERR_NAN_G | BFX_ERR_NAN_THETA */
+  BFX_STATE_CONVERGED = 8 /* int32  C       BFX_MODE: 1 once the convergence window fell below ϵ */
 };
 
 enum { BFX_BATCH_PER_CHAIN = 0, BFX_BATCH_SHARED = 1 };

@@ -968,3 +968,92 @@ def mcmc(m: Model, x, y, batchsize, numsamples, sampler, theta_start, rng,
             theta = sampler.update(theta, grad_fn, full_lp, normals, uniforms)
             step += 1
     return sampler.samples
+
+
+# --------------------------------------------------------------------------
+# find_mode: src/inference/mode/abstract.jl:36-86,
+# src/inference/mode/flux.jl:8-54.  The optimisers are Flux.Optimise rules
+# (third party, Flux 0.13: Descent, Momentum, RMSProp, ADAM with EPS = 1e-8),
+# applied to -g because Flux minimises (flux.jl:49-51).
+# --------------------------------------------------------------------------
+OPT_DESCENT, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADAM = 0, 1, 2, 3
+
+
+@dataclass
+class FluxOptimiser:
+    kind: int = OPT_ADAM
+    eta: float = 0.001
+    rho: float = 0.9       # Momentum rho / RMSProp rho / ADAM beta1
+    beta2: float = 0.999   # ADAM beta2
+    eps: float = 1e-8
+    m: Optional[np.ndarray] = None
+    v: Optional[np.ndarray] = None
+    bp1: float = 0.0
+    bp2: float = 0.0
+
+    def apply(self, theta, delta):
+        """Flux.update!(opt, theta, delta): theta .-= apply!(opt, theta, delta)."""
+        dt = theta.dtype
+        f = dt.type
+        if self.m is None:
+            self.m = np.zeros_like(theta)
+            self.v = np.zeros_like(theta)
+            self.bp1, self.bp2 = self.rho, self.beta2
+        if self.kind == OPT_DESCENT:
+            step = f(self.eta) * delta
+        elif self.kind == OPT_MOMENTUM:
+            self.m = (f(self.rho) * self.m - f(self.eta) * delta).astype(dt)
+            step = -self.m
+        elif self.kind == OPT_RMSPROP:
+            self.v = (f(self.rho) * self.v + f(1.0 - self.rho) * delta * delta).astype(dt)
+            step = delta * (f(self.eta) / (np.sqrt(self.v) + f(self.eps)))
+        else:
+            self.m = (f(self.rho) * self.m + f(1.0 - self.rho) * delta).astype(dt)
+            self.v = (f(self.beta2) * self.v + f(1.0 - self.beta2) * delta * delta).astype(dt)
+            step = self.m / f(1.0 - self.bp1) / (np.sqrt(self.v / f(1.0 - self.bp2)) + f(self.eps)) * f(self.eta)
+            self.bp1 *= self.rho
+            self.bp2 *= self.beta2
+        return (theta - step.astype(dt)).astype(dt)
+
+
+@dataclass
+class FluxModeFinder:
+    """src/inference/mode/flux.jl:8-54."""
+    opt: FluxOptimiser
+    windowlength: int = 100
+    eps: float = 1e-6
+    window: Optional[np.ndarray] = None
+    prev: Optional[np.ndarray] = None
+    i: int = 1
+
+    def step(self, theta, grad_fn):
+        if self.window is None:
+            self.window = np.full(self.windowlength, -np.inf, theta.dtype)
+            self.prev = np.full(theta.size, np.inf, theta.dtype)
+        if self.i == 1:                                          # flux.jl:36-41
+            if float(np.max(np.abs(self.window))) <= self.eps:
+                return theta, True
+        _, g = grad_fn(theta)                                    # :43
+        self.window[self.i - 1] = np.max(np.abs(self.prev - theta))  # :44-45
+        self.prev = theta.copy()                                 # :46
+        self.i = 1 if self.i == self.windowlength else self.i + 1   # :47
+        theta = self.opt.apply(theta, -g)                        # :51
+        return theta, False
+
+
+def find_mode(m: Model, x, y, batchsize, epochs, finder: FluxModeFinder, theta_start, rng=None, shuffle=True,
+              partial=True, perms=None):
+    """src/inference/mode/abstract.jl:36-86 (theta_start replaces the bnn.init() draw)."""
+    n = y.shape[0]
+    theta = theta_start.copy()
+    slices = batch_slices(n, batchsize, partial)
+    nb = len(slices)
+    for e in range(epochs):
+        perm = perms(e) if perms is not None else (rng.permutation(n) if shuffle else np.arange(n))
+        for (s, t) in slices:
+            idx = perm[s:t]
+            xb, yb = take_batch(x, y, idx)
+            theta, conv = finder.step(theta, lambda th, xb=xb, yb=yb: grad_loglikeprior(m, th, xb, yb, float(nb)))
+            if conv:
+                return theta, True
+    return theta, False
