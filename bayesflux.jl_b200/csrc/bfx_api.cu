@@ -345,17 +345,37 @@ extern "C" {
 
 int32_t bfx_model_set_compute(bfx_model* m, int32_t mode) {
   if (!m) return fail(BFX_ERR_BAD_ARG, "model is NULL");
+  if (mode != BFX_COMPUTE_FP32 && mode != BFX_COMPUTE_TC_BF16X3) return fail(BFX_ERR_BAD_ARG, "unknown compute mode");
+  if (m->stream_regime) {
+    // large-P regime: per layer, the three GEMMs go to the tcgen05 kernel when the layer is a real GEMM whose
+    // operands can be fetched in aligned 16-byte chunks (bfx_stream_tc.cu)
+    int any = 0;
+    for (int l = 0; l < m->SM.nlayers; ++l) {
+      StreamLayer& L = m->SM.L[l];
+      L.tc = mode == BFX_COMPUTE_TC_BF16X3 && L.nout >= 64 && L.nin >= 16 && L.nout % 8 == 0 && L.nin % 8 == 0 &&
+             L.w_off % 8 == 0;
+      any |= L.tc;
+    }
+    if (mode == BFX_COMPUTE_TC_BF16X3 && !any)
+      return fail(BFX_ERR_UNSUPPORTED, "tensor-core path: no layer of this network is a 16-byte aligned GEMM of width >= 64");
+    m->SM.tc = any;
+    if (m->W.Bc) {  // the workspace depends on the mode
+      cudaSetDevice(m->device);
+      if (m->stream) cudaStreamSynchronize(m->stream);
+      stream_work_free(m->W);
+    }
+    return BFX_OK;
+  }
   if (mode == BFX_COMPUTE_FP32) {
     m->M.tc = TcDesc{};
     return BFX_OK;
   }
-  if (mode == BFX_COMPUTE_TC_BF16X3) return build_tc(m);
-  return fail(BFX_ERR_BAD_ARG, "unknown compute mode");
+  return build_tc(m);
 }
 
 int32_t bfx_model_get_compute(const bfx_model* m, int32_t* mode) {
   if (!m || !mode) return fail(BFX_ERR_BAD_ARG, "NULL argument");
-  *mode = m->M.tc.enabled ? BFX_COMPUTE_TC_BF16X3 : BFX_COMPUTE_FP32;
+  *mode = (m->M.tc.enabled || m->SM.tc) ? BFX_COMPUTE_TC_BF16X3 : BFX_COMPUTE_FP32;
   return BFX_OK;
 }
 

@@ -27,6 +27,8 @@ struct GemmArgs {
   int accumulate;      // EPI_PLAIN: C += acc
   long long kchunk;    // split-K: blockIdx.z handles k in [z*kchunk, (z+1)*kchunk) and writes C + z*part_stride
   long long part_stride;
+  __nv_bfloat16* chi;  // optional BF16 halves of the output (tensor-core consumers)
+  __nv_bfloat16* clo;
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 16, GLD = 132;
@@ -97,6 +99,11 @@ __global__ void __launch_bounds__(256) k_sgemm(const GemmArgs g) {
       else if (EPI == EPI_MUL_DACT) v *= act_deriv_from_out(g.act, __ldg(g.aux + m + g.ldaux * n));
       else if (g.accumulate) v += C[m + g.ldc * n];
       C[m + g.ldc * n] = v;
+      if (g.chi) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        g.chi[m + g.ldc * n] = h;
+        g.clo[m + g.ldc * n] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
     }
   }
 }
@@ -120,8 +127,38 @@ static cudaError_t launch_gemm(const GemmArgs& g, int ksplit, cudaStream_t st) {
 // =====================================================================================================
 // batch gather, likelihood, scalar kernels
 // =====================================================================================================
+// FP32 array -> BF16 hi / lo halves (theta after an update; activations produced by an FP32 layer)
+__global__ void k_split(const float* __restrict__ src, long long n, __nv_bfloat16* __restrict__ hi,
+                        __nv_bfloat16* __restrict__ lo) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// bias gradient of a tensor-core layer: db[o] += sum_b D[o + nout*b], deterministic two-level sum
+__global__ void k_rowsum_part(const float* __restrict__ D, int nout, int nc, float* __restrict__ part) {
+  const int o = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int sy = threadIdx.x >> 5;                      // 8 sub-slices per block
+  const int slice = blockIdx.y * 8 + sy, nslices = gridDim.y * 8;
+  float s = 0.f;
+  if (o < nout)
+    for (int b = slice; b < nc; b += nslices) s += D[o + (long long)nout * b];
+  if (o < nout) part[(long long)slice * nout + o] = s;
+}
+__global__ void k_rowsum_final(const float* __restrict__ part, int nout, int nslices, float* __restrict__ g) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nout) return;
+  float s = 0.f;
+  for (int i = 0; i < nslices; ++i) s += part[(long long)i * nout + o];
+  g[o] += s;
+}
+
 __global__ void k_gather(const float* __restrict__ x, const float* __restrict__ y, StreamBatch b, long long c0, int nc,
-                         int d, float* __restrict__ X, float* __restrict__ yb) {
+                         int d, float* __restrict__ X, float* __restrict__ yb, __nv_bfloat16* __restrict__ xhi,
+                         __nv_bfloat16* __restrict__ xlo) {
   // one warp per column: the d features of an observation are contiguous in x
   const int lane = threadIdx.x & 31;
   const long long col = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -129,7 +166,15 @@ __global__ void k_gather(const float* __restrict__ x, const float* __restrict__ 
   BatchSrc bs;
   bs.idx = b.idx; bs.n = b.n; bs.first = b.first; bs.k0 = b.k0; bs.k1 = b.k1; bs.shuffle = b.shuffle; bs.full = b.full;
   const long long o = batch_obs(bs, c0 + col);
-  for (int f = lane; f < d; f += 32) X[col * d + f] = __ldg(x + o * d + f);
+  for (int f = lane; f < d; f += 32) {
+    const float v = __ldg(x + o * d + f);
+    X[col * d + f] = v;
+    if (xhi) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      xhi[col * d + f] = h;
+      xlo[col * d + f] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
   if (lane == 0) yb[col] = __ldg(y + o);
 }
 
@@ -279,6 +324,21 @@ cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W)
   }
   W.part_floats = big * 32;
   if (e == cudaSuccess) e = cudaMalloc(&W.part, (size_t)W.part_floats * sizeof(float));
+  if (M.tc) {
+    if (e == cudaSuccess) e = cudaMalloc(&W.rowpart, (size_t)64 * maxw * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&W.act_hi[0], (size_t)M.d_in * Bc * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&W.act_lo[0], (size_t)M.d_in * Bc * 2);
+    for (int l = 0; l < M.nlayers && e == cudaSuccess; ++l) {
+      e = cudaMalloc(&W.act_hi[l + 1], (size_t)M.L[l].nout * Bc * 2);
+      if (e == cudaSuccess) e = cudaMalloc(&W.act_lo[l + 1], (size_t)M.L[l].nout * Bc * 2);
+    }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+      e = cudaMalloc(&W.delta_hi[i], (size_t)maxw * Bc * 2);
+      if (e == cudaSuccess) e = cudaMalloc(&W.delta_lo[i], (size_t)maxw * Bc * 2);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&W.w_hi, (size_t)(M.P + 8) * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&W.w_lo, (size_t)(M.P + 8) * 2);
+  }
   if (e != cudaSuccess) stream_work_free(W);
   return e;
 }
@@ -290,6 +350,17 @@ void stream_work_free(StreamWork& W) {
   cudaFree(W.yb);
   cudaFree(W.dl);
   cudaFree(W.part);
+  cudaFree(W.rowpart);
+  for (int l = 0; l <= BFX_MAX_LAYERS; ++l) {
+    cudaFree(W.act_hi[l]);
+    cudaFree(W.act_lo[l]);
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(W.delta_hi[i]);
+    cudaFree(W.delta_lo[i]);
+  }
+  cudaFree(W.w_hi);
+  cudaFree(W.w_lo);
   W = StreamWork{};
 }
 
@@ -313,16 +384,32 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
                              const StreamBatch& b, float nb, bool want_grad, float* g, StreamScalars* sc,
                              cudaStream_t st) {
   const int nl = M.nlayers;
+  if (M.tc) {  // BF16 halves of theta for the tensor-core layers
+    k_split<<<592, 256, 0, st>>>(theta, M.P, W.w_hi, W.w_lo);
+    SCK(cudaGetLastError());
+  }
   for (long long c0 = 0; c0 < b.B; c0 += W.Bc) {
     const int nc = (int)((b.B - c0) < W.Bc ? (b.B - c0) : W.Bc);
     {
       const long long threads = (long long)nc * 32;
-      k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, y, b, c0, nc, M.d_in, W.act[0], W.yb);
+      k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, y, b, c0, nc, M.d_in, W.act[0], W.yb,
+                                                               M.tc ? W.act_hi[0] : nullptr, M.tc ? W.act_lo[0] : nullptr);
       SCK(cudaGetLastError());
     }
     // forward: act[l+1] (nout x nc) = act(W_l act[l] + b_l)
     for (int l = 0; l < nl; ++l) {
       const StreamLayer& L = M.L[l];
+      if (L.tc) {
+        TcGemmArgs t{};
+        t.M = L.nout; t.N = nc; t.K = L.nin;
+        t.A = TcOperand{W.w_hi + L.w_off, W.w_lo + L.w_off, L.nout};
+        t.B = TcOperand{W.act_hi[l], W.act_lo[l], L.nin};
+        t.C = W.act[l + 1]; t.Chi = W.act_hi[l + 1]; t.Clo = W.act_lo[l + 1]; t.ldc = L.nout;
+        t.bias = theta + L.b_off; t.act = L.act;
+        t.kchunk = L.nin; t.part_stride = 0;
+        SCK(tc_gemm_forward(t, st));
+        continue;
+      }
       GemmArgs a{};
       a.M = L.nout; a.N = nc; a.K = L.nin;
       a.A = theta + L.w_off; a.sam = 1; a.sak = L.nout;
@@ -330,6 +417,7 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
       a.C = W.act[l + 1]; a.ldc = L.nout;
       a.bias = theta + L.b_off; a.act = L.act;
       a.kchunk = L.nin; a.part_stride = 0;
+      if (M.tc && l + 1 < nl && M.L[l + 1].tc) { a.chi = W.act_hi[l + 1]; a.clo = W.act_lo[l + 1]; }
       SCK((launch_gemm<true, true, EPI_BIAS_ACT>(a, 1, st)));
     }
     k_like<<<148, 256, 0, st>>>(M, theta, W.act[nl], W.yb, nc, nb, M.L[nl - 1].act, W.dl, sc);
@@ -337,9 +425,54 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
     if (!want_grad) continue;
     // backward: delta of layer l in D (nout x nc); the output layer's delta is dl (1 x nc)
     const float* D = W.dl;
+    const __nv_bfloat16 *Dhi = nullptr, *Dlo = nullptr;
     int ping = 0;
     for (int l = nl - 1; l >= 0; --l) {
       const StreamLayer& L = M.L[l];
+      if (L.tc) {
+        // dW (nout x nin) += D * act[l]^T on the tensor cores, split over the batch; db by a deterministic row sum
+        const long long cnt = (long long)L.nout * L.nin;
+        int ksplit = 1;
+        const int tiles = ((L.nout + 127) / 128) * ((L.nin + 127) / 128);
+        while (ksplit < 32 && tiles * ksplit < 148 && (nc / (ksplit * 2)) >= 512) ksplit *= 2;
+        TcGemmArgs t{};
+        t.M = L.nout; t.N = L.nin; t.K = nc;
+        t.A = TcOperand{Dhi, Dlo, L.nout};
+        t.B = TcOperand{W.act_hi[l], W.act_lo[l], L.nin};
+        t.ldc = L.nout;
+        if (ksplit == 1) {
+          t.C = g + L.w_off; t.accumulate = 1; t.kchunk = nc; t.part_stride = 0;
+          SCK(tc_gemm_dw(t, 1, st));
+        } else {
+          long long kch = (nc + ksplit - 1) / ksplit;
+          kch = (kch + 63) / 64 * 64;
+          t.C = W.part; t.accumulate = 0; t.kchunk = kch; t.part_stride = cnt;
+          SCK(tc_gemm_dw(t, ksplit, st));
+          k_reduce_parts<<<(unsigned)((cnt + 255) / 256 < 1184 ? (cnt + 255) / 256 : 1184), 256, 0, st>>>(g + L.w_off, W.part, cnt, ksplit, cnt, 1);
+          SCK(cudaGetLastError());
+        }
+        {
+          dim3 grid((L.nout + 31) / 32, 8);
+          k_rowsum_part<<<grid, 256, 0, st>>>(D, L.nout, nc, W.rowpart);
+          SCK(cudaGetLastError());
+          k_rowsum_final<<<(L.nout + 127) / 128, 128, 0, st>>>(W.rowpart, L.nout, 64, g + L.b_off);
+          SCK(cudaGetLastError());
+        }
+        if (l > 0) {
+          // delta_{l-1} (nin x nc) = (W_l^T D) .* act'(act[l])
+          TcGemmArgs u{};
+          u.M = L.nin; u.N = nc; u.K = L.nout;
+          u.A = TcOperand{W.w_hi + L.w_off, W.w_lo + L.w_off, L.nout};
+          u.B = TcOperand{Dhi, Dlo, L.nout};
+          u.C = W.delta[ping]; u.Chi = W.delta_hi[ping]; u.Clo = W.delta_lo[ping]; u.ldc = L.nin;
+          u.aux = W.act[l]; u.ldaux = L.nin; u.act = M.L[l - 1].act;
+          u.kchunk = L.nout; u.part_stride = 0;
+          SCK(tc_gemm_dx(u, st));
+          D = W.delta[ping]; Dhi = W.delta_hi[ping]; Dlo = W.delta_lo[ping];
+          ping ^= 1;
+        }
+        continue;
+      }
       // [dW | db] (nout x (nin+1), exactly the flat layout of the layer) += D * [act[l] ; 1]^T, split over the batch
       {
         const long long cnt = (long long)L.nout * (L.nin + 1);
@@ -370,8 +503,9 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
         a.C = W.delta[ping]; a.ldc = L.nin;
         a.aux = W.act[l]; a.ldaux = L.nin; a.act = M.L[l - 1].act;
         a.kchunk = L.nout; a.part_stride = 0;
+        if (M.tc && M.L[l - 1].tc) { a.chi = W.delta_hi[ping]; a.clo = W.delta_lo[ping]; }
         SCK((launch_gemm<false, true, EPI_MUL_DACT>(a, 1, st)));
-        D = W.delta[ping];
+        D = W.delta[ping]; Dhi = W.delta_hi[ping]; Dlo = W.delta_lo[ping];
         ping ^= 1;
       }
     }

@@ -9,6 +9,7 @@
 // (src/model/BNN.jl:50-69, src/likelihoods/feedforward.jl:30-43,86-97, src/netpriors/*.jl,
 // src/inference/mcmc/sgld.jl:96-112, sgnht.jl:64-90, sgnht-s.jl:81-116).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "bfx_common.cuh"
@@ -19,6 +20,7 @@ namespace bfx {
 struct StreamLayer {
   int nin, nout, act;
   long long w_off, b_off;
+  int tc;  // 1: this layer's three GEMMs run on the tensor cores (bfx_stream_tc.cu)
 };
 
 struct StreamModel {
@@ -29,6 +31,7 @@ struct StreamModel {
   float nu, sprior_a, sprior_b, prior_c2;
   double prior_c0n, tdist_const, sprior_const;
   StreamLayer L[BFX_MAX_LAYERS];
+  int tc;  // any layer on the tensor cores
 };
 
 // device-side scalars of one chain in the stream regime
@@ -55,7 +58,42 @@ struct StreamWork {
   float* dl;                  // [Bc] likelihood deltas (scaled by num_batches)
   float* part;                // split-K partials of the weight-gradient GEMMs
   long long part_floats;
+  float* rowpart;             // [64][max width] partial row sums (bias gradients of the tensor-core layers)
+  // tensor-core mode: BF16 hi / lo halves of the activations, the deltas and theta
+  __nv_bfloat16* act_hi[BFX_MAX_LAYERS + 1];
+  __nv_bfloat16* act_lo[BFX_MAX_LAYERS + 1];
+  __nv_bfloat16* delta_hi[2];
+  __nv_bfloat16* delta_lo[2];
+  __nv_bfloat16* w_hi;
+  __nv_bfloat16* w_lo;
 };
+
+// ---- tcgen05 GEMM (bfx_stream_tc.cu) ---------------------------------------------------------------------
+enum { EPI_BIAS_ACT_TC = 0, EPI_MUL_DACT_TC = 1, EPI_PLAIN_TC = 2 };
+// one operand: element (mn, k) lives at hi[mn * ld + k] (K-major) or hi[k * ld + mn] (MN-major)
+struct TcOperand {
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;
+  long long ld;
+};
+struct TcGemmArgs {
+  int M, N, K;
+  TcOperand A, B;
+  float* C;              // FP32 output; EPI_PLAIN: the split-K partial / accumulate target
+  __nv_bfloat16* Chi;    // BF16 halves of the output (nullptr: not written)
+  __nv_bfloat16* Clo;
+  long long ldc;
+  const float* bias;
+  int act;
+  const float* aux;      // EPI_MUL_DACT: multiply by act'(aux[m + ldaux * n])
+  long long ldaux;
+  int accumulate;        // EPI_PLAIN, single split: C += acc
+  long long kchunk;      // split-K: blockIdx.z handles k in [z * kchunk, ...), writes C + z * part_stride
+  long long part_stride;
+};
+cudaError_t tc_gemm_forward(const TcGemmArgs& g, cudaStream_t st);          // A MN-major (W), B K-major (activations)
+cudaError_t tc_gemm_dx(const TcGemmArgs& g, cudaStream_t st);               // A K-major (W^T), B K-major (delta)
+cudaError_t tc_gemm_dw(const TcGemmArgs& g, int ksplit, cudaStream_t st);   // A MN-major (delta), B MN-major (activations)
 
 cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W);
 void stream_work_free(StreamWork& W);

@@ -200,9 +200,11 @@ int32_t bfx_model_set_data_device(bfx_model* m, const float* x_dev, const int64_
 /* Arithmetic of the contractions (no reference counterpart: the reference has one Float32 path).
  *   BFX_COMPUTE_FP32      FP32 FMA on the CUDA cores -- the correctness gate, every model
  *   BFX_COMPUTE_TC_BF16X3 tcgen05 tensor cores, 3-term BF16 split with FP32 accumulation in TMEM
- *                         (same 1e-4 gradient bar); MLPs whose hidden widths are multiples of 16
- *                         and <= 64, input dimension <= 64; otherwise BFX_ERR_UNSUPPORTED and the
- *                         model stays on the FP32 path. */
+ *                         (same 1e-4 gradient bar).  Shared-memory regime: MLPs whose hidden widths are
+ *                         multiples of 16 and <= 64, input dimension <= 64.  Large-P regime: every layer
+ *                         with fan-out >= 64 and fan-in >= 16, both multiples of 8 (128 x 128 x 64 tcgen05
+ *                         GEMM tiles); narrower layers of the same net stay FP32.  Otherwise
+ *                         BFX_ERR_UNSUPPORTED and the model stays on the FP32 path. */
 enum { BFX_COMPUTE_FP32 = 0, BFX_COMPUTE_TC_BF16X3 = 1 };
 int32_t bfx_model_set_compute(bfx_model* m, int32_t mode);
 int32_t bfx_model_get_compute(const bfx_model* m, int32_t* mode);

@@ -178,3 +178,100 @@ def test_minibatch_sharded_chain_matches_the_unsharded_update(bf):
         th_ref = ref.step_injected(np.concatenate(idx_union), float(nb), z.reshape(1, -1, 1), None)[:, 0]
         err = float(np.max(np.abs(th_a - th_ref))) / max(1.0, float(np.max(np.abs(th_ref))))
         assert err < 1e-5, (t, err)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 GEMMs of the stream regime (bfx_stream_tc.cu): same 1e-4 bar through the 3-term BF16 split
+# ---------------------------------------------------------------------------------------------------------
+def relu_margin(layers, theta, xb):
+    """Smallest |pre-activation| of a ReLU unit relative to its magnitude scale sum|w||a| + |b|: below ~2e-5 the
+    3-term BF16 split (pre-activations accurate to ~1e-5) can land on the other side of the kink, which flips that
+    unit's derivative -- a discontinuity of the function, not an arithmetic error."""
+    th = theta.astype(np.float64)
+    a = xb.astype(np.float64)
+    starts, ends = O.layer_bounds(layers)
+    worst = np.inf
+    for l, s0, e0 in zip(layers, starts, ends):
+        W, b = O.unpack_layer(l, th[s0:e0])
+        z = W @ a + b[:, None]
+        if l.act == O.RELU:
+            worst = min(worst, float(np.min(np.abs(z) / (np.abs(W) @ np.abs(a) + np.abs(b)[:, None]))))
+        a = O._act(l.act, z)
+    return worst
+
+
+TC_NETS = {
+    "cfg3_small": NETS["cfg3_small"],
+    "cfg3_small_smooth": (O.Dense(64, 200, O.TANH), O.Dense(200, 200, O.SIGMOID), O.Dense(200, 200, O.TANH), O.Dense(200, 1)),
+    "tc_mixed": (O.Dense(24, 256, O.RELU), O.Dense(256, 192, O.TANH), O.Dense(192, 1)),
+    "cfg3_one_wide": (O.Dense(64, 512, O.RELU), O.Dense(512, 512, O.SIGMOID), O.Dense(512, 1)),
+}
+
+
+def _tc(bf, bnn):
+    import ctypes as C
+    from bayesflux_b200 import _lib as L
+    L.check(L.lib.bfx_model_set_compute(bnn._h, L.COMPUTE_TC_BF16X3))
+    mode = C.c_int32()
+    L.check(L.lib.bfx_model_get_compute(bnn._h, C.byref(mode)))
+    assert mode.value == L.COMPUTE_TC_BF16X3
+
+
+@pytest.mark.parametrize("net", list(TC_NETS))
+@pytest.mark.parametrize("like,prior", [("normal_gamma", "gauss"), ("tdist_gamma", "mix")])
+@pytest.mark.parametrize("B", [50, 700])
+def test_stream_tc_grad_and_value_parity(bf, net, like, prior, B):
+    rng = np.random.default_rng(SEED + 10)
+    layers = TC_NETS[net]
+    n = 900
+    x = rng.standard_normal((layers[0].nin, n)).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    bnn, m = build(bf, layers, LIKES[like], PRIORS[prior], x, y)
+    assert bf.model_regime(bnn) == "stream"
+    _tc(bf, bnn)
+    theta = (0.1 * rng.standard_normal((m.n_total, 2))).astype(np.float32)
+    idx = np.stack([rng.permutation(n)[:B] for _ in range(2)], axis=1)
+    v, g = bf.grad_loglikeprior(bnn, theta, idx, num_batches=4.0)
+    for c in range(2):
+        vo, go = O.grad_loglikeprior(m, theta[:, c].astype(np.float64), x[:, idx[:, c]].astype(np.float64),
+                                     y[idx[:, c]].astype(np.float64), 4.0)
+        rel = np.linalg.norm(g[:, c] - go) / np.linalg.norm(go)
+        # 1e-4 wherever the gradient is continuous; a looser bound when a ReLU pre-activation sits within the
+        # split's rounding of its kink (see relu_margin)
+        tol = TOL if relu_margin(layers, theta[:, c], x[:, idx[:, c]]) > 5e-5 else 1e-2
+        assert rel <= tol, f"chain {c}: {rel}"
+        assert abs(v[c] - vo) <= TOL * abs(vo)
+
+
+def test_stream_tc_full_data_two_chunks(bf):
+    rng = np.random.default_rng(SEED + 11)
+    layers = TC_NETS["cfg3_small_smooth"]
+    n = 9000   # > one 8192-column chunk: weight gradients accumulate over chunks
+    x = rng.standard_normal((64, n)).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    bnn, m = build(bf, layers, LIKES["normal_gamma"], PRIORS["gauss"], x, y)
+    _tc(bf, bnn)
+    th = (0.1 * rng.standard_normal(m.n_total)).astype(np.float32)
+    v, g = bf.grad_loglikeprior(bnn, th, None, 1.0)
+    vo, go = O.grad_loglikeprior(m, th.astype(np.float64), x.astype(np.float64), y.astype(np.float64), 1.0)
+    assert abs(v - vo) <= TOL * abs(vo)
+    assert np.linalg.norm(g - go) <= TOL * np.linalg.norm(go)
+
+
+def test_stream_tc_sgnhts_tracks_fp32(bf):
+    rng = np.random.default_rng(SEED + 12)
+    layers = TC_NETS["cfg3_small_smooth"]
+    n = 2048
+    x = rng.standard_normal((64, n)).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    like = O.Likelihood(O.TDIST, nu=5.0, prior_a=2.0, prior_b=0.5)
+    prior = O.NetPrior(O.NETPRIOR_MIXTURE, sigma1=1.0, sigma2=0.1, pi1=0.5)
+    th0 = (0.05 * rng.standard_normal(sum(l.nin * l.nout + l.nout for l in layers) + 1)).astype(np.float32)
+    out = []
+    for tcmode in (False, True):
+        bnn, m = build(bf, layers, like, prior, x, y)
+        if tcmode:
+            _tc(bf, bnn)
+        out.append(bf.mcmc(bnn, 256, 8, bf.SGNHTS(1e-3, 1.0), theta_start=th0, seed=3))
+    rel = np.linalg.norm(out[0] - out[1]) / np.linalg.norm(out[0])
+    assert rel < 1e-4, rel
