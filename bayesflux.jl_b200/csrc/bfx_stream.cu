@@ -139,14 +139,57 @@ __global__ void k_split(const float* __restrict__ src, long long n, __nv_bfloat1
 }
 
 // bias gradient of a tensor-core layer: db[o] += sum_b D[o + nout*b], deterministic two-level sum
-__global__ void k_rowsum_part(const float* __restrict__ D, int nout, int nc, float* __restrict__ part) {
+// (optionally weighted by wgt[b]: the weight gradient of a 1-wide output layer is sum_b dl[b] * act[:, b])
+__global__ void k_rowsum_part(const float* __restrict__ D, int nout, int nc, const float* __restrict__ wgt,
+                              float* __restrict__ part) {
   const int o = blockIdx.x * 32 + (threadIdx.x & 31);
   const int sy = threadIdx.x >> 5;                      // 8 sub-slices per block
   const int slice = blockIdx.y * 8 + sy, nslices = gridDim.y * 8;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (o < nout) {
+    int b = slice;
+    for (; b + 3 * nslices < nc; b += 4 * nslices) {  // four independent loads in flight
+      const float d0 = D[o + (long long)nout * b], d1 = D[o + (long long)nout * (b + nslices)];
+      const float d2 = D[o + (long long)nout * (b + 2 * nslices)], d3 = D[o + (long long)nout * (b + 3 * nslices)];
+      s0 += wgt ? wgt[b] * d0 : d0;
+      s1 += wgt ? wgt[b + nslices] * d1 : d1;
+      s2 += wgt ? wgt[b + 2 * nslices] * d2 : d2;
+      s3 += wgt ? wgt[b + 3 * nslices] * d3 : d3;
+    }
+    for (; b < nc; b += nslices) s0 += wgt ? wgt[b] * D[o + (long long)nout * b] : D[o + (long long)nout * b];
+    part[(long long)slice * nout + o] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+// 1-wide output layer: out[b] = act(sum_i w[i] * A[i + nin*b] + b0), one warp per column
+__global__ void k_out_fwd(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ A, int nin,
+                          int nc, int act, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long col = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (col >= nc) return;
+  const float* a = A + col * nin;
   float s = 0.f;
-  if (o < nout)
-    for (int b = slice; b < nc; b += nslices) s += D[o + (long long)nout * b];
-  if (o < nout) part[(long long)slice * nout + o] = s;
+  for (int i = lane; i < nin; i += 32) s = fmaf(__ldg(w + i), a[i], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[col] = act_apply(act, s + __ldg(bias));
+}
+
+// its input gradient: D[i + nin*b] = w[i] * dl[b] * act'(A[i + nin*b])  (+ BF16 halves for tensor-core consumers)
+__global__ void k_out_dx(const float* __restrict__ w, const float* __restrict__ dl, const float* __restrict__ A, int nin,
+                         int nc, int act_prev, float* __restrict__ D, __nv_bfloat16* __restrict__ hi,
+                         __nv_bfloat16* __restrict__ lo) {
+  const long long total = (long long)nin * nc;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / nin;
+    const int i = (int)(e - b * nin);
+    const float v = __ldg(w + i) * dl[b] * act_deriv_from_out(act_prev, A[e]);
+    D[e] = v;
+    if (hi) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[e] = h;
+      lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
 }
 __global__ void k_rowsum_final(const float* __restrict__ part, int nout, int nslices, float* __restrict__ g) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,8 +367,8 @@ cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W)
   }
   W.part_floats = big * 32;
   if (e == cudaSuccess) e = cudaMalloc(&W.part, (size_t)W.part_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&W.rowpart, (size_t)64 * maxw * sizeof(float));
   if (M.tc) {
-    if (e == cudaSuccess) e = cudaMalloc(&W.rowpart, (size_t)64 * maxw * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&W.act_hi[0], (size_t)M.d_in * Bc * 2);
     if (e == cudaSuccess) e = cudaMalloc(&W.act_lo[0], (size_t)M.d_in * Bc * 2);
     for (int l = 0; l < M.nlayers && e == cudaSuccess; ++l) {
@@ -410,6 +453,13 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
         SCK(tc_gemm_forward(t, st));
         continue;
       }
+      if (L.nout == 1) {
+        const long long threads = (long long)nc * 32;
+        k_out_fwd<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(theta + L.w_off, theta + L.b_off, W.act[l], L.nin, nc,
+                                                                  L.act, W.act[l + 1]);
+        SCK(cudaGetLastError());
+        continue;
+      }
       GemmArgs a{};
       a.M = L.nout; a.N = nc; a.K = L.nin;
       a.A = theta + L.w_off; a.sam = 1; a.sak = L.nout;
@@ -445,7 +495,7 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
           SCK(tc_gemm_dw(t, 1, st));
         } else {
           long long kch = (nc + ksplit - 1) / ksplit;
-          kch = (kch + 63) / 64 * 64;
+          kch = (kch + 31) / 32 * 32;
           t.C = W.part; t.accumulate = 0; t.kchunk = kch; t.part_stride = cnt;
           SCK(tc_gemm_dw(t, ksplit, st));
           k_reduce_parts<<<(unsigned)((cnt + 255) / 256 < 1184 ? (cnt + 255) / 256 : 1184), 256, 0, st>>>(g + L.w_off, W.part, cnt, ksplit, cnt, 1);
@@ -453,7 +503,7 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
         }
         {
           dim3 grid((L.nout + 31) / 32, 8);
-          k_rowsum_part<<<grid, 256, 0, st>>>(D, L.nout, nc, W.rowpart);
+          k_rowsum_part<<<grid, 256, 0, st>>>(D, L.nout, nc, nullptr, W.rowpart);
           SCK(cudaGetLastError());
           k_rowsum_final<<<(L.nout + 127) / 128, 128, 0, st>>>(W.rowpart, L.nout, 64, g + L.b_off);
           SCK(cudaGetLastError());
@@ -468,6 +518,27 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
           u.aux = W.act[l]; u.ldaux = L.nin; u.act = M.L[l - 1].act;
           u.kchunk = L.nout; u.part_stride = 0;
           SCK(tc_gemm_dx(u, st));
+          D = W.delta[ping]; Dhi = W.delta_hi[ping]; Dlo = W.delta_lo[ping];
+          ping ^= 1;
+        }
+        continue;
+      }
+      if (L.nout == 1 && W.rowpart) {
+        // 1-wide output layer: dW[i] += sum_b dl[b] act[l][i, b], db += sum_b dl[b]; delta = w dl^T .* act'
+        dim3 grid((L.nin + 31) / 32, 8);
+        k_rowsum_part<<<grid, 256, 0, st>>>(W.act[l], L.nin, nc, D, W.rowpart);
+        SCK(cudaGetLastError());
+        k_rowsum_final<<<(L.nin + 127) / 128, 128, 0, st>>>(W.rowpart, L.nin, 64, g + L.w_off);
+        SCK(cudaGetLastError());
+        k_rowsum_part<<<dim3(1, 8), 256, 0, st>>>(D, 1, nc, nullptr, W.rowpart);
+        SCK(cudaGetLastError());
+        k_rowsum_final<<<1, 32, 0, st>>>(W.rowpart, 1, 64, g + L.b_off);
+        SCK(cudaGetLastError());
+        if (l > 0) {
+          const bool tcn = M.tc && M.L[l - 1].tc;
+          k_out_dx<<<1184, 256, 0, st>>>(theta + L.w_off, D, W.act[l], L.nin, nc, M.L[l - 1].act, W.delta[ping],
+                                        tcn ? W.delta_hi[ping] : nullptr, tcn ? W.delta_lo[ping] : nullptr);
+          SCK(cudaGetLastError());
           D = W.delta[ping]; Dhi = W.delta_hi[ping]; Dlo = W.delta_lo[ping];
           ping ^= 1;
         }

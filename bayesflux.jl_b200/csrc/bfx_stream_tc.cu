@@ -1,6 +1,6 @@
 // tcgen05 GEMM of the large-P ("stream") regime: C[M x N] = A * B with every operand stored in HBM as two
 // BF16 arrays (hi, lo = the 3-term split of the FP32 value, see bfx_tc.cuh), column-major.  One CTA computes a
-// 128 x 128 tile: K is consumed in chunks of 64 through a 3-stage cp.async ring of no-swizzle core-block tiles,
+// 128 x 128 tile: K is consumed in chunks of 32 through a 3-stage cp.async ring (96 KB: two CTAs per SM) of no-swizzle core-block tiles,
 // one thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = 128, K = 16; hi*hi + hi*lo + lo*hi per
 // k-step) into a 128-column FP32 accumulator in TMEM, and the epilogue reads it back with tcgen05.ld.32x32b
 // (thread = accumulator row) fused with bias + activation / the act' multiply / the split-K partial store.
@@ -25,8 +25,8 @@ using tc::mbar_init;
 using tc::mbar_wait;
 using tc::smem_u32;
 
-constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3;
-constexpr int TILE_BYTES = 128 * 64 * 2;               // one operand half (hi or lo) of one stage
+constexpr int TBM = 128, TBN = 128, TBK = 32, TSTAGES = 3;
+constexpr int TILE_BYTES = 128 * TBK * 2;              // one operand half (hi or lo) of one stage (8 KB)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;            // A hi, A lo, B hi, B lo
 
 BFX_DEV void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -41,6 +41,9 @@ BFX_DEV uint32_t idesc_128x128(int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 }
+
+template <class F>
+BFX_DEV void with_act_tc(int act, F f) { tc::with_act(act, f); }
 
 BFX_DEV void mma_issue(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   tc::mma(tmem_d, da, db, idesc, acc);
@@ -67,17 +70,18 @@ BFX_DEV void ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
 template <bool MN_MAJOR>
 BFX_DEV void load_tile(unsigned char* s_hi, unsigned char* s_lo, const TcOperand& op, long long mn0, long long mn_lim,
                        long long k0, long long k_lim) {
-  for (int q = threadIdx.x; q < 1024; q += 256) {
+  constexpr int KCH = TBK / 8;  // 16-byte chunks along k per row
+  for (int q = threadIdx.x; q < 128 * KCH; q += 256) {
     long long gidx;
     int soff;
     bool ok;
     if (!MN_MAJOR) {  // rows = mn (128), 16-byte chunks along k
-      const int r = q >> 3, kc = q & 7;
+      const int r = q / KCH, kc = q % KCH;
       const long long mn = mn0 + r, k = k0 + kc * 8;
       ok = mn < mn_lim && k < k_lim;
       gidx = mn * op.ld + k;
-      soff = (r >> 3) * 1024 + kc * 128 + (r & 7) * 16;
-    } else {          // rows = k (64), 16-byte chunks along mn
+      soff = (r >> 3) * (KCH * 128) + kc * 128 + (r & 7) * 16;
+    } else {          // rows = k (TBK), 16-byte chunks along mn
       const int kk = q >> 4, mc = q & 15;
       const long long mn = mn0 + mc * 8, k = k0 + kk;
       ok = mn < mn_lim && k < k_lim;
@@ -91,7 +95,7 @@ BFX_DEV void load_tile(unsigned char* s_hi, unsigned char* s_lo, const TcOperand
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(256, 1) k_tc_gemm(const TcGemmArgs g) {
+__global__ void __launch_bounds__(256, 2) k_tc_gemm(const TcGemmArgs g) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar[TSTAGES + 1];
   __shared__ uint32_t tmem_slot;
@@ -137,12 +141,13 @@ __global__ void __launch_bounds__(256, 1) k_tc_gemm(const TcGemmArgs g) {
       const uint32_t bhi = smem_u32(stage_ptr(s, 2)), blo = smem_u32(stage_ptr(s, 3));
 #pragma unroll
       for (int k = 0; k < TBK / 16; ++k) {
-        // K-major tile: LBO = 128 (next 16-byte k chunk), SBO = 1024 (next 8 rows), 16 k = 256 bytes
+        // K-major tile: LBO = 128 (next 16-byte k chunk), SBO = (TBK/8)*128 (next 8 rows), 16 k = 256 bytes
         // MN-major tile: SBO = 128 (next 8 mn), LBO = 2048 (next 8 k rows), 16 k = 4096 bytes
-        const uint64_t dah = A_MN ? make_desc(ahi + k * 4096, 2048, 128) : make_desc(ahi + k * 256, 128, 1024);
-        const uint64_t dal = A_MN ? make_desc(alo + k * 4096, 2048, 128) : make_desc(alo + k * 256, 128, 1024);
-        const uint64_t dbh = B_MN ? make_desc(bhi + k * 4096, 2048, 128) : make_desc(bhi + k * 256, 128, 1024);
-        const uint64_t dbl = B_MN ? make_desc(blo + k * 4096, 2048, 128) : make_desc(blo + k * 256, 128, 1024);
+        constexpr uint32_t KSBO = (TBK / 8) * 128;
+        const uint64_t dah = A_MN ? make_desc(ahi + k * 4096, 2048, 128) : make_desc(ahi + k * 256, 128, KSBO);
+        const uint64_t dal = A_MN ? make_desc(alo + k * 4096, 2048, 128) : make_desc(alo + k * 256, 128, KSBO);
+        const uint64_t dbh = B_MN ? make_desc(bhi + k * 4096, 2048, 128) : make_desc(bhi + k * 256, 128, KSBO);
+        const uint64_t dbl = B_MN ? make_desc(blo + k * 4096, 2048, 128) : make_desc(blo + k * 256, 128, KSBO);
         mma_issue(tmem, dah, dbh, idesc, (kc | k) ? 1u : 0u);
         mma_issue(tmem, dah, dbl, idesc, 1u);
         mma_issue(tmem, dal, dbh, idesc, 1u);
@@ -179,25 +184,47 @@ __global__ void __launch_bounds__(256, 1) k_tc_gemm(const TcGemmArgs g) {
       float v[32];
       const int c0 = 64 * half + 32 * cb;
       ld_32x32b_x32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
-      if (m < g.M) {
+      const long long nb0 = n0 + c0;
+      if (m < g.M && nb0 < g.N) {
+        const int ncols = (int)((g.N - nb0) < 32 ? (g.N - nb0) : 32);
+        // phase 1: everything the epilogue READS (all loads in flight before the first store: the output
+        // arrays may alias nothing, but the compiler cannot know that across the stores)
+        if (EPI == EPI_MUL_DACT_TC) {
+          const float* ap = g.aux + m + g.ldaux * nb0;
+          float a[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const long long n = n0 + c0 + j;
-          if (n >= g.N) continue;
-          float o = v[j];
-          const long long idx = m + g.ldc * n;
-          if (EPI == EPI_BIAS_ACT_TC) {
-            o = act_apply(g.act, o + bias);
-          } else if (EPI == EPI_MUL_DACT_TC) {
-            o *= act_deriv_from_out(g.act, __ldg(g.aux + m + g.ldaux * n));
-          } else if (g.accumulate) {
-            o += C[idx];
-          }
-          if (C) C[idx] = o;
-          if (EPI != EPI_PLAIN_TC && g.Chi) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(o);
-            g.Chi[idx] = h;
-            g.Clo[idx] = __float2bfloat16_rn(o - __bfloat162float(h));
+          for (int j = 0; j < 32; ++j) a[j] = j < ncols ? __ldg(ap + (long long)j * g.ldaux) : 0.f;
+          with_act_tc(g.act, [&](auto A) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= decltype(A)::d(a[j]);
+          });
+        } else if (EPI == EPI_BIAS_ACT_TC) {
+          with_act_tc(g.act, [&](auto A) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = decltype(A)::f(v[j] + bias);
+          });
+        } else if (g.accumulate) {
+          const float* cp = C + m + g.ldc * nb0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += j < ncols ? cp[(long long)j * g.ldc] : 0.f;
+        }
+        // phase 2: stores (lanes = consecutive rows m: every store instruction is one coalesced line)
+        if (C) {
+          float* cp = C + m + g.ldc * nb0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) cp[(long long)j * g.ldc] = v[j];
+        }
+        if (EPI != EPI_PLAIN_TC && g.Chi) {
+          __nv_bfloat16* hp = g.Chi + m + g.ldc * nb0;
+          __nv_bfloat16* lp = g.Clo + m + g.ldc * nb0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+              hp[(long long)j * g.ldc] = h;
+              lp[(long long)j * g.ldc] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+            }
           }
         }
       }

@@ -63,7 +63,8 @@ def cfg3(bf, torch, args):
     y = torch.randn((n_loc,), generator=g, device="cuda", dtype=torch.float32)
     net = bf.Chain(bf.Dense(64, W, bf.relu), bf.Dense(W, W, bf.relu), bf.Dense(W, W, bf.relu), bf.Dense(W, 1))
     nc = bf.destruct(net)
-    bnn = bf.BNN(None, None, bf.FeedforwardTDist(nc, bf.Gamma(2.0, 0.5), 5.0), bf.MixtureScalePrior(nc, 1.0, 0.1, 0.5), device=local)
+    bnn = bf.BNN(None, None, bf.FeedforwardTDist(nc, bf.Gamma(2.0, 0.5), 5.0), bf.MixtureScalePrior(nc, 1.0, 0.1, 0.5), device=local,
+                 compute=args.compute)
     bnn.set_data_device(x.data_ptr(), (64, n_loc), y.data_ptr())
     P = bnn.num_total_params
     th0 = (0.03 * np.random.default_rng(SEED).standard_normal(P)).astype(np.float32)
@@ -100,7 +101,7 @@ def cfg3(bf, torch, args):
     ms = float(tm.item())
     flop = 3279872.0 * Bl  # per rank per step (SURVEY.md section 8 sizes table)
     theta = ch.theta
-    out = {"cfg": 3, "workload": f"wide MLP 64-512-512-512-1, TDist(5)+MixtureScale, SGNHTS, 1 chain, B={Bl}/GPU x {world} GPUs, n={n_loc}/GPU",
+    out = {"cfg": 3, "workload": f"wide MLP 64-512-512-512-1, TDist(5)+MixtureScale, SGNHTS, 1 chain, B={Bl}/GPU x {world} GPUs, n={n_loc}/GPU, compute={bnn.compute}",
            "n_gpus": world, "steps": K, "ms_per_step": ms / K, "grad_evals_per_s": K / ms * 1e3,
            "observations_per_s": K * Bl * world / ms * 1e3,
            "tflops_per_gpu": flop * K / (ms * 1e-3) / 1e12,
