@@ -48,6 +48,26 @@ struct SamplerDesc
     maxnorm::Float32; l::Float32; A::Float32; sigmaA::Float32; xi::Float32; mu::Float32; beta::Float32
     da_target_accept::Float32; da_gamma::Float32; da_kappa::Float32
     ma_kappa::Float32; ma_epsilon::Float32; ma_lambda::Float32; ma_alpha::Float32
+    # BFX_MODE (find_mode): Flux optimiser rule + FluxModeFinder window
+    opt_kind::Int32; mode_windowlength::Int32
+    opt_eta::Float32; opt_rho::Float32; opt_beta2::Float32; opt_eps::Float32
+    mode_abstol::Float32; _pad2::Float32
+end
+# the five samplers do not use the find_mode fields
+SamplerDesc(a::Vararg{Any,28}) = SamplerDesc(a..., Int32(3), Int32(100), 0.001f0, 0.9f0, 0.999f0, 1f-8, 1f-6, 0f0)
+
+# FluxModeFinder (src/inference/mode/flux.jl:8-31) with Flux.ADAM / RMSProp / Momentum / Descent
+function samplerdesc(f::FluxModeFinder)
+    o = f.opt
+    kind, eta, rho, b2, eps =
+        o isa Flux.Optimise.ADAM ? (Int32(3), o.eta, o.beta[1], o.beta[2], o.epsilon) :
+        o isa Flux.Optimise.RMSProp ? (Int32(2), o.eta, o.rho, 0.999, o.epsilon) :
+        o isa Flux.Optimise.Momentum ? (Int32(1), o.eta, o.rho, 0.999, 1e-8) :
+        o isa Flux.Optimise.Descent ? (Int32(0), o.eta, 0.9, 0.999, 1e-8) :
+        error("optimiser $(typeof(o)) is not supported by the B200 engine")
+    SamplerDesc(5, 1, 1, 0, 0, 10, 0, 0, 2, 0, 0f0, 0f0, 0f0, -Inf32, 0f0, 0f0, 1f0, 1f0, 0f0, 1f0, 0.55f0,
+                0.65f0, 0.05f0, 0.75f0, 0f0, 0f0, 0f0, 0f0,
+                kind, Int32(f.windowlength), Float32(eta), Float32(rho), Float32(b2), Float32(eps), Float32(f.ϵ), 0f0)
 end
 
 struct RunDesc
