@@ -351,7 +351,17 @@ BFX_DEV void for_each_quad(const ModelDev& M, F f) {
 // call f(flat index J, padded index k) for every parameter (boundary code only: one table load each)
 template <int NT, class F>
 BFX_DEV void for_each_flat(const ModelDev& M, F f) {
-  for (int J = threadIdx.x; J < M.P; J += NT) f(J, __ldg(M.flat_pad + J));
+  // four table entries in flight per thread: the loop is otherwise a chain of dependent L2 round trips
+  int J = threadIdx.x;
+  for (; J + 3 * NT < M.P; J += 4 * NT) {
+    const int k0 = __ldg(M.flat_pad + J), k1 = __ldg(M.flat_pad + J + NT);
+    const int k2 = __ldg(M.flat_pad + J + 2 * NT), k3 = __ldg(M.flat_pad + J + 3 * NT);
+    f(J, k0);
+    f(J + NT, k1);
+    f(J + 2 * NT, k2);
+    f(J + 3 * NT, k3);
+  }
+  for (; J < M.P; J += NT) f(J, __ldg(M.flat_pad + J));
 }
 
 BFX_DEV float4 mask4(float4 v, unsigned m) {
