@@ -348,6 +348,41 @@ def grad_loglikeprior(bnn: BNN, theta, idx=None, num_batches=1.0):
     return v, g
 
 
+def predict(bnn: BNN, theta, x=None):
+    """Network outputs vec(net(x)) for every column of theta, and sigma = exp(theta_like) per column.
+    Returns (yhat (n, C), sigma (C,)); x = None uses the model's data."""
+    th, nc = _theta_cols(bnn, theta)
+    if x is None:
+        n, xp, dims, nd = bnn.n, None, None, 0
+    else:
+        xx = _as_f32(x)
+        n, xp, nd = xx.shape[-1], _ptr(xx), xx.ndim
+        dims = (C.c_int64 * xx.ndim)(*xx.shape)
+    yhat = np.empty((n, nc), np.float32, order="F")
+    sig = np.empty(nc, np.float32)
+    L.check(L.lib.bfx_predict(bnn._h, _ptr(th), nc, xp, dims, nd, _ptr(yhat), _ptr(sig)))
+    return yhat, sig
+
+
+def sample_posterior_predict(bnn: BNN, ch, x=None, rng=None):
+    """sample_posterior_predict(bnn, ch; x = bnn.x)  src/model/BNN.jl:129-135: one predictive draw per posterior
+    draw (columns of ch).  The forward passes run on the device; the draw around yhat is made here on the host
+    (posterior_predict: Normal -> yhat + sigma * randn, TDist -> yhat + sigma * rand(TDist(nu)))."""
+    rng = rng or np.random.default_rng()
+    yhat, sig = predict(bnn, ch, x)
+    if bnn.like.kind == L.LIKE_NORMAL:
+        eps = rng.standard_normal(yhat.shape)
+    else:
+        eps = rng.standard_t(bnn.like.nu, yhat.shape)
+    return (yhat + sig[None, :] * eps).astype(np.float32)
+
+
+def get_posterior_networks(bnn: BNN, ch):
+    """get_posterior_networks  src/model/BNN.jl:104-107: the network parameter vectors of the posterior draws."""
+    ch = np.asarray(ch)
+    return [split_params(bnn, ch[:, i])[0].astype(np.float32) for i in range(ch.shape[1])]
+
+
 # ------------------------------------------------------------------ adapters ---
 @dataclass
 class ConstantStepsize:

@@ -745,6 +745,109 @@ int32_t bfx_grad_loglikeprior(bfx_model* m, const float* theta, int32_t nchains,
   return eval_impl(m, theta, nchains, idx, B, idx_chain_stride, num_batches, v_out, g_out);
 }
 
+
+// ---------------------------------------------------------------------------------
+// posterior predictive support: network outputs for many theta x many inputs
+// ---------------------------------------------------------------------------------
+int32_t bfx_predict(bfx_model* m, const float* theta, int32_t C, const float* x_new, const int64_t* dims, int32_t ndims,
+                    float* yhat_out, float* sigma_out) {
+  if (!m || !theta || !yhat_out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (C <= 0) return fail(BFX_ERR_BAD_ARG, "nchains must be > 0");
+  if (!x_new && !m->x) return fail(BFX_ERR_NO_DATA, "no x given and bfx_model_set_data has not been called");
+  int32_t st = ensure_stream(m);
+  if (st) return st;
+  const int P = m->M.P;
+  int64_t n = m->n;
+  size_t per = (size_t)m->M.d_in * (m->M.seq ? (size_t)m->M.T : 1);
+  if (x_new) {
+    if (!dims || (ndims != 2 && ndims != 3)) return fail(BFX_ERR_BAD_ARG, "x must be d x n or T x d x n");
+    if ((ndims == 3) != (m->M.rec_layer >= 0)) return fail(BFX_ERR_BAD_ARG, "rank of x does not match the network");
+    if (dims[ndims - 2] != m->M.d_in) return fail(BFX_ERR_BAD_ARG, "feature dimension of x does not match the first layer");
+    if (ndims == 3 && m->x && dims[0] != m->M.T) return fail(BFX_ERR_BAD_ARG, "sequence length differs from the model's data");
+    n = dims[ndims - 1];
+    per = (size_t)dims[ndims - 2] * (ndims == 3 ? (size_t)dims[0] : 1);
+    if (n <= 0 || n > 2147483647LL) return fail(BFX_ERR_BAD_ARG, "bad number of observations");
+  }
+  float *d_x = nullptr, *d_y = nullptr, *d_theta = nullptr, *d_out = nullptr;
+  double* d_v = nullptr;
+  StreamScalars* d_sc = nullptr;
+  float* d_g = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_x);
+    cudaFree(d_y);
+    cudaFree(d_theta);
+    cudaFree(d_out);
+    cudaFree(d_v);
+    cudaFree(d_sc);
+    cudaFree(d_g);
+  };
+  const float* xs = m->x;
+  const float* ys = m->y;
+  int savedT = m->M.T, savedSeq = m->M.seq;
+  if (x_new) {
+    CKC(cudaMalloc(&d_x, per * (size_t)n * 4));
+    CKC(cudaMalloc(&d_y, (size_t)n * 4));
+    CKC(cudaMemcpyAsync(d_x, x_new, per * (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    CKC(cudaMemsetAsync(d_y, 0, (size_t)n * 4, m->stream));
+    xs = d_x;
+    ys = d_y;
+    if (ndims == 3) {
+      m->M.T = (int)dims[0];
+      m->M.seq = 1;
+    }
+  }
+  CKC(cudaMalloc(&d_out, (size_t)C * n * 4));
+  int32_t rc = BFX_OK;
+  if (m->stream_regime) {
+    CKC(cudaMalloc(&d_theta, (size_t)P * 4));
+    CKC(cudaMalloc(&d_g, ((size_t)P + 4) * 4));
+    CKC(cudaMalloc(&d_sc, sizeof(StreamScalars)));
+    rc = ensure_work(m, n);
+    for (int c = 0; c < C && !rc; ++c) {
+      CKC(cudaMemcpyAsync(d_theta, theta + (size_t)c * P, (size_t)P * 4, cudaMemcpyHostToDevice, m->stream));
+      StreamBatch b{};
+      b.n = n;
+      b.full = 1;
+      b.B = n;
+      CKC(stream_zero(d_g, P, d_sc, m->stream));
+      CKC(stream_eval_like(m->SM, m->W, d_theta, xs, ys, b, 1.f, false, d_g, d_sc, m->stream, d_out + (size_t)c * n));
+    }
+  } else {
+    CKC(cudaMalloc(&d_theta, (size_t)C * P * 4));
+    CKC(cudaMalloc(&d_v, (size_t)C * sizeof(double)));
+    CKC(cudaMemcpyAsync(d_theta, theta, (size_t)C * P * 4, cudaMemcpyHostToDevice, m->stream));
+    EvalDev E{};
+    E.M = m->M;
+    E.M.tc = TcDesc{};  // forward only: the FP32 tiles
+    E.x = xs;
+    E.y = ys;
+    E.n = n;
+    E.C = C;
+    E.theta = d_theta;
+    E.idx = nullptr;
+    E.B = n;
+    E.num_batches = 1.f;
+    E.want_grad = 0;
+    E.v_out = d_v;
+    E.g_out = nullptr;
+    E.yhat_out = d_out;
+    rc = ensure_scratch(m, (size_t)C, &E.scratch, &E.scratch_stride);
+    if (!rc) CKC(launch_eval(E, m->cfg, m->stream));
+  }
+  m->M.T = savedT;
+  m->M.seq = savedSeq;
+  if (rc) {
+    cleanup();
+    return rc;
+  }
+  CKC(cudaMemcpyAsync(yhat_out, d_out, (size_t)C * n * 4, cudaMemcpyDeviceToHost, m->stream));
+  CKC(cudaStreamSynchronize(m->stream));
+  if (sigma_out)
+    for (int c = 0; c < C; ++c) sigma_out[c] = std::exp(theta[(size_t)c * P + (P - 1)]);  // invlink = exp (log link)
+  cleanup();
+  return BFX_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // samplers
 // ---------------------------------------------------------------------------------

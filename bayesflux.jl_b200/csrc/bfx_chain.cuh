@@ -16,7 +16,7 @@ BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, f
 template <int NT, int BT>
 BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
                           const float* __restrict__ y, const BatchSrc& bs, long long B, float nb, bool want_grad,
-                          float& gn2) {
+                          float& gn2, float* yhat = nullptr) {
   if (want_grad) for_each_quad<NT>(M, [&](int k) { st4(s.g + k, make_float4(0.f, 0.f, 0.f, 0.f)); });
   const float sl = s.th[M.like_s];
   const float sigma = expf(sl);
@@ -28,8 +28,9 @@ BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __
   for (long long t0 = 0; t0 < B; t0 += BT) {
     int nvalid = (int)((B - t0) < (long long)BT ? (B - t0) : (long long)BT);
     float sums[2] = {0.f, 0.f};
-    if (M.rec_layer >= 0) rec_tile<NT, BT>(M, s, x, y, bs, t0, nvalid, lc, want_grad, sums);
-    else mlp_tile<NT, BT>(M, s, x, y, bs, t0, nvalid, lc, want_grad, sums);
+    float* yt = yhat ? yhat + t0 : nullptr;
+    if (M.rec_layer >= 0) rec_tile<NT, BT>(M, s, x, y, bs, t0, nvalid, lc, want_grad, sums, yt);
+    else mlp_tile<NT, BT>(M, s, x, y, bs, t0, nvalid, lc, want_grad, sums, yt);
     ds0 += (double)sums[0];
     ds1 += (double)sums[1];
     __syncthreads();

@@ -204,6 +204,7 @@ struct EvalDev {
   float* g_out;   // [C][P]
   float* scratch;
   long long scratch_stride;
+  float* yhat_out;  // [C][B] network outputs (bfx_predict) or nullptr
 };
 
 }  // namespace bfx

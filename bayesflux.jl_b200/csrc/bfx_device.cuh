@@ -492,7 +492,7 @@ BFX_DEV void dense_forward(const ModelDev& M, const ChainSmem& s, int l0) {
 // likelihood epilogue on the network output; leaves dl[b] (scaled by num_batches) in the output buffer
 template <int NT, int BT>
 BFX_DEV void like_epilogue(const ModelDev& M, const ChainSmem& s, int nvalid, const LikeCoef& lc, bool want_grad,
-                           float (&sums)[2]) {
+                           float (&sums)[2], float* __restrict__ yhat_tile = nullptr) {
   constexpr int LDB = TileCfg<BT>::LDB;
   float* out = s.act + M.act_off[M.nlayers];
   const int out_act = M.L[M.nlayers - 1].act;
@@ -500,6 +500,7 @@ BFX_DEV void like_epilogue(const ModelDev& M, const ChainSmem& s, int nvalid, co
     float dl = 0.f;
     if (b < nvalid) {
       float yh = out[b];
+      if (yhat_tile) yhat_tile[b] = yh;  // predictive helpers: the network output itself
       float z = (s.ys[b] - yh) * lc.inv_sigma;
       if (M.like_kind == LK_NORMAL) {
         sums[0] += z * z;
@@ -545,7 +546,7 @@ BFX_DEV void dense_backward(const ModelDev& M, const ChainSmem& s, int l0) {
 template <int NT, int BT>
 BFX_DEV void mlp_tile(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
                       const float* __restrict__ y, const BatchSrc& bs, long long tile0, int nvalid,
-                      const LikeCoef& lc, bool want_grad, float (&sums)[2]) {
+                      const LikeCoef& lc, bool want_grad, float (&sums)[2], float* yhat_tile = nullptr) {
   constexpr int LDB = TileCfg<BT>::LDB;
   const int d = M.d_in;
   stage_targets<NT, BT>(s, y, bs, tile0, nvalid);
@@ -561,7 +562,7 @@ BFX_DEV void mlp_tile(const ModelDev& M, const ChainSmem& s, const float* __rest
   }
   __syncthreads();
   dense_forward<NT, BT>(M, s, 0);
-  like_epilogue<NT, BT>(M, s, nvalid, lc, want_grad, sums);
+  like_epilogue<NT, BT>(M, s, nvalid, lc, want_grad, sums, yhat_tile);
   if (!want_grad) return;
   __syncthreads();
   dense_backward<NT, BT>(M, s, 0);
@@ -595,7 +596,7 @@ BFX_DEV void rec_stage_x(const ModelDev& M, const ChainSmem& s, const float* __r
 template <int NT, int BT>
 BFX_DEV void rec_tile(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
                       const float* __restrict__ y, const BatchSrc& bs, long long tile0, int nvalid,
-                      const LikeCoef& lc, bool want_grad, float (&sums)[2]) {
+                      const LikeCoef& lc, bool want_grad, float (&sums)[2], float* yhat_tile = nullptr) {
   constexpr int LDB = TileCfg<BT>::LDB;
   const LayerDev& L = M.L[0];
   const int H = L.H, T = M.T;
@@ -652,7 +653,7 @@ BFX_DEV void rec_tile(const ModelDev& M, const ChainSmem& s, const float* __rest
   }
   // ---- Dense head on h_T, likelihood, head backward (leaves dL/dh_T in Hc) ---------------------
   dense_forward<NT, BT>(M, s, 1);
-  like_epilogue<NT, BT>(M, s, nvalid, lc, want_grad, sums);
+  like_epilogue<NT, BT>(M, s, nvalid, lc, want_grad, sums, yhat_tile);
   if (!want_grad) return;
   __syncthreads();
   dense_backward<NT, BT>(M, s, 1);

@@ -425,7 +425,7 @@ cudaError_t stream_pack_sums(float* g, long long P, StreamScalars* sc, bool to_b
 
 cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* theta, const float* x, const float* y,
                              const StreamBatch& b, float nb, bool want_grad, float* g, StreamScalars* sc,
-                             cudaStream_t st) {
+                             cudaStream_t st, float* yhat_out) {
   const int nl = M.nlayers;
   if (M.tc) {  // BF16 halves of theta for the tensor-core layers
     k_split<<<592, 256, 0, st>>>(theta, M.P, W.w_hi, W.w_lo);
@@ -472,6 +472,7 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
     }
     k_like<<<148, 256, 0, st>>>(M, theta, W.act[nl], W.yb, nc, nb, M.L[nl - 1].act, W.dl, sc);
     SCK(cudaGetLastError());
+    if (yhat_out) SCK(cudaMemcpyAsync(yhat_out + c0, W.act[nl], (size_t)nc * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (!want_grad) continue;
     // backward: delta of layer l in D (nout x nc); the output layer's delta is dl (1 x nc)
     const float* D = W.dl;

@@ -110,7 +110,7 @@ struct StreamBatch {
 // (g must be zeroed by the caller when accumulate == 0), sc->ds0/ds1/bcount += sums.
 cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* theta, const float* x, const float* y,
                              const StreamBatch& b, float nb, bool want_grad, float* g, StreamScalars* sc,
-                             cudaStream_t st);
+                             cudaStream_t st, float* yhat_out = nullptr);
 // prior + sigma prior + value + ||g||^2 (all on the device; nothing is synchronised)
 cudaError_t stream_finish(const StreamModel& M, const float* theta, float* g, StreamScalars* sc, float nb, bool want_grad,
                           cudaStream_t st);

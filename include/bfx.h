@@ -220,6 +220,15 @@ int32_t bfx_loglikeprior(bfx_model* m, const float* theta, int32_t nchains, cons
 int32_t bfx_grad_loglikeprior(bfx_model* m, const float* theta, int32_t nchains, const int64_t* idx, int64_t B,
                               int64_t idx_chain_stride, float num_batches, double* v_out, float* g_out);
 
+/* ---- predictive helpers (forward only, many theta x many inputs) ------------------------------------- *
+ * yhat = vec(net(x)) of posterior_predict (src/likelihoods/feedforward.jl:45-55,99-110, seq_to_one.jl:46-57,
+ * 102-114) for every column of theta (P x C): yhat_out is n x C column-major, sigma_out[c] = invlink(theta_like)
+ * = exp(theta_like).  x_new == NULL: the model's own data.  The random draw around yhat (Normal or sigma * TDist)
+ * stays on the host side like every other RNG of the reference's post-processing
+ * (sample_posterior_predict, src/model/BNN.jl:129-135). */
+int32_t bfx_predict(bfx_model* m, const float* theta, int32_t nchains, const float* x_new, const int64_t* dims,
+                    int32_t ndims, float* yhat_out, float* sigma_out);
+
 /* ---- samplers ----------------------------------------------------------- *
  * SGLD/SGNHT/SGNHTS/GGMC/HMC constructors + initialise!  (sgld.jl:47-88 etc.) for
  * nchains independent chains living on the model's device. */
