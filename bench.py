@@ -175,7 +175,7 @@ def run_reference(args):
                             "sample": last["sample"]},
            "e2e": {"value": v, "unit": "grad-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -330,13 +330,39 @@ def run_ours(args):
         if not args.no_cpu and world == 1:
             cb = cpu_sgld(B, args.cpu_seconds)
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+class StdoutGuard:
+    """Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) are sent to stderr
+    for the duration of the run, the result is written to the real stdout at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+GUARD = None
+
+
+def emit(line):
+    if GUARD is not None:
+        GUARD.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global GUARD
+    GUARD = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
