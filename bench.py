@@ -120,7 +120,12 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 def cpu_sgld(B, target_seconds, x=None, y=None, n=200_000):
     from oracle import cbind as OC
-    nthreads = OC.max_threads()
+    # all host cores of the box: torchrun exports OMP_NUM_THREADS=1, which would otherwise throttle the CPU arm
+    try:
+        nthreads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nthreads = os.cpu_count() or 1
+    nthreads = max(nthreads, OC.max_threads())
     rng = np.random.default_rng(SEED)
     if x is None:
         x, y = synth_data(n, rng)
