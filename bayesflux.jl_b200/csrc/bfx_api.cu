@@ -318,7 +318,7 @@ static int32_t build_tc(bfx_model* m) {
   T.d_off = off;
   off += 2 * T.d_bytes;
   T.misc_off = off;
-  off += 1024;
+  off += 2304;  // yh[128], glast[72], 4 barriers, tmem slot, gpart[4][65]
   T.total_bytes = off;
   int cols = 32;
   while (cols < col) cols <<= 1;

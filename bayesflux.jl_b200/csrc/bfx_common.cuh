@@ -63,7 +63,7 @@ struct TcDesc {
   int enabled;
   int nh;              // hidden layers on the tensor cores (= nlayers - 1; the 1-wide output layer runs in the epilogue)
   int d_off, d_bytes;  // delta tile 64 x 64 (hi); lo at d_off + d_bytes
-  int misc_off;        // float yh[128], float glast[72], uint64 bar[4], uint32 tmem slot
+  int misc_off;        // float yh[128], float glast[72], uint64 bar[4], uint32 tmem slot, float gpart[4][65]
   int total_bytes;
   int tmem_cols;       // allocation (power of two >= 32); the Z accumulator sits at column 0
   int smem_pad;        // extra dynamic smem requested at launch so that co-resident CTAs never over-subscribe TMEM

@@ -134,6 +134,7 @@ struct Region {
   uint32_t tmem;        // TMEM base address (lane 0, column 0)
   float* yh;            // [2][64] partial network outputs of the two column halves
   float* glast;         // [72]    gradient of the output layer (weights, then bias at [64])
+  float* gpart;         // [4][65] its per-lane-quadrant partials of the current tile
   uint64_t* bar;        // [4]
   uint32_t* tmem_slot;
   uint32_t par[3];      // phase parity of bar[0..2]
@@ -147,6 +148,7 @@ BFX_DEV Region region_of(const ModelDev& M, const ChainSmem& s) {
   R.glast = f + 128;
   R.bar = reinterpret_cast<uint64_t*>(f + 200);
   R.tmem_slot = reinterpret_cast<uint32_t*>(f + 208);
+  R.gpart = f + 256;
   R.tmem = 0;
   R.par[0] = R.par[1] = R.par[2] = 0;
   return R;
@@ -436,14 +438,16 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           for (int i = 0; i < 8; ++i) pc[i] += __shfl_xor_sync(0xffffffffu, pc[i], o);
           pb += __shfl_xor_sync(0xffffffffu, pb, o);
         }
+        // per-quadrant partials, then a fixed-order sum: the result must not depend on warp timing (resume
+        // determinism: a continued run reproduces the uninterrupted one bit for bit)
         if (lane < 4) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = cbase + 8 * j;
-            if (c < hl) atomicAdd(&R.glast[c], pc[2 * j]);
-            if (c + 1 < hl) atomicAdd(&R.glast[c + 1], pc[2 * j + 1]);
+            R.gpart[q * 65 + c] = pc[2 * j];
+            R.gpart[q * 65 + c + 1] = pc[2 * j + 1];
           }
-          if (lane == 0 && h == 0) atomicAdd(&R.glast[64], pb);
+          if (lane == 0 && h == 0) R.gpart[q * 65 + 64] = pb;
         }
       }
       // delta of the last hidden layer -> D tile (64 x 64, zero beyond hl)
@@ -474,6 +478,8 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       fence_async_smem();
       fence_before();
       __syncthreads();
+      if (tid <= 64 && (tid < hl || tid == 64))
+        R.glast[tid] += (R.gpart[tid] + R.gpart[65 + tid]) + (R.gpart[130 + tid] + R.gpart[195 + tid]);
       // ---- backward ------------------------------------------------------------------------------
       for (int l = nh - 1; l >= 0; --l) {
         const TcLayer& L = T.L[l];
