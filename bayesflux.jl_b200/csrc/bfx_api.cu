@@ -77,6 +77,9 @@ struct bfx_sampler {
   float* mode_window = nullptr;
   ChainScalars* sc = nullptr;
   int* work = nullptr;           // [1 + C] work-item counter and per-chain chunk counters of a launch
+  float* stage = nullptr;        // [C][P] flat staging of per-parameter state crossing the ABI
+  float* samp_cache[2] = {nullptr, nullptr};  // device sample chunks of bfx_mcmc_run, kept between calls
+  size_t samp_cap = 0;
   StreamScalars* ssc = nullptr;  // stream regime: per-chain device scalars
   float* gbuf = nullptr;         // stream regime: [P + 3] gradient + likelihood sums (the all-reduce payload)
   unsigned long long* progress_host = nullptr;  // mapped pinned
@@ -494,13 +497,7 @@ static int32_t ensure_scratch(bfx_model* m, size_t ctas, float** out, long long*
   return BFX_OK;
 }
 
-// host-side layout conversion of per-parameter state: flat P x C (ABI)  <->  padded C rows of S floats
-static void flat_to_padded(const bfx_model* m, const float* flat, int C, float fill, std::vector<float>& out) {
-  const int P = m->M.P, S = m->M.S;
-  out.assign((size_t)S * C, fill);
-  for (int c = 0; c < C; ++c)
-    for (int J = 0; J < P; ++J) out[(size_t)c * S + m->flat_pad[J]] = flat[(size_t)c * P + J];
-}
+// host-side layout conversion of per-parameter state (parity entry only; the hot paths convert on the device)
 static void padded_to_flat(const bfx_model* m, const std::vector<float>& pad, int C, float* flat) {
   const int P = m->M.P, S = m->M.S;
   for (int c = 0; c < C; ++c)
@@ -863,6 +860,9 @@ static void free_sampler(bfx_sampler* s) {
   cudaFree(s->mode_window);
   cudaFree(s->sc);
   cudaFree(s->work);
+  cudaFree(s->stage);
+  cudaFree(s->samp_cache[0]);
+  cudaFree(s->samp_cache[1]);
   cudaFree(s->ssc);
   cudaFree(s->gbuf);
   if (s->progress_host) cudaFreeHost(s->progress_host);
@@ -955,6 +955,7 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
   if (e == cudaSuccess && S.madapter_kind == MA_RMSPROP) e = cudaMalloc(&s->rms_v, all);
   if (e == cudaSuccess && S.madapter_kind == MA_DIAGCOV) e = cudaMalloc(&s->ring, all * (size_t)S.ma_windowlength);
   if (e == cudaSuccess) e = cudaMalloc(&s->work, sizeof(int) * ((size_t)nchains + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&s->stage, sizeof(float) * (size_t)nchains * m->M.P);
   if (e == cudaSuccess && m->stream_regime) e = cudaMalloc(&s->ssc, sizeof(StreamScalars) * (size_t)nchains);
   if (e == cudaSuccess && m->stream_regime) e = cudaMalloc(&s->gbuf, ((size_t)m->M.P + 4) * sizeof(float));
   if (e == cudaSuccess) e = cudaHostAlloc(&s->progress_host, sizeof(unsigned long long), cudaHostAllocMapped);
@@ -974,24 +975,38 @@ int32_t bfx_sampler_destroy(bfx_sampler* s) {
   return BFX_OK;
 }
 
+// per-parameter state across the ABI: host flat P x C  <->  device padded rows, converted on the device
+static int32_t state_h2d(bfx_sampler* s, float* dst_pad, const float* src_flat, float fill) {
+  bfx_model* m = s->m;
+  const size_t bytes = (size_t)s->C * m->M.P * 4;
+  CK(cudaMemcpyAsync(s->stage, src_flat, bytes, cudaMemcpyHostToDevice, m->stream));
+  CK(launch_flat_to_padded(s->stage, dst_pad, m->d_flat_pad, m->M.P, s->Ps, s->C, fill, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return BFX_OK;
+}
+static int32_t state_d2h(bfx_sampler* s, const float* src_pad, float* dst_flat) {
+  bfx_model* m = s->m;
+  const size_t bytes = (size_t)s->C * m->M.P * 4;
+  CK(launch_padded_to_flat(src_pad, s->stage, m->d_flat_pad, m->M.P, s->Ps, s->C, m->stream));
+  CK(cudaMemcpyAsync(dst_flat, s->stage, bytes, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return BFX_OK;
+}
+
 int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) {
   if (!s || !theta_start) return fail(BFX_ERR_BAD_ARG, "NULL argument");
   bfx_model* m = s->m;
   int32_t st = ensure_stream(m);
   if (st) return st;
   const size_t all = (size_t)s->Ps * sizeof(float) * (size_t)s->C;
-  {
-    std::vector<float> pad;
-    flat_to_padded(m, theta_start, s->C, 0.f, pad);
-    CK(cudaMemcpyAsync(s->theta, pad.data(), all, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
-  }
+  st = state_h2d(s, s->theta, theta_start, 0.f);
+  if (st) return st;
   if (s->mom) CK(cudaMemsetAsync(s->mom, 0, all, m->stream));
   if (s->theta_old) CK(cudaMemsetAsync(s->theta_old, 0, all, m->stream));
   if (s->minv) {
-    std::vector<float> ones((size_t)s->Ps * s->C, 1.0f);
-    CK(cudaMemcpyAsync(s->minv, ones.data(), all, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
+    std::vector<float> ones((size_t)m->M.P * s->C, 1.0f);
+    st = state_h2d(s, s->minv, ones.data(), 1.f);
+    if (st) return st;
   }
   if (s->rms_v) CK(cudaMemsetAsync(s->rms_v, 0, all, m->stream));
   if (s->S.kind == S_MODE) {
@@ -1096,11 +1111,7 @@ int32_t bfx_sampler_get_state(bfx_sampler* s, int32_t field, void* out, int64_t 
       for (int64_t i = 0; i < (int64_t)P * C; ++i) o[i] = field == BFX_STATE_MINV ? 1.f : 0.f;
       return BFX_OK;
     }
-    std::vector<float> pad((size_t)s->Ps * C);
-    CK(cudaMemcpyAsync(pad.data(), src, pad.size() * 4, cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
-    padded_to_flat(m, pad, C, o);
-    return BFX_OK;
+    return state_d2h(s, src, o);
   }
   std::vector<ChainScalars> sc;
   st = fetch_scalars(s, sc);
@@ -1137,11 +1148,7 @@ int32_t bfx_sampler_set_state(bfx_sampler* s, int32_t field, const void* in, int
     float* dst = field == BFX_STATE_THETA ? s->theta : field == BFX_STATE_MOMENTUM ? s->mom : s->minv;
     if (!dst) return fail(BFX_ERR_STATE, "this sampler does not carry that state");
     if (nbytes != (int64_t)P * C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold P x C floats");
-    std::vector<float> pad;
-    flat_to_padded(m, static_cast<const float*>(in), C, field == BFX_STATE_MINV ? 1.f : 0.f, pad);
-    CK(cudaMemcpyAsync(dst, pad.data(), pad.size() * 4, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
-    return BFX_OK;
+    return state_h2d(s, dst, static_cast<const float*>(in), field == BFX_STATE_MINV ? 1.f : 0.f);
   }
   std::vector<ChainScalars> sc;
   st = fetch_scalars(s, sc);
@@ -1502,8 +1509,6 @@ int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   bool registered = false;
   auto cleanup = [&]() {
-    cudaFree(d_samp[0]);
-    cudaFree(d_samp[1]);
     cudaFree(d_kin);
     cudaFree(d_acc);
     for (int i = 0; i < 2; ++i) {
@@ -1515,13 +1520,27 @@ int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta
   int64_t slots_per_chunk = 0;
   if (samples_out && nkept > 0) {
     slots_per_chunk = chunk_samples / ke + 1;
+    const int64_t need_slots = std::min<int64_t>(slots_per_chunk, nkept + 1);
+    const size_t need = (size_t)need_slots * bytes_per_kept;
+    if (need > s->samp_cap) {  // the device chunks are kept between calls (grow only)
+      for (int i = 0; i < 2; ++i) {
+        cudaFree(s->samp_cache[i]);
+        s->samp_cache[i] = nullptr;
+      }
+      s->samp_cap = 0;
+      for (int i = 0; i < 2; ++i) CKC(cudaMalloc(&s->samp_cache[i], need));
+      s->samp_cap = need;
+    }
     for (int i = 0; i < 2; ++i) {
-      CKC(cudaMalloc(&d_samp[i], (size_t)slots_per_chunk * bytes_per_kept));
+      d_samp[i] = s->samp_cache[i];
       CKC(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
       CKC(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
     }
-    registered = cudaHostRegister(samples_out, (size_t)nkept * bytes_per_kept, cudaHostRegisterDefault) == cudaSuccess;
-    if (!registered) cudaGetLastError();
+    // pinning pays for long streams only: registering costs milliseconds
+    if ((size_t)nkept * bytes_per_kept >= ((size_t)256 << 20)) {
+      registered = cudaHostRegister(samples_out, (size_t)nkept * bytes_per_kept, cudaHostRegisterDefault) == cudaSuccess;
+      if (!registered) cudaGetLastError();
+    }
   }
   if (kinetic_out && (s->S.kind == S_SGNHT || s->S.kind == S_SGNHTS)) {
     CKC(cudaMalloc(&d_kin, (size_t)C * nnew * 4));

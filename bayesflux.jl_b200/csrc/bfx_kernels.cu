@@ -38,6 +38,38 @@ __global__ void k_debug_noise(unsigned long long seed, unsigned chain, unsigned 
   if (J == 0) *uni = uniform_draw(key, gstep);
 }
 
+// ---- flat (ABI) <-> padded (engine) state conversion on the device --------------------------------------
+__global__ void k_flat_to_padded(const float* __restrict__ flat, float* __restrict__ pad, const int* __restrict__ flat_pad,
+                                 int P, int S, long long total) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long c = e / P;
+    const int J = (int)(e - c * P);
+    pad[c * S + flat_pad[J]] = flat[e];
+  }
+}
+__global__ void k_padded_to_flat(const float* __restrict__ pad, float* __restrict__ flat, const int* __restrict__ flat_pad,
+                                 int P, int S, long long total) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long c = e / P;
+    const int J = (int)(e - c * P);
+    flat[e] = pad[c * S + flat_pad[J]];
+  }
+}
+__global__ void k_fill(float* p, long long n, float v) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) p[e] = v;
+}
+
+cudaError_t launch_flat_to_padded(const float* flat, float* pad, const int* flat_pad, int P, int S, int C, float fill,
+                                  cudaStream_t st) {
+  k_fill<<<592, 256, 0, st>>>(pad, (long long)S * C, fill);
+  k_flat_to_padded<<<1184, 256, 0, st>>>(flat, pad, flat_pad, P, S, (long long)P * C);
+  return cudaGetLastError();
+}
+cudaError_t launch_padded_to_flat(const float* pad, float* flat, const int* flat_pad, int P, int S, int C, cudaStream_t st) {
+  k_padded_to_flat<<<1184, 256, 0, st>>>(pad, flat, flat_pad, P, S, (long long)P * C);
+  return cudaGetLastError();
+}
+
 size_t smallp_smem_bytes(const ModelDev& M, int bt) {
   return bt == 16 ? chain_smem_bytes<16>(M) : bt == 32 ? chain_smem_bytes<32>(M) : chain_smem_bytes<64>(M);
 }

@@ -19,4 +19,8 @@ cudaError_t launch_debug_batch(const RunDev& R, int c, unsigned long long gstep,
 cudaError_t launch_debug_noise(unsigned long long seed, unsigned chain, unsigned long long gstep, unsigned slot, int P,
                                const int* flat_pad, float* normals, float* uni, cudaStream_t st);
 
+cudaError_t launch_flat_to_padded(const float* flat, float* pad, const int* flat_pad, int P, int S, int C, float fill,
+                                  cudaStream_t st);
+cudaError_t launch_padded_to_flat(const float* pad, float* flat, const int* flat_pad, int P, int S, int C, cudaStream_t st);
+
 }  // namespace bfx
