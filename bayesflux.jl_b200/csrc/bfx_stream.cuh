@@ -90,6 +90,7 @@ struct TcGemmArgs {
   int accumulate;        // EPI_PLAIN, single split: C += acc
   long long kchunk;      // split-K: blockIdx.z handles k in [z * kchunk, ...), writes C + z * part_stride
   long long part_stride;
+  int debug;             // timing experiments only (env BFX_GEMM_DEBUG): 1 no epilogue stores, 2 no MMA, 4 no loads
 };
 cudaError_t tc_gemm_forward(const TcGemmArgs& g, cudaStream_t st);          // A MN-major (W), B K-major (activations)
 cudaError_t tc_gemm_dx(const TcGemmArgs& g, cudaStream_t st);               // A K-major (W^T), B K-major (delta)

@@ -9,6 +9,8 @@
 //
 // Reference arithmetic replaced: Flux Dense forward (called at src/likelihoods/feedforward.jl:35,91) and its
 // Zygote pullbacks (src/model/BNN.jl:66) for layers wide enough to be real GEMMs (configs[2]: 512 x 512 x 8192).
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 
 #include "bfx_stream.cuh"
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256, 2) k_tc_gemm(const TcGemmArgs g) {
   const uint32_t tmem = tmem_slot;
   auto stage_ptr = [&](int s, int which) { return smem + s * STAGE_BYTES + which * TILE_BYTES; };
   auto issue_loads = [&](int kc) {
-    if (kc < nk) {
+    if (kc < nk && !(g.debug & 4)) {
       const int s = kc % TSTAGES;
       const long long k0 = kbeg + (long long)kc * TBK;
       load_tile<A_MN>(stage_ptr(s, 0), stage_ptr(s, 1), g.A, m0, g.M, k0, kend);
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256, 2) k_tc_gemm(const TcGemmArgs g) {
     fence_async_smem();
     fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !(g.debug & 2)) {
       fence_after();
       const uint32_t ahi = smem_u32(stage_ptr(s, 0)), alo = smem_u32(stage_ptr(s, 1));
       const uint32_t bhi = smem_u32(stage_ptr(s, 2)), blo = smem_u32(stage_ptr(s, 3));
@@ -152,6 +154,8 @@ __global__ void __launch_bounds__(256, 2) k_tc_gemm(const TcGemmArgs g) {
         mma_issue(tmem, dah, dbl, idesc, 1u);
         mma_issue(tmem, dal, dbh, idesc, 1u);
       }
+      commit(&bar[s]);
+    } else if (tid == 0) {
       commit(&bar[s]);
     }
     // the stage of chunk kc-1 is refilled with chunk kc + TSTAGES - 1 once its MMAs have completed
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(256, 2) k_tc_gemm(const TcGemmArgs g) {
   cp_async_wait<0>();
   fence_after();
   // ---- epilogue: thread = accumulator row (lane quadrant of the warp), 64 columns per warp half ----------
-  if (nk >= 1) {
+  if (nk >= 1 && !(g.debug & 1)) {
     const int q = warp & 3, half = warp >> 2;
     const long long m = m0 + 32 * q + lane;
     float* C = g.C ? g.C + (long long)blockIdx.z * g.part_stride : nullptr;
@@ -236,7 +240,16 @@ __global__ void __launch_bounds__(256, 2) k_tc_gemm(const TcGemmArgs g) {
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static cudaError_t launch_tc(const TcGemmArgs& g, int ksplit, cudaStream_t st) {
+static cudaError_t launch_tc(const TcGemmArgs& g0, int ksplit, cudaStream_t st) {
+  TcGemmArgs g = g0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("BFX_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    g.debug = dbg;
+  }
   auto kern = k_tc_gemm<A_MN, B_MN, EPI>;
   const size_t smem = (size_t)TSTAGES * STAGE_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
