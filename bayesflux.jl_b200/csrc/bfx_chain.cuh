@@ -45,27 +45,55 @@ BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, f
                            bool want_grad, float& gn2) {
   const float sl = s.th[M.like_s];
   const float sigma = expf(sl);
-  // reduce the likelihood sums in double
+  // prior over theta_net + the network part of the gradient; theta_like (element 0 of its own quad) is handled
+  // after the reduction because its gradient needs the reduced likelihood sums
+  float acc[2] = {0.f, 0.f};  // sum theta_net^2, sum g_net^2
+  const float c2 = M.prior_c2;
+  const int like_q = M.like_s;
+  for_each_quad<NT>(M, [&](int k) {
+    const unsigned m = s.mask[k >> 2];
+    float4 th = ld4(s.th + k);
+    if (k == like_q) th.x = 0.f;
+    acc[0] += th.x * th.x + th.y * th.y + th.z * th.z + th.w * th.w;
+    if (want_grad) {
+      float4 g = mask4(ld4(s.g + k), m);
+      g.x -= c2 * th.x; g.y -= c2 * th.y; g.z -= c2 * th.z; g.w -= c2 * th.w;
+      if (k == like_q) g.x = 0.f;
+      st4(s.g + k, g);
+      acc[1] += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+    }
+  });
+  // ONE block reduction for everything: the likelihood sums in double, the two norms in float
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ds0 += __shfl_xor_sync(0xffffffffu, ds0, o);
     ds1 += __shfl_xor_sync(0xffffffffu, ds1, o);
+    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+    acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], o);
   }
   if (NT > 32) {
-    double* dred = reinterpret_cast<double*>(s.red);  // 32*4 floats = 64 doubles
+    double* dred = reinterpret_cast<double*>(s.red);  // 32*4 floats = 64 doubles: [w][0..1] doubles, floats behind
+    float* fred = s.red + 4 * (NT / 32);               // after 2 doubles per warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // (`red` is free here: every caller arrives through a barrier and the pass above does not touch it)
     if (lane == 0) {
       dred[2 * w] = ds0;
       dred[2 * w + 1] = ds1;
+      fred[2 * w] = acc[0];
+      fred[2 * w + 1] = acc[1];
     }
     __syncthreads();
     ds0 = 0.0;
     ds1 = 0.0;
+    acc[0] = 0.f;
+    acc[1] = 0.f;
+#pragma unroll
     for (int ww = 0; ww < NT / 32; ++ww) {
       ds0 += dred[2 * ww];
       ds1 += dred[2 * ww + 1];
+      acc[0] += fred[2 * ww];
+      acc[1] += fred[2 * ww + 1];
     }
-    __syncthreads();
   }
   // sigma prior (log link): logpdf(prior, e^s) + s and its derivative w.r.t. s
   double lps, dlps;
@@ -86,26 +114,10 @@ BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, f
   }
   like += -(double)B * (double)sl + lps;
   dlike_ds += -(double)B + dlps;
-  // prior over theta_net + finish the gradient
-  float acc[2] = {0.f, 0.f};  // sum theta_net^2, sum g^2
-  const float c2 = M.prior_c2;
   const float glike = (float)((double)nb * dlike_ds);
-  const int like_q = M.like_s;  // a multiple of 4 by construction: theta_like is element 0 of its own quad
-  for_each_quad<NT>(M, [&](int k) {
-    const unsigned m = s.mask[k >> 2];
-    float4 th = ld4(s.th + k);
-    if (k == like_q) th.x = 0.f;  // theta_like is not a network parameter: no prior term, its gradient is glike
-    acc[0] += th.x * th.x + th.y * th.y + th.z * th.z + th.w * th.w;
-    if (want_grad) {
-      float4 g = mask4(ld4(s.g + k), m);
-      g.x -= c2 * th.x; g.y -= c2 * th.y; g.z -= c2 * th.z; g.w -= c2 * th.w;
-      if (k == like_q) g.x = glike;
-      st4(s.g + k, g);
-      acc[1] += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
-    }
-  });
-  block_sum<NT, 2>(acc, s.red);
-  gn2 = acc[1];
+  if (want_grad && threadIdx.x == 0) s.g[like_q] = glike;  // made visible by the barrier every consumer pass starts after
+  gn2 = acc[1] + glike * glike;
+  __syncthreads();
   return (double)nb * like + (M.prior_c0n - 0.5 * (double)c2 * (double)acc[0]);
 }
 

@@ -75,6 +75,46 @@ BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns) {
   }
 }
 
+// The same recording fused into the pass that produces the new theta (SGLD / SGNHT / SGNHTS): the thread that
+// updates padded quad k also writes it out, so the separate pass over theta and its barrier disappear.
+struct Recorder {
+  float* dst;   // flat sample slot of this chain for this step, or nullptr
+  float* rdst;  // DiagCov window slot (padded), or nullptr
+};
+
+template <int NT, int BT, bool TC>
+BFX_DEV Recorder make_recorder(Ctx<NT, BT, TC>& X, long long ns) {
+  const RunDev& R = X.R;
+  Recorder r{nullptr, nullptr};
+  if (R.samples && (ns % R.keep_every) == 0) {
+    long long slot = ns / R.keep_every - 1 - R.kept_origin;
+    if (R.ring_slots > 0) slot %= R.ring_slots;
+    r.dst = R.samples + (long long)X.c * R.samples_chain_stride + slot * R.M.P;
+  }
+  if (X.ring) r.rdst = X.ring + ((ns - 1) % R.S.ma_windowlength) * (long long)R.Ps;
+  return r;
+}
+
+// J0 = flat index of element 0 of quad k (the valid elements of a quad are consecutive in the flat order: padding
+// only ever follows the last row of a column)
+BFX_DEV void rec_store(const Recorder& r, int k, unsigned m, const float4& t, int J0) {
+  if (r.rdst) st4(r.rdst + k, t);
+  if (r.dst) {
+    float* p = r.dst + J0;
+    if (m == 15u && (reinterpret_cast<unsigned long long>(p) & 15ull) == 0) {
+      st4(p, t);
+    } else if (m == 15u && (reinterpret_cast<unsigned long long>(p) & 7ull) == 0) {
+      *reinterpret_cast<float2*>(p) = make_float2(t.x, t.y);
+      *reinterpret_cast<float2*>(p + 2) = make_float2(t.z, t.w);
+    } else {
+      if (m & 1u) p[0] = t.x;
+      if (m & 2u) p[1] = t.y;
+      if (m & 4u) p[2] = t.z;
+      if (m & 8u) p[3] = t.w;
+    }
+  }
+}
+
 // DualAveragingStepSize / ConstantStepsize  (adapters/stepsize/*.jl)
 BFX_DEV float stepsize_adapt(ChainScalars& sc, const SamplerDev& S, float mh_prob) {
   if (S.sadapter_kind == SA_CONST) return S.l;
@@ -174,18 +214,21 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
   float* th = X.s.th;
   const float* g = X.s.g;
   const float* inj = X.inj(0);
+  X.sc.nsampled += 1;
+  const Recorder rec = make_recorder(X, X.sc.t);  // samples[:, t] = θ, written by the update pass itself
   for_each_quad<NT>(X.R.M, [&](int k) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
+    const int J0 = rec.dst ? __ldg(X.R.M.pad_flat + k) : 0;  // issued early: overlaps the Philox block
     const float4 z = noise_quad(X.R.M, X.key, X.gstep, 0, inj, k);
     const float4 t = ld4(th + k), gg = ld4(g + k);
     float4 o;
     BFX_MAP4(o, comp(t, c) + ha * comp(gg, c) + sa * comp(z, c));
-    st4(th + k, mask4(o, m));
+    o = mask4(o, m);
+    st4(th + k, o);
+    rec_store(rec, k, m, o, J0);
   });
   __syncthreads();
-  X.sc.nsampled += 1;
-  record_sample(X, X.sc.t);  // samples[:, t] = θ
   X.sc.t += 1;
 }
 
