@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbfx.so")
+LIB_PATH = os.environ.get("LIBBFX") or os.path.join(_HERE, "libbfx.so")
 
 # names mirror include/bfx.h
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NAN_G, ERR_NAN_THETA, ERR_NO_DATA, ERR_STATE = range(8)

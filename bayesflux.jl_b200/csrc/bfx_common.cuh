@@ -139,6 +139,18 @@ struct ChainScalars {
 };
 
 // everything a launch needs (passed by value as a __grid_constant__ kernel parameter)
+// division by a per-launch constant: q = hi64(n * m) for n < 2^32 (m = floor(2^64 / d) + 1, exact while n * d < 2^64),
+// so the per-step schedule arithmetic (batch of the epoch, kept-sample slot) costs a multiply, not a 64-bit divide
+struct FastDiv {
+  unsigned long long m;  // 0: use the plain division
+  unsigned long long d;
+};
+inline FastDiv make_fastdiv(long long dv) {
+  FastDiv f{0ull, dv > 0 ? (unsigned long long)dv : 1ull};
+  if (f.d > 1 && f.d < (1ull << 32)) f.m = ~0ull / f.d + 1ull;
+  return f;
+}
+
 struct RunDev {
   ModelDev M;
   SamplerDev S;
@@ -185,6 +197,8 @@ struct RunDev {
   int* work;
   int chunk_len;               // update! calls per work item
   long long grid_cap;          // upper bound of the CTA pool (recurrent scratch is sized by it)
+  // filled by the launcher from nb, keep_every, ring_slots, S.ma_windowlength
+  FastDiv fd_nb, fd_keep, fd_slots, fd_window;
 };
 
 // evaluation-only launch (bfx_loglikeprior / bfx_grad_loglikeprior)

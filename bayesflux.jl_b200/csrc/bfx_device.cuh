@@ -15,6 +15,23 @@ namespace bfx {
 
 #define BFX_DEV __device__ __forceinline__
 
+// Phase timing of the fused kernels (build with -DBFX_TIMING; off by default: TICK compiles to nothing).
+// Thread 0 of every CTA adds the cycles since its previous TICK to counter i.
+#ifdef BFX_TIMING
+static __device__ unsigned long long g_bfx_timing[24];
+__shared__ long long s_bfx_tprev;
+#define BFX_TICK(i)                                                        \
+  do {                                                                     \
+    if (threadIdx.x == 0) {                                                \
+      const long long now__ = clock64();                                   \
+      atomicAdd(&g_bfx_timing[i], (unsigned long long)(now__ - s_bfx_tprev)); \
+      s_bfx_tprev = now__;                                                 \
+    }                                                                      \
+  } while (0)
+#else
+#define BFX_TICK(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011).  counter = (quad index, step, chain, draw slot)
 // ---------------------------------------------------------------------------------
@@ -39,6 +56,19 @@ BFX_DEV float2 box_muller(unsigned a, unsigned b) {
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   return make_float2(r * c, r * s);
+}
+
+BFX_DEV void fdivmod(const FastDiv& f, unsigned long long n, unsigned long long& q, unsigned long long& r) {
+  if (f.d == 1ull) {
+    q = n;
+    r = 0ull;
+  } else if (f.m != 0ull && n < (1ull << 32)) {
+    q = __umul64hi(n, f.m);
+    r = n - q * f.d;
+  } else {
+    q = n / f.d;
+    r = n - q * f.d;
+  }
 }
 
 struct NoiseKey {
@@ -397,6 +427,7 @@ struct ChainSmem {
   float* red;   // [32*4] reduction scratch
   double* dacc; // [4]   double accumulators (thread 0)
   unsigned char* mask;  // [S/4] validity bits of each padded quad (copy of M.pad_mask)
+  unsigned short* qflat;  // [S/4] flat index of element 0 of each padded quad (P < 65536 in this regime)
   float* scr;   // per-CTA HBM scratch of the recurrent path (per-step records) or nullptr
   unsigned char* tc;  // tensor-core region (128-byte aligned) or nullptr
 };
@@ -405,7 +436,7 @@ struct ChainSmem {
 template <int BT>
 __host__ __device__ inline size_t chain_smem_floats(const ModelDev& M) {
   return (size_t)2 * M.S + (M.tc.enabled ? 0 : M.act_total) + BT /*ys*/ + BT /*idx*/ + 32 * 4 /*red*/ +
-         (size_t)((M.S / 4 + 15) & ~15) / 4 /*mask*/;
+         (size_t)((M.S / 4 + 15) & ~15) / 4 /*mask*/ + (size_t)((M.S / 4 + 15) & ~15) / 2 /*qflat*/;
 }
 
 template <int BT>
@@ -428,6 +459,7 @@ BFX_DEV ChainSmem carve_smem(const ModelDev& M, unsigned char* base) {
   s.idx = reinterpret_cast<int*>(f); f += BT;
   s.red = f; f += 32 * 4;
   s.mask = reinterpret_cast<unsigned char*>(f); f += ((M.S / 4 + 15) & ~15) / 4;
+  s.qflat = reinterpret_cast<unsigned short*>(f); f += ((M.S / 4 + 15) & ~15) / 2;
   s.tc = nullptr;
   s.scr = nullptr;
   if (M.tc.enabled) {

@@ -92,7 +92,7 @@ cudaError_t launch_mcmc(const RunDev& R, const LaunchCfg& cfg, cudaStream_t st) 
 
 cudaError_t launch_debug_batch(const RunDev& R, int c, unsigned long long gstep, long long* out, long long* Bout,
                                cudaStream_t st) {
-  k_debug_batch<<<64, 256, 0, st>>>(R, c, gstep, out, Bout);
+  k_debug_batch<<<64, 256, 0, st>>>(with_fastdiv(R), c, gstep, out, Bout);
   return cudaGetLastError();
 }
 

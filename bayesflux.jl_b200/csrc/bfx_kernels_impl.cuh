@@ -22,7 +22,9 @@ BFX_DEV void perm_keys(unsigned long long seed, unsigned chainkey, unsigned long
 
 // minibatch of global step `gstep` (0-based): epoch = gstep / nb, batch k = gstep % nb covers
 // positions [k*B, min(n, (k+1)*B)) of that epoch's permutation (abstract.jl:102-105,117-118)
-BFX_DEV void make_batch(const RunDev& R, int c, unsigned long long gstep, BatchSrc& bs, long long& Bk) {
+// `fresh` = false: bs still holds the keys of the previous step of the same chain, which stay valid inside an epoch
+BFX_DEV void make_batch(const RunDev& R, int c, unsigned long long gstep, BatchSrc& bs, long long& Bk,
+                        bool fresh = true) {
   bs.n = R.n;
   bs.full = 0;
   bs.shuffle = R.shuffle;
@@ -34,17 +36,24 @@ BFX_DEV void make_batch(const RunDev& R, int c, unsigned long long gstep, BatchS
     return;
   }
   bs.idx = nullptr;
-  unsigned long long epoch = gstep / (unsigned long long)R.nb, k = gstep % (unsigned long long)R.nb;
+  unsigned long long epoch, k;
+  fdivmod(R.fd_nb, gstep, epoch, k);
   bs.first = (long long)k * R.B;
   long long rem = R.n - bs.first;
   Bk = rem < R.B ? rem : R.B;
-  unsigned chainkey = R.batch_shared ? 0xFFFFFFFFu : (R.chain0 + (unsigned)c);
-  perm_keys(R.seed, chainkey, epoch, bs.k0, bs.k1);
+  if (fresh || k == 0ull) {
+    unsigned chainkey = R.batch_shared ? 0xFFFFFFFFu : (R.chain0 + (unsigned)c);
+    perm_keys(R.seed, chainkey, epoch, bs.k0, bs.k1);
+  }
 }
 
 template <int NT>
 BFX_DEV void load_mask(const ModelDev& M, const ChainSmem& s) {
-  for (int i = threadIdx.x; i < M.S / 4; i += NT) s.mask[i] = __ldg(M.pad_mask + i);
+  for (int i = threadIdx.x; i < M.S / 4; i += NT) {
+    s.mask[i] = __ldg(M.pad_mask + i);
+    const int J0 = __ldg(M.pad_flat + 4 * i);
+    s.qflat[i] = (unsigned short)(J0 < 0 ? 0 : J0);
+  }
 }
 
 template <int NT, int BT, bool TC>
@@ -144,12 +153,13 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_c
     X.window = R.mode_window ? R.mode_window + (long long)c * R.S.mode_windowlength : nullptr;
     for_each_quad<NT>(M, [&](int k) { st4(s.th + k, gld4(X.th_g + k)); });
     __syncthreads();
+    BFX_TICK(13);  // work-item fetch + chain state load
     const int it0 = chunk * R.chunk_len;
     const int it1 = it0 + R.chunk_len < R.nsteps ? it0 + R.chunk_len : R.nsteps;
     for (int it = it0; it < it1; ++it) {
       if (X.sc.status != 0) break;  // a NaN guard fired: this chain is frozen
       X.gstep = (unsigned long long)(R.gstep0 + it);
-      make_batch(R, c, X.gstep, X.bs, X.Bk);
+      make_batch(R, c, X.gstep, X.bs, X.Bk, it == it0);
       if (KIND == S_SGLD) step_sgld(X);
       else if (KIND == S_SGNHT) step_sgnht(X);
       else if (KIND == S_SGNHTS) step_sgnhts(X);
@@ -157,6 +167,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_c
       else if (KIND == S_HMC) step_hmc(X);
       else step_mode(X);
       __syncthreads();
+      BFX_TICK(11);  // sampler update pass (+ fused recording)
       if (R.progress && c == 0 && threadIdx.x == 0) *(volatile unsigned long long*)R.progress = X.gstep + 1ull;
     }
     __syncthreads();
@@ -165,11 +176,21 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_c
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicExch(R.work + 1 + c, chunk + 1);
+    BFX_TICK(12);  // chain state store + hand-over
   }
   if constexpr (TC) tc::teardown<NT>(M, tr);
 }
 
 // ---- launchers --------------------------------------------------------------------
+inline RunDev with_fastdiv(const RunDev& R) {
+  RunDev Rf = R;
+  Rf.fd_nb = make_fastdiv(R.nb);
+  Rf.fd_keep = make_fastdiv(R.keep_every);
+  Rf.fd_slots = make_fastdiv(R.ring_slots);
+  Rf.fd_window = make_fastdiv(R.S.ma_windowlength);
+  return Rf;
+}
+
 template <int NT, int BT, bool TC = false>
 inline cudaError_t launch_eval_t(const EvalDev& E, cudaStream_t st) {
   size_t smem = chain_smem_bytes<BT>(E.M) + (size_t)E.M.tc.smem_pad;
@@ -184,6 +205,7 @@ template <int NT, int BT, bool TC = false>
 inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
   size_t smem = chain_smem_bytes<BT>(R.M) + (size_t)R.M.tc.smem_pad;
   cudaError_t e;
+  const RunDev Rf = with_fastdiv(R);
 #define BFX_LAUNCH(KIND)                                                                        \
   {                                                                                             \
     auto kern = k_mcmc<NT, BT, KIND, TC>;                                                           \
@@ -215,7 +237,7 @@ inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
     long long grid = (long long)(per_sm > 0 ? per_sm : 1) * sms;                                \
     if (grid > items) grid = items;                                                             \
     if (grid > R.grid_cap) grid = R.grid_cap;                                                   \
-    kern<<<(unsigned)grid, NT, smem, st>>>(R);                                                  \
+    kern<<<(unsigned)grid, NT, smem, st>>>(Rf);                                                 \
   }
   switch (R.S.kind) {
     case S_SGLD: BFX_LAUNCH(S_SGLD); break;

@@ -57,20 +57,42 @@ BFX_DEV bool block_any(bool f, float* red) {
   return v[0] > 0.f;
 }
 
+// where the ns-th sample of this chain is kept (flat row of P floats), or nullptr when it is not kept
+template <int NT, int BT, bool TC>
+BFX_DEV float* sample_slot(const Ctx<NT, BT, TC>& X, long long ns) {
+  const RunDev& R = X.R;
+  if (!R.samples) return nullptr;
+  unsigned long long q, r;
+  fdivmod(R.fd_keep, (unsigned long long)ns, q, r);
+  if (r != 0ull) return nullptr;
+  long long slot = (long long)q - 1 - R.kept_origin;
+  if (R.ring_slots > 0) {
+    unsigned long long sq, sr;
+    fdivmod(R.fd_slots, (unsigned long long)slot, sq, sr);
+    slot = (long long)sr;
+  }
+  return R.samples + (long long)X.c * R.samples_chain_stride + slot * R.M.P;
+}
+// row of the DiagCov window ring (padded layout) that takes the ns-th sample
+template <int NT, int BT, bool TC>
+BFX_DEV float* window_slot(const Ctx<NT, BT, TC>& X, long long ns) {
+  unsigned long long q, r;
+  fdivmod(X.R.fd_window, (unsigned long long)(ns - 1), q, r);
+  return X.ring + (long long)r * (long long)X.R.Ps;
+}
+
 // s.samples[:, t] = copy(θ)  (+ DiagCov window ring).  ns = nsampled AFTER the increment.
 // Recorded samples leave the engine in the reference's flat order; the window ring is internal (padded).
 template <int NT, int BT, bool TC>
 BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns) {
   const RunDev& R = X.R;
-  if (R.samples && (ns % R.keep_every) == 0) {
-    long long slot = ns / R.keep_every - 1 - R.kept_origin;
-    if (R.ring_slots > 0) slot %= R.ring_slots;
-    float* dst = R.samples + (long long)X.c * R.samples_chain_stride + slot * R.M.P;
+  float* dst = sample_slot(X, ns);
+  if (dst) {
     const float* th = X.s.th;
     for_each_flat<NT>(R.M, [&](int J, int k) { dst[J] = th[k]; });
   }
   if (X.ring) {
-    float* rdst = X.ring + ((ns - 1) % R.S.ma_windowlength) * (long long)R.Ps;
+    float* rdst = window_slot(X, ns);
     for_each_quad<NT>(R.M, [&](int k) { st4(rdst + k, ld4(X.s.th + k)); });
   }
 }
@@ -84,14 +106,8 @@ struct Recorder {
 
 template <int NT, int BT, bool TC>
 BFX_DEV Recorder make_recorder(Ctx<NT, BT, TC>& X, long long ns) {
-  const RunDev& R = X.R;
-  Recorder r{nullptr, nullptr};
-  if (R.samples && (ns % R.keep_every) == 0) {
-    long long slot = ns / R.keep_every - 1 - R.kept_origin;
-    if (R.ring_slots > 0) slot %= R.ring_slots;
-    r.dst = R.samples + (long long)X.c * R.samples_chain_stride + slot * R.M.P;
-  }
-  if (X.ring) r.rdst = X.ring + ((ns - 1) % R.S.ma_windowlength) * (long long)R.Ps;
+  Recorder r{sample_slot(X, ns), nullptr};
+  if (X.ring) r.rdst = window_slot(X, ns);
   return r;
 }
 
@@ -219,7 +235,7 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
   for_each_quad<NT>(X.R.M, [&](int k) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
-    const int J0 = rec.dst ? __ldg(X.R.M.pad_flat + k) : 0;  // issued early: overlaps the Philox block
+    const int J0 = X.s.qflat[k >> 2];
     const float4 z = noise_quad(X.R.M, X.key, X.gstep, 0, inj, k);
     const float4 t = ld4(th + k), gg = ld4(g + k);
     float4 o;

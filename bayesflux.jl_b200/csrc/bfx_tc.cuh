@@ -250,9 +250,11 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   const float inv_sigma = 1.f / expf(sl);
   double ds0 = 0.0, ds1 = 0.0;
 
+  BFX_TICK(0);  // everything since the previous evaluation ended (update, record, bookkeeping)
   pack_weights<NT>(M, s, R);
   if (want_grad)
     for (int k = tid; k < 72; k += NT) R.glast[k] = 0.f;
+  BFX_TICK(1);  // pack
   // (made visible to the async proxy by the fence + barrier after the first tile is staged)
 
   const int d = M.d_in;
@@ -295,6 +297,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
     fence_async_smem();
     fence_before();
     __syncthreads();
+    BFX_TICK(2);  // stage indices, targets, X
 
     // ---- forward ---------------------------------------------------------------------------------
     float a[16];       // activations of the last hidden layer (this thread's fragment)
@@ -320,6 +323,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       mbar_wait(&R.bar[0], R.par[0]);
       R.par[0] ^= 1;
       fence_after();
+      BFX_TICK(3);  // forward MMA issue + wait
       // epilogue of layer l on the fragment: rows r0/r1, columns 32h + 8j + 2(lane%4) + {0,1}
       const bool active = 32 * h < L.hout;
       if (active) ld_16x256b_x4(zaddr + (uint32_t)(32 * h), a);
@@ -366,6 +370,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         fence_async_smem();
         fence_before();
         __syncthreads();
+        BFX_TICK(4);  // hidden-layer epilogue
       }
     }
     // ---- output layer (fan-out 1) + likelihood on the fragment of the last hidden layer -----------
@@ -480,6 +485,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       __syncthreads();
       if (tid <= 64 && (tid < hl || tid == 64))
         R.glast[tid] += (R.gpart[tid] + R.gpart[65 + tid]) + (R.gpart[130 + tid] + R.gpart[195 + tid]);
+      BFX_TICK(5);  // output layer + likelihood + delta tile
       // ---- backward ------------------------------------------------------------------------------
       for (int l = nh - 1; l >= 0; --l) {
         const TcLayer& L = T.L[l];
@@ -510,6 +516,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           mbar_wait(&R.bar[1], R.par[1]);
           R.par[1] ^= 1;
           fence_after();
+          BFX_TICK(6);  // backward MMA issue + wait (dA)
           // delta of layer l-1 = dA * act'(A_{l-1}); A_{l-1} is the input tile of layer l
           const int hp = L.kpad;  // = fan-out of layer l-1
           const int act_p = M.L[l - 1].act;
@@ -560,10 +567,12 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           fence_async_smem();
           fence_before();
           __syncthreads();
+          BFX_TICK(7);  // backward epilogue (delta of the layer below)
         } else {
           mbar_wait(&R.bar[2], R.par[2]);
           R.par[2] ^= 1;
           fence_after();
+          BFX_TICK(8);  // last dW MMA issue + wait
         }
       }
     }
@@ -606,7 +615,10 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
     fence_before();
   }
   __syncthreads();
-  return eval_finish<NT>(M, s, B, nb, ds0, ds1, want_grad, gn2);
+  BFX_TICK(9);  // gradient dump
+  const double v__ = eval_finish<NT>(M, s, B, nb, ds0, ds1, want_grad, gn2);
+  BFX_TICK(10);  // prior + norms + value
+  return v__;
 }
 
 }  // namespace tc
