@@ -78,6 +78,17 @@ struct NoiseKey {
 
 // the 4 standard normals of flat parameters 4q..4q+3 for (chain, step, slot)
 BFX_DEV float4 normal_quad(const NoiseKey& k, unsigned long long step, unsigned slot, unsigned q) {
+#ifdef BFX_EXP_NONOISE
+  return make_float4(__uint_as_float(0x3f000000u ^ (q << 3)), 0.25f, -0.5f, __uint_as_float(0x3e000000u ^ ((unsigned)step << 2)));
+#endif
+#ifdef BFX_EXP_NOBM
+  {
+    uint4 ctr = make_uint4(q, (unsigned)step, k.chain, (slot << 24) | (unsigned)((step >> 32) & 0xFFFFFFu));
+    uint2 key = make_uint2((unsigned)k.seed, (unsigned)(k.seed >> 32));
+    uint4 r = philox4x32_10(ctr, key);
+    return make_float4((float)(int)r.x * 4.6e-10f, (float)(int)r.y * 4.6e-10f, (float)(int)r.z * 4.6e-10f, (float)(int)r.w * 4.6e-10f);
+  }
+#endif
   uint4 ctr = make_uint4(q, (unsigned)step, k.chain, (slot << 24) | (unsigned)((step >> 32) & 0xFFFFFFu));
   uint2 key = make_uint2((unsigned)k.seed, (unsigned)(k.seed >> 32));
   uint4 r = philox4x32_10(ctr, key);

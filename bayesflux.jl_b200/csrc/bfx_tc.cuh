@@ -43,6 +43,13 @@ BFX_DEV void mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint
       "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
+// one lane of a converged warp.  MMA issue sits in warp-uniform code behind this predicate: inside a divergent
+// `tid == 0` region the compiler wraps every tcgen05.mma in an elect/broadcast loop (~100 cycles per MMA).
+BFX_DEV bool elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(e));
+  return e != 0;
+}
 BFX_DEV void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -305,20 +312,28 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
     for (int l = 0; l < nh; ++l) {
       const TcLayer& L = T.L[l];
       const LayerDev& D = M.L[l];
-      if (tid == 0) {
+      if (warp == 0) {
         fence_after();
+        const bool lead = elect_one();
         const uint32_t a_sbo = (L.ccols >> 3) * 128, b_lbo = (L.hout >> 3) * 128;
-        const uint32_t ahi = smem_u32(R.base + L.a_off), alo = ahi + L.a_bytes;
-        const uint32_t bhi = smem_u32(R.base + L.w_off), blo = bhi + L.w_bytes;
+        const uint32_t ahi = smem_u32(R.base + L.a_off), bhi = smem_u32(R.base + L.w_off);
         const uint32_t idesc = make_idesc(L.hout, 0, 1);
-        for (int k = 0; k < (L.kpad >> 4); ++k) {
-          // A: K-major (rows = batch): LBO = next 16-byte K chunk, SBO = next 8 rows; 16 k = 2 chunks
-          // B: MN-major (rows = fan-in k, cols = fan-out n): SBO = next 8 n, LBO = next 8 k rows
-          mma3(R.tmem, make_desc(ahi + k * 256, 128, a_sbo), make_desc(alo + k * 256, 128, a_sbo),
-               make_desc(bhi + k * 2 * b_lbo, b_lbo, 128), make_desc(blo + k * 2 * b_lbo, b_lbo, 128), idesc,
-               k ? 1u : 0u);
+        // A: K-major (rows = batch): LBO = next 16-byte K chunk, SBO = next 8 rows; 16 k = 2 chunks
+        // B: MN-major (rows = fan-in k, cols = fan-out n): SBO = next 8 n, LBO = next 8 k rows
+        // a k-step only moves the start-address field (bytes >> 4) of the four descriptors
+        uint64_t dahi = make_desc(ahi, 128, a_sbo), dalo = make_desc(ahi + L.a_bytes, 128, a_sbo);
+        uint64_t dbhi = make_desc(bhi, b_lbo, 128), dblo = make_desc(bhi + L.w_bytes, b_lbo, 128);
+        const uint64_t astep = 256 >> 4, bstep = (2 * b_lbo) >> 4;
+        const int nk = L.kpad >> 4;
+        for (int k = 0; k < nk; ++k) {
+          if (lead) mma3(R.tmem, dahi, dalo, dbhi, dblo, idesc, k ? 1u : 0u);
+          dahi += astep;
+          dalo += astep;
+          dbhi += bstep;
+          dblo += bstep;
         }
-        commit(&R.bar[0]);
+        if (lead) commit(&R.bar[0]);
+        __syncwarp();
       }
       mbar_wait(&R.bar[0], R.par[0]);
       R.par[0] ^= 1;
@@ -489,28 +504,44 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       // ---- backward ------------------------------------------------------------------------------
       for (int l = nh - 1; l >= 0; --l) {
         const TcLayer& L = T.L[l];
-        if (tid == 0) {
+        if (warp == 0) {
           fence_after();
-          const uint32_t dhi = smem_u32(R.base + T.d_off), dlo = dhi + T.d_bytes;
-          const uint32_t whi = smem_u32(R.base + L.w_off), wlo = whi + L.w_bytes;
-          const uint32_t xhi = smem_u32(R.base + L.a_off), xlo = xhi + L.a_bytes;
+          const bool lead = elect_one();
+          const uint32_t dhi = smem_u32(R.base + T.d_off), whi = smem_u32(R.base + L.w_off);
+          const uint32_t xhi = smem_u32(R.base + L.a_off);
           if (l > 0) {
             // dA[b][i] = sum_o D[b][o] W[o][i]:  A = D tile K-major (K = fan-out), B = W tile K-major (rows n = fan-in)
             const uint32_t w_sbo = (L.hout >> 3) * 128;
             const uint32_t idesc = make_idesc(L.kpad, 0, 0);
-            for (int k = 0; k < (L.hout >> 4); ++k)
-              mma3(R.tmem, make_desc(dhi + k * 256, 128, 1024), make_desc(dlo + k * 256, 128, 1024),
-                   make_desc(whi + k * 256, 128, w_sbo), make_desc(wlo + k * 256, 128, w_sbo), idesc, k ? 1u : 0u);
-            commit(&R.bar[1]);
+            uint64_t ddhi = make_desc(dhi, 128, 1024), ddlo = make_desc(dhi + T.d_bytes, 128, 1024);
+            uint64_t dwhi = make_desc(whi, 128, w_sbo), dwlo = make_desc(whi + L.w_bytes, 128, w_sbo);
+            const int nk = L.hout >> 4;
+            for (int k = 0; k < nk; ++k) {
+              if (lead) mma3(R.tmem, ddhi, ddlo, dwhi, dwlo, idesc, k ? 1u : 0u);
+              ddhi += 16;  // 256 bytes
+              ddlo += 16;
+              dwhi += 16;
+              dwlo += 16;
+            }
+            if (lead) commit(&R.bar[1]);
           }
           // dW[o][c] += sum_b D[b][o] Ain[b][c]:  A = D tile MN-major (M = fan-out), B = Ain tile MN-major, K = batch
           const uint32_t x_lbo = (L.ccols >> 3) * 128;
           const uint32_t idesc = make_idesc(L.ccols, 1, 1);
-          for (int k = 0; k < 4; ++k)
-            mma3(R.tmem + (uint32_t)L.dw_col, make_desc(dhi + k * 2048, 1024, 128), make_desc(dlo + k * 2048, 1024, 128),
-                 make_desc(xhi + k * 2 * x_lbo, x_lbo, 128), make_desc(xlo + k * 2 * x_lbo, x_lbo, 128), idesc,
-                 (k || !first_tile) ? 1u : 0u);
-          commit(&R.bar[2]);
+          uint64_t ddhi = make_desc(dhi, 1024, 128), ddlo = make_desc(dhi + T.d_bytes, 1024, 128);
+          uint64_t dxhi = make_desc(xhi, x_lbo, 128), dxlo = make_desc(xhi + L.a_bytes, x_lbo, 128);
+          const uint64_t xstep = (2 * x_lbo) >> 4;
+          const uint32_t dwacc = R.tmem + (uint32_t)L.dw_col;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (lead) mma3(dwacc, ddhi, ddlo, dxhi, dxlo, idesc, (k || !first_tile) ? 1u : 0u);
+            ddhi += 128;  // 2048 bytes
+            ddlo += 128;
+            dxhi += xstep;
+            dxlo += xstep;
+          }
+          if (lead) commit(&R.bar[2]);
+          __syncwarp();
         }
         if (l > 0) {
           mbar_wait(&R.bar[1], R.par[1]);
