@@ -2,6 +2,7 @@
 // No exceptions cross the boundary; every entry returns a status and records a message.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -69,6 +70,7 @@ struct bfx_model {
 
 struct bfx_sampler {
   bfx_model* m = nullptr;
+  int device = 0;  // copy of m->device: destroying a sampler must not touch the model (it may already be gone)
   bfx_sampler_desc d{};
   SamplerDev S{};
   int C = 0;
@@ -850,7 +852,7 @@ int32_t bfx_predict(bfx_model* m, const float* theta, int32_t C, const float* x_
 // ---------------------------------------------------------------------------------
 static void free_sampler(bfx_sampler* s) {
   if (!s) return;
-  cudaSetDevice(s->m->device);
+  cudaSetDevice(s->device);
   cudaFree(s->theta);
   cudaFree(s->mom);
   cudaFree(s->minv);
@@ -903,6 +905,7 @@ int32_t bfx_sampler_create(const bfx_sampler_desc* d, bfx_model* m, int32_t ncha
   bfx_sampler* s = new (std::nothrow) bfx_sampler();
   if (!s) return fail(BFX_ERR_BAD_ARG, "out of host memory");
   s->m = m;
+  s->device = m->device;
   s->d = *d;
   s->C = nchains;
   s->Ps = m->M.S;
@@ -1211,6 +1214,10 @@ static cudaError_t launch_run(bfx_sampler* s, RunDev& R, cudaStream_t st) {
   int cl = R.nsteps / 16;
   R.chunk_len = cl < 1 ? 1 : (cl > 16 ? 16 : cl);
   R.grid_cap = s->C;
+  if (const char* cap = std::getenv("BFX_GRID_CAP")) {  // developer knob: size of the CTA pool (occupancy experiments)
+    const long long v = std::atoll(cap);
+    if (v > 0 && v < R.grid_cap) R.grid_cap = v;
+  }
   return launch_mcmc(R, s->m->cfg, st);
 }
 

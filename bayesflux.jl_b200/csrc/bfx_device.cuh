@@ -52,9 +52,13 @@ BFX_DEV uint4 philox4x32_10(uint4 ctr, uint2 key) {
 BFX_DEV float2 box_muller(unsigned a, unsigned b) {
   float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
   float u2 = (float)b * 2.3283064365386963e-10f;           // [0,1)
-  float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
+  // straight-line MUFU code (no denormal / slow-path branches: u1 >= 2^-32)
+  float l2, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));  // sqrt(-2 ln u1)
+  const float ang = 6.283185307179586f * u2;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
   return make_float2(r * c, r * s);
 }
 

@@ -5,6 +5,7 @@
 //   k_debug_*: expose the engine's batch schedule / noise streams to the tests
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 
 #include "bfx_kernels.h"
 #include "bfx_samplers.cuh"
@@ -224,7 +225,7 @@ inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
       /* Over-subscribing the pool is harmless (late CTAs find the work counter exhausted).     */ \
       cudaFuncAttributes fa;                                                                    \
       if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {                                    \
-        long long by_smem = 233472 / (long long)(smem + fa.sharedSizeBytes + 1024);             \
+        long long by_smem = 232448 / (long long)(smem + fa.sharedSizeBytes + 1024);  /* 227 KB usable per SM */             \
         long long by_regs = 65536 / ((long long)(fa.numRegs > 0 ? fa.numRegs : 1) * NT);        \
         long long by_thr = 2048 / NT;                                                           \
         long long mn = by_smem < by_regs ? by_smem : by_regs;                                   \
@@ -237,6 +238,9 @@ inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
     long long grid = (long long)(per_sm > 0 ? per_sm : 1) * sms;                                \
     if (grid > items) grid = items;                                                             \
     if (grid > R.grid_cap) grid = R.grid_cap;                                                   \
+    if (std::getenv("BFX_DEBUG_LAUNCH"))                                                        \
+      std::fprintf(stderr, "[bfx] k_mcmc<%d,%d,kind %d,tc %d>: dyn smem %zu (S %d, tc %d + pad %d), CTAs/SM %d, grid %lld\n", \
+                   NT, BT, (int)KIND, (int)TC, smem, R.M.S, R.M.tc.total_bytes, R.M.tc.smem_pad, per_sm, grid); \
     kern<<<(unsigned)grid, NT, smem, st>>>(Rf);                                                 \
   }
   switch (R.S.kind) {

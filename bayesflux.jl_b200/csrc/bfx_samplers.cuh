@@ -232,6 +232,7 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
   const float* inj = X.inj(0);
   X.sc.nsampled += 1;
   const Recorder rec = make_recorder(X, X.sc.t);  // samples[:, t] = θ, written by the update pass itself
+  BFX_TICK(14);
   for_each_quad<NT>(X.R.M, [&](int k) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
@@ -244,6 +245,7 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
     st4(th + k, o);
     rec_store(rec, k, m, o, J0);
   });
+  BFX_TICK(15);
   __syncthreads();
   X.sc.t += 1;
 }

@@ -233,6 +233,8 @@ int32_t bfx_predict(bfx_model* m, const float* theta, int32_t nchains, const flo
  * SGLD/SGNHT/SGNHTS/GGMC/HMC constructors + initialise!  (sgld.jl:47-88 etc.) for
  * nchains independent chains living on the model's device. */
 int32_t bfx_sampler_create(const bfx_sampler_desc* desc, bfx_model* m, int32_t nchains, bfx_sampler** out);
+/* The model must outlive every other call on the sampler; destroy itself does not touch the model, so a garbage
+ * collector may finalise the two handles in either order. */
 int32_t bfx_sampler_destroy(bfx_sampler* s);
 /* initialise!(sampler, θ, numsamples; continue_sampling=false): zero momentum, reset
  * counters/adapters, theta_start P x C host floats. */

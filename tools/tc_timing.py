@@ -14,7 +14,8 @@ import numpy as np
 
 NAMES = ["step prologue (batch keys, dispatch)", "pack weights", "stage idx/targets/X", "fwd MMA issue+wait",
          "hidden epilogue", "output layer+like+delta", "bwd dA MMA wait", "bwd epilogue", "last dW wait",
-         "gradient dump", "eval_finish", "sampler update pass", "chunk store+hand-over", "chunk fetch+load"]
+         "gradient dump", "eval_finish", "sampler update pass", "chunk store+hand-over", "chunk fetch+load",
+         "  (update: setup before the pass)", "  (update: thread 0's own pass)"]
 
 
 def main():
