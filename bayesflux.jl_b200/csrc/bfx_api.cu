@@ -53,6 +53,8 @@ struct bfx_model {
   float* x = nullptr;
   float* y = nullptr;
   int64_t n = 0;
+  void* xsplit = nullptr;  // tensor-core path: x as bf16 hi/lo rows (4 * kpad bytes per observation), built lazily
+  int xsplit_kpad = 0;
   cudaStream_t stream = nullptr;
   // flat (ABI) <-> padded (engine) parameter layout
   std::vector<int> flat_pad, pad_flat;
@@ -345,6 +347,20 @@ static int32_t build_tc(bfx_model* m) {
   return BFX_OK;
 }
 
+// tensor-core path: the bf16 hi/lo copy of x the tiles are staged from (one pass over x per data set / first layer width)
+static int32_t ensure_xsplit(bfx_model* m) {
+  if (!m->M.tc.enabled || !m->x || m->M.seq) return BFX_OK;
+  const int kpad = m->M.tc.L[0].kpad;
+  if (m->xsplit && m->xsplit_kpad == kpad) return BFX_OK;
+  if (m->xsplit) cudaFree(m->xsplit);
+  m->xsplit = nullptr;
+  CK(cudaMalloc(&m->xsplit, (size_t)m->n * 4 * (size_t)kpad));
+  CK(launch_split_x(m->x, m->xsplit, m->n, m->M.d_in, kpad, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  m->xsplit_kpad = kpad;
+  return BFX_OK;
+}
+
 // ---------------------------------------------------------------------------------
 extern "C" {
 
@@ -427,6 +443,7 @@ int32_t bfx_model_destroy(bfx_model* m) {
     cudaSetDevice(m->device);
     if (m->x) cudaFree(m->x);
     if (m->y) cudaFree(m->y);
+    if (m->xsplit) cudaFree(m->xsplit);
     if (m->stream) cudaStreamDestroy(m->stream);
   }
   if (m->scratch) {
@@ -520,7 +537,9 @@ static int32_t set_data_impl(bfx_model* m, const float* x, const int64_t* dims, 
   if (st) return st;
   if (m->x) cudaFree(m->x);
   if (m->y) cudaFree(m->y);
+  if (m->xsplit) cudaFree(m->xsplit);
   m->x = m->y = nullptr;
+  m->xsplit = nullptr;
   size_t per = (size_t)d * (ndims == 3 ? (size_t)dims[0] : 1);
   CK(cudaMalloc(&m->x, per * (size_t)n * sizeof(float)));
   CK(cudaMalloc(&m->y, (size_t)n * sizeof(float)));
@@ -708,6 +727,11 @@ static int32_t eval_impl(bfx_model* m, const float* theta, int32_t C, const int6
   E.M = m->M;
   E.x = m->x;
   E.y = m->y;
+  if (int32_t xst = ensure_xsplit(m)) {
+    cleanup();
+    return xst;
+  }
+  E.xs = m->M.tc.enabled ? static_cast<const uint4*>(m->xsplit) : nullptr;
   E.n = m->n;
   E.C = C;
   E.theta = d_theta;
@@ -1187,6 +1211,8 @@ static int32_t fill_run_common(bfx_sampler* s, RunDev& R) {
   R.S = s->S;
   R.x = m->x;
   R.y = m->y;
+  if (int32_t xst = ensure_xsplit(m)) return xst;
+  R.xs = m->M.tc.enabled ? static_cast<const uint4*>(m->xsplit) : nullptr;
   R.n = m->n;
   R.C = s->C;
   R.chain0 = 0;

@@ -156,6 +156,7 @@ struct RunDev {
   SamplerDev S;
   const float* x;
   const float* y;
+  const uint4* xs;  // tensor-core path: x pre-split into bf16 hi/lo rows (bfx_api.cu ensure_xsplit), or nullptr
   long long n;
   int C;
   unsigned chain0;  // global id of local chain 0 (noise / permutation keys)
@@ -206,6 +207,7 @@ struct EvalDev {
   ModelDev M;
   const float* x;
   const float* y;
+  const uint4* xs;  // as RunDev::xs
   long long n;
   int C;
   const float* theta;  // [C][P] flat (ABI layout)

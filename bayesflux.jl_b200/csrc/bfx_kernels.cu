@@ -55,6 +55,28 @@ __global__ void k_padded_to_flat(const float* __restrict__ pad, float* __restric
     flat[e] = pad[c * S + flat_pad[J]];
   }
 }
+// x (d x n, column-major) -> rows of [kpad/8 hi chunks | kpad/8 lo chunks], 8 bf16 per 16-byte chunk, zero beyond d:
+// the staging format of the tensor-core path (tc::chain_eval_tc)
+__global__ void k_split_x(const float* __restrict__ x, uint4* __restrict__ out, long long n, int d, int nch) {
+  const long long total = n * nch;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / nch;
+    const int ch = (int)(e - r * nch);
+    float v[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      const int ff = 8 * ch + f;
+      v[f] = ff < d ? x[r * d + ff] : 0.f;
+    }
+    uint4 hh, ll;
+    tc::split2(v[0], v[1], hh.x, ll.x);
+    tc::split2(v[2], v[3], hh.y, ll.y);
+    tc::split2(v[4], v[5], hh.z, ll.z);
+    tc::split2(v[6], v[7], hh.w, ll.w);
+    out[r * (2 * nch) + ch] = hh;
+    out[r * (2 * nch) + nch + ch] = ll;
+  }
+}
 __global__ void k_fill(float* p, long long n, float v) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) p[e] = v;
 }
@@ -63,6 +85,10 @@ cudaError_t launch_flat_to_padded(const float* flat, float* pad, const int* flat
                                   cudaStream_t st) {
   k_fill<<<592, 256, 0, st>>>(pad, (long long)S * C, fill);
   k_flat_to_padded<<<1184, 256, 0, st>>>(flat, pad, flat_pad, P, S, (long long)P * C);
+  return cudaGetLastError();
+}
+cudaError_t launch_split_x(const float* x, void* out, long long n, int d, int kpad, cudaStream_t st) {
+  k_split_x<<<1184, 256, 0, st>>>(x, static_cast<uint4*>(out), n, d, kpad >> 3);
   return cudaGetLastError();
 }
 cudaError_t launch_padded_to_flat(const float* pad, float* flat, const int* flat_pad, int P, int S, int C, cudaStream_t st) {

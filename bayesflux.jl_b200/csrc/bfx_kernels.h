@@ -14,6 +14,7 @@ struct LaunchCfg {
 size_t smallp_smem_bytes(const ModelDev& M, int bt);
 cudaError_t launch_eval(const EvalDev& E, const LaunchCfg& cfg, cudaStream_t st);
 cudaError_t launch_mcmc(const RunDev& R, const LaunchCfg& cfg, cudaStream_t st);
+cudaError_t launch_split_x(const float* x, void* out, long long n, int d, int kpad, cudaStream_t st);
 cudaError_t launch_debug_batch(const RunDev& R, int c, unsigned long long gstep, long long* out, long long* Bout,
                                cudaStream_t st);
 cudaError_t launch_debug_noise(unsigned long long seed, unsigned chain, unsigned long long gstep, unsigned slot, int P,

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) 
   bs.idx = E.idx ? E.idx + (long long)c * E.idx_chain_stride : nullptr;
   float gn2;
   double v;
-  if constexpr (TC) v = tc::chain_eval_tc<NT>(M, s, tr, E.x, E.y, bs, E.B, E.num_batches, E.want_grad != 0, gn2);
+  if constexpr (TC) v = tc::chain_eval_tc<NT>(M, s, tr, E.x, E.xs, E.y, bs, E.B, E.num_batches, E.want_grad != 0, gn2);
   else v = chain_eval<NT, BT>(M, s, E.x, E.y, bs, E.B, E.num_batches, E.want_grad != 0, gn2,
                               E.yhat_out ? E.yhat_out + (long long)c * E.B : nullptr);
   if (threadIdx.x == 0) E.v_out[c] = v;

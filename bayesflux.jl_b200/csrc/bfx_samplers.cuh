@@ -34,7 +34,7 @@ struct Ctx {
   BFX_DEV float uniform() const { return R.inj_uniforms ? R.inj_uniforms[c] : uniform_draw(key, gstep); }
 
   BFX_DEV double eval(const BatchSrc& b, long long Bn, float nbs, bool want_grad, float& gn2) {
-    if constexpr (TC) return tc::chain_eval_tc<NT>(R.M, s, *tcr, R.x, R.y, b, Bn, nbs, want_grad, gn2);
+    if constexpr (TC) return tc::chain_eval_tc<NT>(R.M, s, *tcr, R.x, R.xs, R.y, b, Bn, nbs, want_grad, gn2);
     else return chain_eval<NT, BT>(R.M, s, R.x, R.y, b, Bn, nbs, want_grad, gn2);
   }
   BFX_DEV double grad(float& gn2) { return eval(bs, Bk, R.num_batches, true, gn2); }

@@ -70,6 +70,12 @@ BFX_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 BFX_DEV void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 BFX_DEV void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 BFX_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte asynchronous copy global -> shared; src_bytes = 0 writes zeros
+BFX_DEV void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+BFX_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 BFX_DEV void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 16 lanes x 32 columns of a warp's lane quadrant: thread t gets, for j = 0..3,
@@ -243,8 +249,8 @@ BFX_DEV void mma3(uint32_t d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t
 // ---------------------------------------------------------------------------------------------
 template <int NT>
 BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, const float* __restrict__ x,
-                             const float* __restrict__ y, const BatchSrc& bs, long long B, float nb, bool want_grad,
-                             float& gn2) {
+                             const uint4* __restrict__ xs, const float* __restrict__ y, const BatchSrc& bs, long long B,
+                             float nb, bool want_grad, float& gn2) {
   static_assert(NT == 256, "the tensor-core path uses 8 warps: 4 lane quadrants x 2 column halves");
   const TcDesc& T = M.tc;
   const int nh = T.nh;
@@ -268,14 +274,31 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   for (long long t0 = 0; t0 < B; t0 += 64) {
     const int nvalid = (int)((B - t0) < 64 ? (B - t0) : 64);
     const bool first_tile = t0 == 0;
-    // ---- stage the tile: indices, targets, X as hi/lo BF16 (rows >= nvalid are zero) ----------
-    if (tid < 64) {
-      long long o = (tid < nvalid) ? batch_obs(bs, t0 + tid) : -1;
-      s.idx[tid] = (int)o;
-      s.ys[tid] = (o >= 0) ? __ldg(y + o) : 0.f;
-    }
-    __syncthreads();
-    {
+    // ---- stage the tile: targets and X as hi/lo BF16 (rows >= nvalid are zero) ------------------------
+    if (xs) {
+      // x was split once per data set into rows of [hi chunks | lo chunks] (16 bytes = 8 bf16 each): staging is one
+      // asynchronous 16-byte copy per chunk straight into the core-block tile.  Four adjacent threads own one
+      // batch row (each derives the row's observation index itself: no index exchange, no barrier).
+      const TcLayer& L0 = T.L[0];
+      const int nch = L0.kpad >> 3, cpr = 2 * nch;
+      const int sbo = (L0.ccols >> 3) * 128;
+      const int b = tid >> 2;
+      const long long o = (b < nvalid) ? batch_obs(bs, t0 + b) : -1;
+      unsigned char* row = R.base + L0.a_off + (b >> 3) * sbo + (b & 7) * 16;
+      const uint4* src = xs + (o >= 0 ? o : 0) * cpr;
+      for (int piece = tid & 3; piece < cpr; piece += 4) {
+        const int half = piece >= nch ? 1 : 0, ch = piece - half * nch;
+        cp_async16(row + half * L0.a_bytes + ch * 128, src + piece, o >= 0 ? 16 : 0);
+      }
+      if ((tid & 3) == 0) s.ys[b] = (o >= 0) ? __ldg(y + o) : 0.f;
+      cp_async_wait_all();
+    } else {
+      if (tid < 64) {
+        long long o = (tid < nvalid) ? batch_obs(bs, t0 + tid) : -1;
+        s.idx[tid] = (int)o;
+        s.ys[tid] = (o >= 0) ? __ldg(y + o) : 0.f;
+      }
+      __syncthreads();
       const TcLayer& L0 = T.L[0];
       const int nch = L0.kpad >> 3;
       const int sbo = (L0.ccols >> 3) * 128;
