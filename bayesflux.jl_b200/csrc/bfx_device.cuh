@@ -82,17 +82,6 @@ struct NoiseKey {
 
 // the 4 standard normals of flat parameters 4q..4q+3 for (chain, step, slot)
 BFX_DEV float4 normal_quad(const NoiseKey& k, unsigned long long step, unsigned slot, unsigned q) {
-#ifdef BFX_EXP_NONOISE
-  return make_float4(__uint_as_float(0x3f000000u ^ (q << 3)), 0.25f, -0.5f, __uint_as_float(0x3e000000u ^ ((unsigned)step << 2)));
-#endif
-#ifdef BFX_EXP_NOBM
-  {
-    uint4 ctr = make_uint4(q, (unsigned)step, k.chain, (slot << 24) | (unsigned)((step >> 32) & 0xFFFFFFu));
-    uint2 key = make_uint2((unsigned)k.seed, (unsigned)(k.seed >> 32));
-    uint4 r = philox4x32_10(ctr, key);
-    return make_float4((float)(int)r.x * 4.6e-10f, (float)(int)r.y * 4.6e-10f, (float)(int)r.z * 4.6e-10f, (float)(int)r.w * 4.6e-10f);
-  }
-#endif
   uint4 ctr = make_uint4(q, (unsigned)step, k.chain, (slot << 24) | (unsigned)((step >> 32) & 0xFFFFFFu));
   uint2 key = make_uint2((unsigned)k.seed, (unsigned)(k.seed >> 32));
   uint4 r = philox4x32_10(ctr, key);
@@ -124,9 +113,28 @@ BFX_DEV unsigned mix32(unsigned x) {
 
 BFX_DEV unsigned long long perm_index(unsigned long long pos, unsigned long long n, unsigned k0, unsigned k1) {
   if (n <= 1) return 0;
+  if (n <= 0x80000000ull) {
+    // every data set the API accepts (n < 2^31): the same network in 32-bit arithmetic (bit-identical results,
+    // half the instructions of the 64-bit form below)
+    const unsigned nn = (unsigned)n;
+    int bits = 32 - __clz((int)(nn - 1u));
+    if (bits < 2) bits = 2;
+    const int lb = bits >> 1, rb = bits - lb;  // left (high) / right (low) widths
+    const unsigned lmask = (1u << lb) - 1u, rmask = (1u << rb) - 1u;
+    unsigned v = (unsigned)pos;
+    do {
+      unsigned L = (v >> rb) & lmask, R = v & rmask;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if ((r & 1) == 0) L = (L ^ mix32(R * 0x9E3779B1u + k0 + (unsigned)r * 0x85EBCA6Bu)) & lmask;
+        else R = (R ^ mix32(L * 0xC2B2AE35u + k1 + (unsigned)r * 0x27D4EB2Fu)) & rmask;
+      }
+      v = (L << rb) | R;
+    } while (v >= nn);
+    return v;
+  }
   int bits = 64 - __clzll((long long)(n - 1));
-  if (bits < 2) bits = 2;
-  const int lb = bits >> 1, rb = bits - lb;  // left (high) / right (low) widths
+  const int lb = bits >> 1, rb = bits - lb;
   const unsigned long long lmask = (1ull << lb) - 1, rmask = (1ull << rb) - 1;
   unsigned long long v = pos;
   do {

@@ -75,6 +75,10 @@ BFX_DEV void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
                : "memory");
 }
+BFX_DEV void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
 BFX_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 BFX_DEV void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -215,16 +219,19 @@ BFX_DEV void pack_weights(const ModelDev& M, const ChainSmem& s, const Region& R
     const TcLayer& L = T.L[l];
     const LayerDev& D = M.L[l];
     const int noc = L.hout >> 3;           // 8-wide fan-out chunks
-    const int items = ((D.nin + 7) >> 3) * 8 * noc;  // rows i >= nin stay zero
+    const int nin8 = (D.nin + 7) >> 3;     // 8-row fan-in blocks (rows i >= nin stay zero)
     unsigned char* hi = R.base + L.w_off;
     unsigned char* lo = hi + L.w_bytes;
-    for (int e = threadIdx.x; e < items; e += NT) {
-      // lanes walk i%8 fastest: 8 lanes x 16 B = one conflict-free 128-byte row of the core block
-      const int il = e & 7, rest = e >> 3, oc = rest % noc, ih = rest / noc;
+    // work item of a warp = (8-row fan-in block, group of 4 fan-out chunks): lanes walk i%8 fastest (8 lanes x 16 B =
+    // one conflict-free 128-byte row of the core block).  No integer division per element.
+    const int lane = threadIdx.x & 31, il = lane & 7;
+    const int ng = (noc + 3) >> 2, items = nin8 * ng;
+    for (int it = threadIdx.x >> 5; it < items; it += NT / 32) {
+      const int ih = it / ng, oc = 4 * (it - ih * ng) + (lane >> 3);
       const int i = ih * 8 + il;
-      if (i >= D.nin) continue;
+      if (i >= D.nin || oc >= noc) continue;
       const float* src = s.th + D.w_s + i * D.ldw + 8 * oc;
-      float4 a = ld4(src), b = ld4(src + 4);
+      const float4 a = ld4(src), b = ld4(src + 4);
       uint4 h, q;
       split2(a.x, a.y, h.x, q.x);
       split2(a.z, a.w, h.y, q.y);
@@ -264,10 +271,9 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   double ds0 = 0.0, ds1 = 0.0;
 
   BFX_TICK(0);  // everything since the previous evaluation ended (update, record, bookkeeping)
-  pack_weights<NT>(M, s, R);
   if (want_grad)
     for (int k = tid; k < 72; k += NT) R.glast[k] = 0.f;
-  BFX_TICK(1);  // pack
+  if (!xs) pack_weights<NT>(M, s, R);  // (with xs: packed while the first tile's copies are in flight)
   // (made visible to the async proxy by the fence + barrier after the first tile is staged)
 
   const int d = M.d_in;
@@ -290,7 +296,9 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         const int half = piece >= nch ? 1 : 0, ch = piece - half * nch;
         cp_async16(row + half * L0.a_bytes + ch * 128, src + piece, o >= 0 ? 16 : 0);
       }
-      if ((tid & 3) == 0) s.ys[b] = (o >= 0) ? __ldg(y + o) : 0.f;
+      if ((tid & 3) == 0) cp_async4(s.ys + b, y + (o >= 0 ? o : 0), o >= 0 ? 4 : 0);
+      BFX_TICK(1);  // stage: indices + copy issue
+      if (first_tile) pack_weights<NT>(M, s, R);  // theta -> bf16 weight tiles, in the shadow of the copies
       cp_async_wait_all();
     } else {
       if (tid < 64) {
@@ -641,7 +649,24 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       const TcLayer& L = T.L[l];
       const LayerDev& D = M.L[l];
       const int ngroups = L.ccols >> 3;
-      for (int gq = h; gq < ngroups; gq += 2) {
+      // 64 columns that lie fully inside the weight matrix: one 32-column fragment per column half
+      int g0 = 0;
+      if (D.nout == 64) {
+        for (; 8 * (g0 + 8) <= D.nin; g0 += 8) {
+          float v[16];
+          ld_16x256b_x4(zaddr + (uint32_t)(L.dw_col + 8 * (g0 + 4 * h)), v);
+          float* gp = s.g + D.w_s + (8 * (g0 + 4 * h) + 2 * (lane & 3)) * D.ldw + r0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gp[0] = v[4 * j + 0];
+            gp[D.ldw] = v[4 * j + 1];
+            gp[8] = v[4 * j + 2];
+            gp[D.ldw + 8] = v[4 * j + 3];
+            gp += 8 * D.ldw;
+          }
+        }
+      }
+      for (int gq = g0 + h; gq < ngroups; gq += 2) {
         float v[4];
         ld_16x256b_x1(zaddr + (uint32_t)(L.dw_col + 8 * gq), v);
         const int c = 8 * gq + 2 * (lane & 3);
@@ -651,6 +676,11 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           gp[D.ldw] = v[1];
           gp[8] = v[2];
           gp[D.ldw + 8] = v[3];
+        } else if (8 * gq == L.kpad) {  // the constant-1 column: the bias gradient sits in column kpad only
+          if ((lane & 3) == 0) {
+            if (r0 < D.nout) s.g[D.b_s + r0] = v[0];
+            if (r1 < D.nout) s.g[D.b_s + r1] = v[2];
+          }
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {

@@ -12,7 +12,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
-NAMES = ["step prologue (batch keys, dispatch)", "pack weights", "stage idx/targets/X", "fwd MMA issue+wait",
+NAMES = ["step prologue (batch keys, dispatch)", "stage: indices + copy issue", "pack weights + copy wait", "fwd MMA issue+wait",
          "hidden epilogue", "output layer+like+delta", "bwd dA MMA wait", "bwd epilogue", "last dW wait",
          "gradient dump", "eval_finish", "sampler update pass", "chunk store+hand-over", "chunk fetch+load",
          "  (update: setup before the pass)", "  (update: thread 0's own pass)"]
