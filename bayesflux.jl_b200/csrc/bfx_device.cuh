@@ -486,8 +486,10 @@ BFX_DEV ChainSmem carve_smem(const ModelDev& M, unsigned char* base) {
   s.tc = nullptr;
   s.scr = nullptr;
   if (M.tc.enabled) {
-    unsigned long long a = reinterpret_cast<unsigned long long>(f);
-    s.tc = reinterpret_cast<unsigned char*>((a + 127ull) & ~127ull);
+    // aligned by pointer arithmetic (not through an integer): the compiler keeps the shared address space and
+    // emits LDS / STS with 32-bit addresses for every tile access instead of generic LD / ST
+    const unsigned mis = (unsigned)__cvta_generic_to_shared(f) & 127u;
+    s.tc = reinterpret_cast<unsigned char*>(f) + ((128u - mis) & 127u);
   }
   return s;
 }
