@@ -121,9 +121,8 @@ BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, f
   return (double)nb * like + (M.prior_c0n - 0.5 * (double)c2 * (double)acc[0]);
 }
 
-BFX_DEV float clip_scale(float gn2, float maxnorm) {
-  float ng = sqrtf(gn2);
-  return ng > maxnorm ? maxnorm / ng : 1.f;  // src/utils/gradient_utils.jl:6-10
-}
+// src/utils/gradient_utils.jl:6-10: ng > maxnorm ? maxnorm / ng : 1, as min(1, maxnorm / sqrt(gn2)) with one rsqrt
+// (same limits: gn2 = 0 or NaN -> 1, gn2 = inf -> 0)
+BFX_DEV float clip_scale(float gn2, float maxnorm) { return fminf(1.f, maxnorm * rsqrtf(gn2)); }
 
 }  // namespace bfx

@@ -222,7 +222,9 @@ BFX_DEV void mass_adapt(Ctx<NT, BT, TC>& X, float gn2) {
 template <int NT, int BT, bool TC>
 BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
   const SamplerDev& S = X.R.S;
-  float alpha = S.stepsize_a * powf(S.stepsize_b + (float)X.sc.t, -S.stepsize_gamma);  // sgld.jl:12
+  // sgld.jl:12  a (b + t)^(-gamma): exp2(-gamma log2(b + t)) with the full-precision log2f / exp2f, within 2e-6
+  // relative of powf for t < 2^24 and a third of its instructions on the serial path of every step
+  float alpha = S.stepsize_a * exp2f(-S.stepsize_gamma * log2f(S.stepsize_b + (float)X.sc.t));
   alpha = fmaxf(alpha, S.min_stepsize);
   float gn2;
   X.grad(gn2);

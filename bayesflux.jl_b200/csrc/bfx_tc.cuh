@@ -225,9 +225,9 @@ BFX_DEV void pack_weights(const ModelDev& M, const ChainSmem& s, const Region& R
     // work item of a warp = (8-row fan-in block, group of 4 fan-out chunks): lanes walk i%8 fastest (8 lanes x 16 B =
     // one conflict-free 128-byte row of the core block).  No integer division per element.
     const int lane = threadIdx.x & 31, il = lane & 7;
-    const int ng = (noc + 3) >> 2, items = nin8 * ng;
+    const int two = noc > 4 ? 1 : 0, items = nin8 << two;  // hout <= 64: one or two groups of 4 chunks per block
     for (int it = threadIdx.x >> 5; it < items; it += NT / 32) {
-      const int ih = it / ng, oc = 4 * (it - ih * ng) + (lane >> 3);
+      const int ih = it >> two, oc = 4 * (it & two) + (lane >> 3);
       const int i = ih * 8 + il;
       if (i >= D.nin || oc >= noc) continue;
       const float* src = s.th + D.w_s + i * D.ldw + 8 * oc;
