@@ -71,6 +71,10 @@ struct TcDesc {
 };
 
 struct ModelDev {
+  // Philox round keys of the run's seed (filled per launch by the launcher, 0 = not set): the noise pass reads them
+  // as constant-bank operands instead of re-deriving the key schedule for every quad
+  unsigned philox_rk[20];
+  int philox_rk_set;
   int nlayers;
   int P, Pnet;   // total / network parameters
   int S;         // floats in the padded smem parameter block (multiple of 4)

@@ -48,6 +48,18 @@ BFX_DEV uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
+// the same rounds with the key schedule given (rk[2r], rk[2r+1] = key + r * (W0, W1))
+BFX_DEV uint4 philox4x32_10_rk(uint4 ctr, const unsigned (&rk)[20]) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ rk[2 * r], lo1, hi0 ^ ctr.w ^ rk[2 * r + 1], lo0);
+  }
+  return ctr;
+}
+
 // two uint32 -> two independent N(0,1) (Box-Muller)
 BFX_DEV float2 box_muller(unsigned a, unsigned b) {
   float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
@@ -429,6 +441,13 @@ BFX_DEV float4 noise_quad(const ModelDev& M, const NoiseKey& key, unsigned long 
     const int4 J = __ldg(reinterpret_cast<const int4*>(M.pad_flat + k));
     return make_float4(J.x >= 0 ? inj[J.x] : 0.f, J.y >= 0 ? inj[J.y] : 0.f, J.z >= 0 ? inj[J.z] : 0.f,
                        J.w >= 0 ? inj[J.w] : 0.f);
+  }
+  if (M.philox_rk_set) {
+    const uint4 ctr = make_uint4((unsigned)(k >> 2), (unsigned)step, key.chain,
+                                 (slot << 24) | (unsigned)((step >> 32) & 0xFFFFFFu));
+    const uint4 r = philox4x32_10_rk(ctr, M.philox_rk);
+    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+    return make_float4(a.x, a.y, b.x, b.y);
   }
   return normal_quad(key, step, slot, (unsigned)(k >> 2));
 }

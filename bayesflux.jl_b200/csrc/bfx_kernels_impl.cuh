@@ -189,6 +189,11 @@ inline RunDev with_fastdiv(const RunDev& R) {
   Rf.fd_keep = make_fastdiv(R.keep_every);
   Rf.fd_slots = make_fastdiv(R.ring_slots);
   Rf.fd_window = make_fastdiv(R.S.ma_windowlength);
+  for (int r = 0; r < 10; ++r) {
+    Rf.M.philox_rk[2 * r] = (unsigned)R.seed + (unsigned)r * 0x9E3779B9u;
+    Rf.M.philox_rk[2 * r + 1] = (unsigned)(R.seed >> 32) + (unsigned)r * 0xBB67AE85u;
+  }
+  Rf.M.philox_rk_set = 1;
   return Rf;
 }
 
