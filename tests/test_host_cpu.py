@@ -137,3 +137,28 @@ def test_sampler_descriptor_mirrors_reference_defaults():
     assert d.sadapter_kind == L.STEP_DUAL_AVERAGING and d.madapter_kind == L.MASS_DIAGCOV
     assert (d.steps, d.maxnorm, d.da_t0, d.da_adapt_steps, d.ma_adapt_steps, d.ma_windowlength) == (1, 5.0, 10, 1000, 1000, 100)
     assert bf.HMC(1e-4, 5)._desc().madapter_kind == L.MASS_FULLCOV  # reference default, rejected by the engine
+
+
+def test_result_buffers_are_recycled_only_when_unreferenced():
+    """mcmc hands out host arrays from a small pool: an array the caller (or a view) still references is never
+    reused, a dropped one is."""
+    from bayesflux_b200 import api
+
+    class Dummy:
+        pass
+
+    s = Dummy()
+    a = api._result_buffer(s, (7, 1, 3))
+    a[:] = 1.0
+    b = api._result_buffer(s, (7, 1, 3))  # `a` is still referenced here
+    assert b is not a
+    view = a[:, -1, :]
+    del a
+    c = api._result_buffer(s, (7, 1, 3))  # the view keeps the first array alive
+    assert c is not view.base and c is not b
+    first_id = id(view.base)
+    del view
+    d = api._result_buffer(s, (7, 1, 3))  # now it may come back
+    assert id(d) == first_id
+    e = api._result_buffer(s, (7, 2, 3))  # other shapes never alias
+    assert e.shape == (7, 2, 3) and e is not d
