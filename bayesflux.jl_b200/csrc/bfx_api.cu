@@ -1,5 +1,6 @@
 // C ABI of libbfx (include/bfx.h): handles, descriptor translation, memory, launches.
 // No exceptions cross the boundary; every entry returns a status and records a message.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1020,14 +1021,17 @@ static int32_t state_d2h(bfx_sampler* s, const float* src_pad, float* dst_flat) 
   return BFX_OK;
 }
 
-int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) {
+// upload_theta = false: the caller brings theta in itself (bfx_mcmc_run, chain group by chain group)
+static int32_t sampler_init_impl(bfx_sampler* s, const float* theta_start, bool upload_theta) {
   if (!s || !theta_start) return fail(BFX_ERR_BAD_ARG, "NULL argument");
   bfx_model* m = s->m;
   int32_t st = ensure_stream(m);
   if (st) return st;
   const size_t all = (size_t)s->Ps * sizeof(float) * (size_t)s->C;
-  st = state_h2d(s, s->theta, theta_start, 0.f);
-  if (st) return st;
+  if (upload_theta) {
+    st = state_h2d(s, s->theta, theta_start, 0.f);
+    if (st) return st;
+  }
   if (s->mom) CK(cudaMemsetAsync(s->mom, 0, all, m->stream));
   if (s->theta_old) CK(cudaMemsetAsync(s->theta_old, 0, all, m->stream));
   if (s->minv) {
@@ -1079,6 +1083,8 @@ int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) {
   s->initialised = true;
   return BFX_OK;
 }
+
+int32_t bfx_sampler_init(bfx_sampler* s, const float* theta_start) { return sampler_init_impl(s, theta_start, true); }
 
 static int32_t fetch_scalars(bfx_sampler* s, std::vector<ChainScalars>& sc) {
   sc.resize((size_t)s->C);
@@ -1490,12 +1496,31 @@ int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta
   bfx_model* m = s->m;
   st = ensure_stream(m);
   if (st) return st;
+  // Chain-group pipelining (fresh runs that fit one launch): theta of group g+1 goes up and the samples of group
+  // g-1 come down while the kernel of group g runs, instead of copy -> kernel -> copy for all chains at once.
+  int groups = 1;
+  if (!run->continue_sampling && samples_out && nkept > 0 && !m->stream_regime && s->C >= 512) {
+    const int64_t ke0 = run->keep_every > 0 ? run->keep_every : 1;
+    const int64_t ups0 = s->S.kind == S_HMC ? s->S.path_len : 1;
+    const int64_t bytes_all = (int64_t)s->C * m->M.P * 4 * (nnew / ke0 + 1);
+    // a group must still fill the persistent CTA pool (chunks of one chain run in order, so chains per launch, not
+    // work items, bound the parallelism): at most 4 groups of >= 320 chains
+    if (nnew * ups0 <= (1 << 16) && bytes_all <= (int64_t)(1ll << 30)) groups = std::max(1, std::min(4, s->C / 320));
+    if (const char* g = std::getenv("BFX_PIPELINE_GROUPS")) groups = std::max(1, std::min(16, std::atoi(g)));
+    if (groups > 1 && !(nnew * ups0 <= (1 << 16) && bytes_all <= (int64_t)(1ll << 30))) groups = 1;
+  }
   if (!run->continue_sampling) {
     if (!theta_start) return fail(BFX_ERR_BAD_ARG, "theta_start is NULL");
-    st = bfx_sampler_init(s, theta_start);
+    st = sampler_init_impl(s, theta_start, groups == 1);
     if (st) return st;
   }
-  if (nnew == 0) return BFX_OK;
+  if (nnew == 0) {
+    if (groups > 1) {  // nothing to run, but theta must still arrive
+      st = state_h2d(s, s->theta, theta_start, 0.f);
+      if (st) return st;
+    }
+    return BFX_OK;
+  }
   if (run->continue_sampling) {
     // initialise!(...; continue_sampling=true) re-zeroes the momentum (sgnht.jl:54, sgnht-s.jl:72,
     // ggmc.jl:122, hmc.jl:92-93) and GGMC restarts its window (ggmc.jl:116); everything else is kept
@@ -1540,10 +1565,13 @@ int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta
   float* d_kin = nullptr;
   int* d_acc = nullptr;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_up, ev_grp;
   bool registered = false;
   auto cleanup = [&]() {
     cudaFree(d_kin);
     cudaFree(d_acc);
+    for (cudaEvent_t e : ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_grp) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
       if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
@@ -1597,6 +1625,59 @@ int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta
     const int64_t slots = b / ke - a / ke;
     R.gstep0 = s->gstep;
     R.nsteps = (int)(cs * ups);
+    if (groups > 1 && !(d_samp[0] && slots > 0 && cs == nnew)) {
+      // (window rounding left it short of one launch after all) bring theta up the plain way
+      int32_t hst = state_h2d(s, s->theta, theta_start, 0.f);
+      if (hst) {
+        cleanup();
+        return hst;
+      }
+      groups = 1;
+    }
+    if (groups > 1) {
+      R.samples = d_samp[0];
+      R.samples_chain_stride = slots * P;
+      R.kept_origin = a / ke;
+      const int Cg = (C + groups - 1) / groups;
+      ev_up.resize(groups, nullptr);
+      ev_grp.resize(groups, nullptr);
+      for (int g = 0; g < groups; ++g) {
+        CKC(cudaEventCreateWithFlags(&ev_up[g], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&ev_grp[g], cudaEventDisableTiming));
+      }
+      auto copy_down = [&](int g) -> cudaError_t {
+        const int c0 = g * Cg, cn = std::min(Cg, C - c0);
+        if (cn <= 0) return cudaSuccess;
+        cudaError_t e = cudaStreamWaitEvent(s->copy_stream, ev_grp[g], 0);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy2DAsync(samples_out + ((size_t)c0 * nkept + kept_written) * P, (size_t)nkept * P * 4,
+                                 d_samp[0] + (size_t)c0 * slots * P, (size_t)slots * P * 4, (size_t)slots * P * 4, cn,
+                                 cudaMemcpyDeviceToHost, s->copy_stream);
+      };
+      for (int g = 0; g < groups; ++g) {
+        const int c0 = g * Cg, cn = std::min(Cg, C - c0);
+        if (cn <= 0) break;
+        CKC(cudaMemcpyAsync(s->stage + (size_t)c0 * P, theta_start + (size_t)c0 * P, (size_t)cn * P * 4,
+                            cudaMemcpyHostToDevice, s->copy_stream));
+        CKC(cudaEventRecord(ev_up[g], s->copy_stream));
+        CKC(cudaStreamWaitEvent(m->stream, ev_up[g], 0));
+        CKC(launch_flat_to_padded(s->stage + (size_t)c0 * P, s->theta + (size_t)c0 * s->Ps, m->d_flat_pad, P, s->Ps, cn,
+                                  0.f, m->stream));
+        R.c_begin = c0;
+        R.c_count = cn;
+        CKC(launch_run(s, R, m->stream));
+        s->launches += 1;
+        CKC(cudaEventRecord(ev_grp[g], m->stream));
+        if (g > 0) CKC(copy_down(g - 1));  // blocks the host on pageable memory while group g computes
+      }
+      CKC(copy_down(groups - 1));
+      R.c_begin = 0;
+      R.c_count = 0;
+      s->gstep += R.nsteps;
+      kept_written += slots;
+      done += cs;
+      continue;
+    }
     if (d_samp[buf] && slots > 0) {
       CKC(cudaStreamWaitEvent(m->stream, ev_copied[buf], 0));  // buffer free again?
       R.samples = d_samp[buf];

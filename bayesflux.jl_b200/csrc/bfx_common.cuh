@@ -202,6 +202,9 @@ struct RunDev {
   int* work;
   int chunk_len;               // update! calls per work item
   long long grid_cap;          // upper bound of the CTA pool (recurrent scratch is sized by it)
+  // a launch may cover only the chains [c_begin, c_begin + c_count) (c_count = 0: all C): bfx_mcmc_run pipelines
+  // chain groups so that the host copies of one group overlap the kernel of the next
+  int c_begin, c_count;
   // filled by the launcher from nb, keep_every, ring_slots, S.ma_windowlength
   FastDiv fd_nb, fd_keep, fd_slots, fd_window;
 };

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_c
   s.scr = R.scratch ? R.scratch + (long long)blockIdx.x * R.scratch_stride : nullptr;
   load_mask<NT>(M, s);
   const int nchunks = (R.nsteps + R.chunk_len - 1) / R.chunk_len;
-  const int total = R.C * nchunks;
+  const int ccount = R.c_count > 0 ? R.c_count : R.C;
+  const int total = ccount * nchunks;
   Ctx<NT, BT, TC> X(R, s);
   X.tcr = &tr;
   X.key.seed = R.seed;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_c
     const int item = s_item;
     __syncthreads();
     if (item >= total) break;
-    const int chunk = item / R.C, c = item - chunk * R.C;
+    const int chunk = item / ccount, c = R.c_begin + (item - chunk * ccount);
     if (threadIdx.x == 0) {
       volatile int* done = R.work + 1 + c;
       while (*done < chunk) __nanosleep(256);
@@ -239,7 +240,7 @@ inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
         if (mn > per_sm) per_sm = (int)mn;                                                      \
       }                                                                                         \
     }                                                                                           \
-    const long long items = (long long)R.C * ((R.nsteps + R.chunk_len - 1) / R.chunk_len);      \
+    const long long items = (long long)(R.c_count > 0 ? R.c_count : R.C) * ((R.nsteps + R.chunk_len - 1) / R.chunk_len); \
     long long grid = (long long)(per_sm > 0 ? per_sm : 1) * sms;                                \
     if (grid > items) grid = items;                                                             \
     if (grid > R.grid_cap) grid = R.grid_cap;                                                   \
