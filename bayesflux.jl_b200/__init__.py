@@ -13,7 +13,7 @@ from .api import (BNN, Chain, Dense, LSTM, RNN, NetConstructor, destruct, Gamma,
                   ConstantStepsize, DualAveragingStepSize, FixedMassAdapter, DiagCovMassAdapter,
                   RMSPropMassAdapter, FullCovMassAdapter, MCMCState, SGLD, SGNHT, SGNHTS, GGMC, HMC, mcmc,
                   advance, launch_count, Descent, Momentum, RMSProp, ADAM, FluxModeFinder, find_mode, predict,
-                  sample_posterior_predict, get_posterior_networks,
+                  sample_posterior_predict, get_posterior_networks, chain_diagnostics,
                   identity, relu, tanh, sigmoid)
 from .sharded import (shard_chains, shard_data, global_num_batches, model_regime, ShardedChain,  # noqa: F401,E402
                       mcmc_sharded)

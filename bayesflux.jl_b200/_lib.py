@@ -80,6 +80,7 @@ SYMBOLS = {
     "bfx_loglikeprior": [_vp, _vp, _i32, _vp, _i64, _i64, _f32, _vp],
     "bfx_grad_loglikeprior": [_vp, _vp, _i32, _vp, _i64, _i64, _f32, _vp, _vp],
     "bfx_predict": [_vp, _vp, _i32, _vp, _pi64, _i32, _vp, _vp],
+    "bfx_chain_diagnostics": [_i32, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
     "bfx_sampler_create": [C.POINTER(SamplerDesc), _vp, _i32, C.POINTER(_vp)],
     "bfx_sampler_destroy": [_vp],
     "bfx_sampler_init": [_vp, _vp],

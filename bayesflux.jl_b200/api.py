@@ -365,6 +365,28 @@ def predict(bnn: BNN, theta, x=None):
     return yhat, sig
 
 
+def chain_diagnostics(samples, max_lag: int = 0, device: int = 0, samples_dev: int = 0, shape=None):
+    """Pooled mean / variance, split-Rhat and effective sample size of every parameter, computed on the device
+    (include/bfx.h bfx_chain_diagnostics; SURVEY.md section 8f #3 -- the reference defers this to MCMCChains,
+    README.md:191-193).  ``samples``: the P x n x C array ``mcmc`` returns (or P x n for one chain); alternatively
+    ``samples_dev`` = device pointer of a [C][n][P] ring (``advance(..., ring_slots=n)``) with ``shape=(P, n, C)``.
+    Returns a dict of four float32 vectors of length P."""
+    if samples_dev:
+        P, n, Cn = (int(v) for v in shape)
+        ptr, on_dev = C.c_void_p(samples_dev), 1
+    else:
+        a = np.asarray(samples, dtype=np.float32)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        a = np.asfortranarray(a)
+        P, n, Cn = a.shape
+        ptr, on_dev = _ptr(a), 0
+    out = {k: np.empty(P, np.float32) for k in ("mean", "var", "rhat", "ess")}
+    L.check(L.lib.bfx_chain_diagnostics(int(device), ptr, on_dev, P, n, Cn, int(max_lag), _ptr(out["mean"]),
+                                        _ptr(out["var"]), _ptr(out["rhat"]), _ptr(out["ess"])))
+    return out
+
+
 def sample_posterior_predict(bnn: BNN, ch, x=None, rng=None):
     """sample_posterior_predict(bnn, ch; x = bnn.x)  src/model/BNN.jl:129-135: one predictive draw per posterior
     draw (columns of ch).  The forward passes run on the device; the draw around yhat is made here on the host

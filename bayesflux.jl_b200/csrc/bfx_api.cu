@@ -1851,3 +1851,8 @@ int32_t bfx_debug_noise(const bfx_sampler* s, const bfx_run_desc* run, int64_t c
 }
 
 }  // extern "C"
+
+// error reporting for the other translation units of the library (same thread-local message as above)
+namespace bfx {
+int32_t report_error(int32_t code, const std::string& msg) { return ::fail(code, msg); }
+}  // namespace bfx

@@ -229,6 +229,18 @@ int32_t bfx_grad_loglikeprior(bfx_model* m, const float* theta, int32_t nchains,
 int32_t bfx_predict(bfx_model* m, const float* theta, int32_t nchains, const float* x_new, const int64_t* dims,
                     int32_t ndims, float* yhat_out, float* sigma_out);
 
+/* ---- chain diagnostics over recorded samples --------------------------------- *
+ * The reference ships none: its README hands samples' to MCMCChains (README.md:191-193).  samples: [C][n][P]
+ * floats = the P x n x C column-major array bfx_mcmc_run returns (host pointer) or the device ring of
+ * bfx_mcmc_advance with ring_slots = n (samples_on_device = 1).  Every chain is split in halves (the middle draw
+ * of an odd n is dropped): m = 2C sequences of nh = n / 2 draws.  Outputs are P host floats each, any may be NULL:
+ * mean / var (ddof 1) of the m * nh draws, split-Rhat = sqrt(((nh-1)/nh W + B/nh) / W), and the effective sample
+ * size m nh / tau with tau from Geyer's initial positive + monotone sequence of the pair sums of
+ * rho_t = 1 - (W - mean_s acov_s(t)) / var+ (Stan reference manual, no rank normalisation), lags t <= max_lag
+ * (max_lag <= 0: all nh - 1 lags). */
+int32_t bfx_chain_diagnostics(int32_t device, const float* samples, int32_t samples_on_device, int64_t P, int64_t n,
+                              int64_t C, int64_t max_lag, float* mean, float* var, float* rhat, float* ess);
+
 /* ---- samplers ----------------------------------------------------------- *
  * SGLD/SGNHT/SGNHTS/GGMC/HMC constructors + initialise!  (sgld.jl:47-88 etc.) for
  * nchains independent chains living on the model's device. */

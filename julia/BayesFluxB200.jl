@@ -221,4 +221,16 @@ function BayesFlux.mcmc(m::DeviceBNN, batchsize::Int, numsamples::Int, sampler::
     return nchains == 1 ? sampler.samples : samples
 end
 
+# R̂ / ESS / pooled moments of the samples `mcmc` returned (P × n or P × n × C, Float32), computed on the device.
+# The reference hands `samples'` to MCMCChains for this (README.md:191-193).
+function diagnostics(samples::Array{Float32}; max_lag::Integer=0, device::Integer=0)
+    P, n = size(samples, 1), size(samples, 2)
+    C = ndims(samples) == 3 ? size(samples, 3) : 1
+    mean, var, rhat, ess = (Vector{Float32}(undef, P) for _ in 1:4)
+    check(GC.@preserve samples ccall((:bfx_chain_diagnostics, libbfx), Int32,
+        (Int32, Ptr{Float32}, Int32, Int64, Int64, Int64, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+        device, samples, 0, P, n, C, max_lag, mean, var, rhat, ess))
+    return (mean=mean, var=var, rhat=rhat, ess=ess)
+end
+
 end # module

@@ -1057,3 +1057,65 @@ def find_mode(m: Model, x, y, batchsize, epochs, finder: FluxModeFinder, theta_s
             if conv:
                 return theta, True
     return theta, False
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Chain diagnostics.  The reference ships none -- its README hands samples' to MCMCChains
+# (README.md:191-193) -- so this restates the published arithmetic: split-Rhat (Gelman et al., BDA3 11.4) and the
+# effective sample size from Geyer's initial positive + monotone sequence as in the Stan reference manual
+# ("Effective sample size"), without rank normalisation.  Parity unpinned against the reference (nothing to pin to);
+# pinned against closed forms in tests/test_oracle_diag.py (iid draws, AR(1) chains).
+# ---------------------------------------------------------------------------------------------------------
+def chain_diagnostics(samples, max_lag=0):
+    """samples: P x n x C (or P x n).  Returns dict(mean, var, rhat, ess), each of length P, float64.
+    Every chain is split in halves (the middle draw of an odd n is dropped): m = 2C sequences of nh = n // 2."""
+    x = np.asarray(samples, dtype=np.float64)
+    if x.ndim == 2:
+        x = x[:, :, None]
+    P, n, C = x.shape
+    nh = n // 2
+    halves = np.concatenate([x[:, :nh, :], x[:, n - nh:, :]], axis=2)  # P x nh x 2C (order does not matter)
+    m = 2 * C
+    mu = halves.mean(axis=1)                       # P x m
+    d = halves - mu[:, None, :]
+    var_s = (d * d).sum(axis=1) / (nh - 1)         # P x m, ddof 1
+    gm = mu.mean(axis=1)
+    W = var_s.mean(axis=1)
+    bsum = ((mu - gm[:, None]) ** 2).sum(axis=1)
+    var_means = bsum / (m - 1) if m > 1 else np.zeros(P)
+    var_plus = W * (nh - 1) / nh + var_means
+    total = m * nh
+    out = {"mean": gm, "var": (W * (nh - 1) * m + bsum * nh) / (total - 1.0)}
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out["rhat"] = np.where(W > 0, np.sqrt(var_plus / W), np.nan)
+    L = nh
+    if max_lag > 0 and max_lag + 1 < L:
+        L = max_lag + 1
+    ess = np.full(P, np.nan)
+    if nh >= 4 and L >= 2:
+        acov = np.empty((L, P))
+        for k in range(L):                          # biased autocovariance, averaged over the sequences
+            acov[k] = (d[:, : nh - k, :] * d[:, k:, :]).sum(axis=1).mean(axis=1) / nh
+        for j in range(P):
+            if not var_plus[j] > 0:
+                continue
+            rho = 1.0 - (W[j] - acov[:, j]) / var_plus[j]
+            rho[0] = 1.0
+            tau, prev, t, last_even = 0.0, np.inf, 0, 1.0
+            while t + 1 < L:
+                pe, po = rho[t], rho[t + 1]
+                pair = pe + po
+                if not pair > 0:
+                    last_even = pe
+                    break
+                pair = min(pair, prev)              # initial monotone sequence
+                tau += pair
+                prev = pair
+                t += 2
+                last_even = 0.0
+            if last_even > 0:
+                tau += 0.5 * last_even
+            tau_hat = max(-1.0 + 2.0 * tau, 1.0 / math.log10(total))
+            ess[j] = total / tau_hat
+    out["ess"] = ess
+    return out
