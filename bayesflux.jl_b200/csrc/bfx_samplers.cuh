@@ -81,35 +81,12 @@ BFX_DEV float* window_slot(const Ctx<NT, BT, TC>& X, long long ns) {
   return X.ring + (long long)r * (long long)X.R.Ps;
 }
 
-// s.samples[:, t] = copy(θ)  (+ DiagCov window ring).  ns = nsampled AFTER the increment.
-// Recorded samples leave the engine in the reference's flat order; the window ring is internal (padded).
-template <int NT, int BT, bool TC>
-BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns) {
-  const RunDev& R = X.R;
-  float* dst = sample_slot(X, ns);
-  if (dst) {
-    const float* th = X.s.th;
-    for_each_flat<NT>(R.M, [&](int J, int k) { dst[J] = th[k]; });
-  }
-  if (X.ring) {
-    float* rdst = window_slot(X, ns);
-    for_each_quad<NT>(R.M, [&](int k) { st4(rdst + k, ld4(X.s.th + k)); });
-  }
-}
-
 // The same recording fused into the pass that produces the new theta (SGLD / SGNHT / SGNHTS): the thread that
 // updates padded quad k also writes it out, so the separate pass over theta and its barrier disappear.
 struct Recorder {
   float* dst;   // flat sample slot of this chain for this step, or nullptr
   float* rdst;  // DiagCov window slot (padded), or nullptr
 };
-
-template <int NT, int BT, bool TC>
-BFX_DEV Recorder make_recorder(Ctx<NT, BT, TC>& X, long long ns) {
-  Recorder r{sample_slot(X, ns), nullptr};
-  if (X.ring) r.rdst = window_slot(X, ns);
-  return r;
-}
 
 // J0 = flat index of element 0 of quad k (the valid elements of a quad are consecutive in the flat order: padding
 // only ever follows the last row of a column)
@@ -129,6 +106,34 @@ BFX_DEV void rec_store(const Recorder& r, int k, unsigned m, const float4& t, in
       if (m & 8u) p[3] = t.w;
     }
   }
+}
+
+// s.samples[:, t] = copy(θ)  (+ DiagCov window ring).  ns = nsampled AFTER the increment.
+// Recorded samples leave the engine in the reference's flat order; the window ring is internal (padded).
+template <int NT, int BT, bool TC>
+BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns) {
+  const RunDev& R = X.R;
+  float* dst = sample_slot(X, ns);
+  if (dst) {
+    // quad order with the shared-memory quad -> flat table: vector stores, no global table lookups
+    const float* th = X.s.th;
+    const Recorder rec{dst, nullptr};
+    for_each_quad<NT>(R.M, [&](int k) {
+      const unsigned m = X.s.mask[k >> 2];
+      if (m) rec_store(rec, k, m, ld4(th + k), X.s.qflat[k >> 2]);
+    });
+  }
+  if (X.ring) {
+    float* rdst = window_slot(X, ns);
+    for_each_quad<NT>(R.M, [&](int k) { st4(rdst + k, ld4(X.s.th + k)); });
+  }
+}
+
+template <int NT, int BT, bool TC>
+BFX_DEV Recorder make_recorder(Ctx<NT, BT, TC>& X, long long ns) {
+  Recorder r{sample_slot(X, ns), nullptr};
+  if (X.ring) r.rdst = window_slot(X, ns);
+  return r;
 }
 
 // DualAveragingStepSize / ConstantStepsize  (adapters/stepsize/*.jl)
