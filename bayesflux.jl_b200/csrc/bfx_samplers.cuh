@@ -275,6 +275,9 @@ BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
   const float* g = X.s.g;
   const float* inj = X.inj(0);
   float acc[2] = {0.f, 0.f};  // p'p, nan flag
+  // the sample is written by the pass that produces it (a chain that turns NaN here is reported as an error, its
+  // slot is undefined either way)
+  const Recorder rec = make_recorder(X, X.sc.t);
   for_each_quad<NT>(R.M, [&](int k) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
@@ -286,6 +289,7 @@ BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
     BFX_MAP4(t, comp(t0, c) + l * comp(p, c));
     st4(X.mom + k, p);
     st4(th + k, t);
+    rec_store(rec, k, m, t, X.s.qflat[k >> 2]);
     acc[0] += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
     acc[1] += any_nan(t) ? 1.f : 0.f;
   });
@@ -300,7 +304,6 @@ BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
     return;
   }
   X.sc.nsampled += 1;
-  record_sample(X, X.sc.t);
   X.sc.t += 1;
 }
 
@@ -350,6 +353,7 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
   }
   acc[0] = 0.f;
   acc[1] = 0.f;
+  const Recorder rec = make_recorder(X, X.sc.t);  // the sample is written by the pass that finishes theta
   // O step with noise ~ N(0, M), second A half drift  (:98-104)
   for_each_quad<NT>(R.M, [&](int k) {
     const unsigned m = X.s.mask[k >> 2];
@@ -363,6 +367,7 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
     BFX_MAP4(t, comp(t0, c) + hl * comp(mi, c) * comp(p, c));
     st4(X.mom + k, p);
     st4(th + k, t);
+    rec_store(rec, k, m, t, X.s.qflat[k >> 2]);
     acc[0] += p.x * p.x * mi.x + p.y * p.y * mi.y + p.z * p.z * mi.z + p.w * p.w * mi.w;
     acc[1] += any_nan(t) ? 1.f : 0.f;
   });
@@ -375,7 +380,6 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
   if (R.kinetic_out && threadIdx.x == 0)
     R.kinetic_out[(long long)X.c * R.hist_stride + (X.sc.t - 1 - R.hist_origin)] = acc[0] / n;
   X.sc.nsampled += 1;
-  record_sample(X, X.sc.t);
   X.sc.t += 1;
 }
 
