@@ -276,6 +276,67 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   if (!xs) pack_weights<NT>(M, s, R);  // (with xs: packed while the first tile's copies are in flight)
   // (made visible to the async proxy by the fence + barrier after the first tile is staged)
 
+  // ---- dW accumulators (TMEM) -> s.g in the padded parameter layout.  ADD = std::true_type: add to what an earlier
+  // dump of the same evaluation left there.  The tensor core's FP32 accumulation truncates, and the bias grows with
+  // the number of MMAs chained into one accumulator (1.3e-3 relative over the 15 625 tiles of a 10^6-observation
+  // batch, tests/test_gpu_fullsize.py): accumulators are therefore flushed every kAccTiles tiles and the partial
+  // sums added on the CUDA cores (round to nearest).
+  constexpr int kAccTiles = 32;
+  auto dump = [&](auto ADD) {
+    constexpr bool add = decltype(ADD)::value;
+    auto put = [&](float* p, float v) { *p = add ? *p + v : v; };
+    fence_after();
+    for (int l = 0; l < nh; ++l) {
+      const TcLayer& L = T.L[l];
+      const LayerDev& D = M.L[l];
+      const int ngroups = L.ccols >> 3;
+      // 64 columns that lie fully inside the weight matrix: one 32-column fragment per column half
+      int g0 = 0;
+      if (D.nout == 64) {
+        for (; 8 * (g0 + 8) <= D.nin; g0 += 8) {
+          float v[16];
+          ld_16x256b_x4(zaddr + (uint32_t)(L.dw_col + 8 * (g0 + 4 * h)), v);
+          float* gp = s.g + D.w_s + (8 * (g0 + 4 * h) + 2 * (lane & 3)) * D.ldw + r0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            put(gp, v[4 * j + 0]);
+            put(gp + D.ldw, v[4 * j + 1]);
+            put(gp + 8, v[4 * j + 2]);
+            put(gp + D.ldw + 8, v[4 * j + 3]);
+            gp += 8 * D.ldw;
+          }
+        }
+      }
+      for (int gq = g0 + h; gq < ngroups; gq += 2) {
+        float v[4];
+        ld_16x256b_x1(zaddr + (uint32_t)(L.dw_col + 8 * gq), v);
+        const int c = 8 * gq + 2 * (lane & 3);
+        if (8 * gq + 8 <= D.nin && D.nout == 64) {  // group fully inside the weight matrix: no bounds checks
+          float* gp = s.g + D.w_s + c * D.ldw + r0;
+          put(gp, v[0]);
+          put(gp + D.ldw, v[1]);
+          put(gp + 8, v[2]);
+          put(gp + D.ldw + 8, v[3]);
+        } else if (8 * gq == L.kpad) {  // the constant-1 column: the bias gradient sits in column kpad only
+          if ((lane & 3) == 0) {
+            if (r0 < D.nout) put(s.g + D.b_s + r0, v[0]);
+            if (r1 < D.nout) put(s.g + D.b_s + r1, v[2]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int o = (e & 2) ? r1 : r0, cc = c + (e & 1);
+            if (o < D.nout) {
+              if (cc < D.nin) put(s.g + D.w_s + cc * D.ldw + o, v[e]);
+              else if (cc == L.kpad) put(s.g + D.b_s + o, v[e]);
+            }
+          }
+        }
+      }
+    }
+  };
+  int acc_tiles = 0;
+  bool dumped = false;
   const int d = M.d_in;
   for (long long t0 = 0; t0 < B; t0 += 64) {
     const int nvalid = (int)((B - t0) < 64 ? (B - t0) : 64);
@@ -565,7 +626,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           const uint32_t dwacc = R.tmem + (uint32_t)L.dw_col;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (lead) mma3(dwacc, ddhi, ddlo, dxhi, dxlo, idesc, (k || !first_tile) ? 1u : 0u);
+            if (lead) mma3(dwacc, ddhi, ddlo, dxhi, dxlo, idesc, (k || acc_tiles > 0) ? 1u : 0u);
             ddhi += 128;  // 2048 bytes
             ddlo += 128;
             dxhi += xstep;
@@ -640,59 +701,19 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
     }
     fence_before();
     __syncthreads();  // tile buffers, yh and the Z accumulator are free again
+    if (want_grad && ++acc_tiles == kAccTiles && t0 + 64 < B) {
+      if (dumped) dump(std::true_type{});
+      else dump(std::false_type{});
+      dumped = true;
+      acc_tiles = 0;
+      fence_before();
+      __syncthreads();
+    }
   }
 
   if (want_grad) {
-    // ---- dW accumulators (TMEM) -> s.g in the padded parameter layout ---------------------------------
-    fence_after();
-    for (int l = 0; l < nh; ++l) {
-      const TcLayer& L = T.L[l];
-      const LayerDev& D = M.L[l];
-      const int ngroups = L.ccols >> 3;
-      // 64 columns that lie fully inside the weight matrix: one 32-column fragment per column half
-      int g0 = 0;
-      if (D.nout == 64) {
-        for (; 8 * (g0 + 8) <= D.nin; g0 += 8) {
-          float v[16];
-          ld_16x256b_x4(zaddr + (uint32_t)(L.dw_col + 8 * (g0 + 4 * h)), v);
-          float* gp = s.g + D.w_s + (8 * (g0 + 4 * h) + 2 * (lane & 3)) * D.ldw + r0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            gp[0] = v[4 * j + 0];
-            gp[D.ldw] = v[4 * j + 1];
-            gp[8] = v[4 * j + 2];
-            gp[D.ldw + 8] = v[4 * j + 3];
-            gp += 8 * D.ldw;
-          }
-        }
-      }
-      for (int gq = g0 + h; gq < ngroups; gq += 2) {
-        float v[4];
-        ld_16x256b_x1(zaddr + (uint32_t)(L.dw_col + 8 * gq), v);
-        const int c = 8 * gq + 2 * (lane & 3);
-        if (8 * gq + 8 <= D.nin && D.nout == 64) {  // group fully inside the weight matrix: no bounds checks
-          float* gp = s.g + D.w_s + c * D.ldw + r0;
-          gp[0] = v[0];
-          gp[D.ldw] = v[1];
-          gp[8] = v[2];
-          gp[D.ldw + 8] = v[3];
-        } else if (8 * gq == L.kpad) {  // the constant-1 column: the bias gradient sits in column kpad only
-          if ((lane & 3) == 0) {
-            if (r0 < D.nout) s.g[D.b_s + r0] = v[0];
-            if (r1 < D.nout) s.g[D.b_s + r1] = v[2];
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int o = (e & 2) ? r1 : r0, cc = c + (e & 1);
-            if (o < D.nout) {
-              if (cc < D.nin) s.g[D.w_s + cc * D.ldw + o] = v[e];
-              else if (cc == L.kpad) s.g[D.b_s + o] = v[e];
-            }
-          }
-        }
-      }
-    }
+    if (dumped) dump(std::true_type{});
+    else dump(std::false_type{});
     const int hl = T.L[nh - 1].hout;
     for (int k = tid; k < hl; k += NT) s.g[LO.w_s + k * LO.ldw] = R.glast[k];
     if (tid == 0) s.g[LO.b_s] = R.glast[64];
