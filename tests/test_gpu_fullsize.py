@@ -121,3 +121,52 @@ def test_resume_equals_the_uninterrupted_run(bf, models):
     two = np.array(bf.mcmc(bnn, B, 16, s, continue_sampling=True, keep_every=8, seed=3), copy=True)
     assert one.shape == two.shape == (P, 2, CHAINS)
     assert np.array_equal(one, two)
+
+
+# ---- configs[2] and configs[3] at their full shapes: additivity of the gradient over data partitions -------------
+def _additivity(bf, bnn, parts, n, rtol=1e-4):
+    """On theta_net:  g(all data) = sum_k g(partition k) - (K - 1) g(network prior).  The network prior part comes
+    from the engine itself: g(k; nb) = nb * (likelihood + sigma prior)_k + prior (src/model/BNN.jl:50-56), hence
+    prior = 2 g(0; nb = 1) - g(0; nb = 2).  (The sigma prior sits inside the likelihood term and only touches
+    theta_like, which is left out of the comparison.)"""
+    P = bnn.num_total_params
+    theta = (0.05 * np.random.default_rng(9).standard_normal(P)).astype(np.float32)
+    v_full, g_full = bf.grad_loglikeprior(bnn, theta)
+    K = len(parts)
+    vs, gs = zip(*[bf.grad_loglikeprior(bnn, theta, idx=ix) for ix in parts])
+    v2, g2 = bf.grad_loglikeprior(bnn, theta, idx=parts[0], num_batches=2.0)
+    p_net = 2.0 * np.asarray(gs[0], np.float64) - np.asarray(g2, np.float64)
+    g_sum = np.sum(np.asarray(gs, np.float64), axis=0) - (K - 1) * p_net
+    err = np.linalg.norm((g_full - g_sum)[:-1]) / np.linalg.norm(g_sum[:-1])
+    assert err < rtol, err
+    assert np.isfinite(v_full) and np.all(np.isfinite(vs)) and np.isfinite(v2)
+
+
+@pytest.mark.parametrize("compute", ["fp32", "tc"])
+def test_cfg3_wide_mlp_gradient_is_additive_over_chunks(bf, compute):
+    """configs[2]: Dense(64,512,relu) x 3 + Dense(512,1), FeedforwardTDist + MixtureScalePrior, B = 8 192 per GPU:
+    the large-P (stream) regime accumulates weight gradients over 8 192-column chunks."""
+    rng = np.random.default_rng(12)
+    n = 16384
+    x = rng.standard_normal((64, n), dtype=np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    nc = bf.destruct(bf.Chain(bf.Dense(64, 512, bf.relu), bf.Dense(512, 512, bf.relu), bf.Dense(512, 512, bf.relu),
+                              bf.Dense(512, 1)))
+    bnn = bf.BNN(x, y, bf.FeedforwardTDist(nc, bf.Gamma(2.0, 0.5), 5.0), bf.MixtureScalePrior(nc, 1.0, 0.1, 0.5),
+                 compute=compute)
+    assert bf.model_regime(bnn) == "stream"
+    parts = [np.arange(0, 8192, dtype=np.int64), np.arange(8192, n, dtype=np.int64)]
+    _additivity(bf, bnn, parts, n)
+
+
+def test_cfg4_lstm_gradient_is_additive_over_partitions(bf):
+    """configs[3]: LSTM(4,64) + Dense(64,1), T = 50, SeqToOneNormal, n = 16 384 sequences (the full-data passes of
+    GGMC run exactly this loop over 1 024 tiles of 16 sequences)."""
+    rng = np.random.default_rng(13)
+    T, n = 50, 16384
+    x = (0.5 * rng.standard_normal((T, 4, n))).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    nc = bf.destruct(bf.Chain(bf.LSTM(4, 64), bf.Dense(64, 1)))
+    bnn = bf.BNN(x, y, bf.SeqToOneNormal(nc, bf.Gamma(2.0, 0.5)), bf.GaussianPrior(nc, 0.5))
+    parts = [np.arange(k * n // 4, (k + 1) * n // 4, dtype=np.int64) for k in range(4)]
+    _additivity(bf, bnn, parts, n)
