@@ -107,3 +107,35 @@ def test_chain_group_pipelining_is_bit_identical(bf, compute, kind, monkeypatch)
         assert np.array_equal(out[groups][0], ref)
         if kin is not None:
             assert np.array_equal(out[groups][1], kin)
+
+
+@pytest.mark.parametrize("kind", ["sgnhts_rms", "ggmc", "hmc"])
+def test_sharding_invariance_of_the_mh_and_thermostat_samplers(bf, kind):
+    """What two ranks run (640 chains as 320 + 320 with chain_offset) equals the one-sampler run bit for bit, also
+    for the samplers with per-chain uniforms (MH accept), adapters and thermostats; the one-sampler run goes through
+    the chain-group pipeline of bfx_mcmc_run."""
+    bnn, m, x, y = _bnn(bf, 400, "tc")
+    C = 640
+    th0 = np.asfortranarray((0.1 * np.random.default_rng(17).standard_normal((m.n_total, C))).astype(np.float32))
+
+    def mk():
+        if kind == "sgnhts_rms":
+            return bf.SGNHTS(1e-3, madapter=bf.RMSPropMassAdapter(5))
+        if kind == "ggmc":
+            return bf.GGMC(l=1e-3, steps=2, sadapter=bf.DualAveragingStepSize(1e-3, adapt_steps=4),
+                           madapter=bf.DiagCovMassAdapter(6, 3))
+        return bf.HMC(1e-3, 3, sadapter=bf.DualAveragingStepSize(1e-3, adapt_steps=3), madapter=bf.DiagCovMassAdapter(6, 3))
+
+    s = mk()
+    whole = np.array(bf.mcmc(bnn, 64, 8, s, theta_start=th0, seed=21), copy=True)
+    acc = None if s.accepted is None else np.array(s.accepted, copy=True)
+    parts, accs = [], []
+    for o in (0, 320):
+        sp = mk()
+        parts.append(np.array(bf.mcmc(bnn, 64, 8, sp, theta_start=np.asfortranarray(th0[:, o:o + 320]), seed=21,
+                                      chain_offset=o), copy=True))
+        accs.append(sp.accepted)
+    assert np.isfinite(whole).all()
+    assert np.array_equal(np.concatenate(parts, axis=2), whole)
+    if acc is not None:
+        assert np.array_equal(np.concatenate(accs, axis=1), acc)
