@@ -262,6 +262,10 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   const TcDesc& T = M.tc;
   const int nh = T.nh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // warp index / TMEM base broadcast from lane 0: tells the compiler they are warp-uniform, so the MMA-issue code
+  // (descriptor arithmetic included) runs on the uniform datapath instead of per-thread registers + R2UR moves
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, R.tmem, 0);
   const int q = warp & 3, h = warp >> 2;
   const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8;  // the two batch rows of this thread's fragment
   const uint32_t zaddr = R.tmem + ((uint32_t)(32 * q) << 16);
@@ -404,9 +408,10 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
     for (int l = 0; l < nh; ++l) {
       const TcLayer& L = T.L[l];
       const LayerDev& D = M.L[l];
-      if (warp == 0) {
+      if (warp_u == 0) {
         fence_after();
         const bool lead = elect_one();
+        const TcLayer& L = T.L[__shfl_sync(0xffffffffu, l, 0)];  // (uniform layer index: see warp_u)
         const uint32_t a_sbo = (L.ccols >> 3) * 128, b_lbo = (L.hout >> 3) * 128;
         const uint32_t ahi = smem_u32(R.base + L.a_off), bhi = smem_u32(R.base + L.w_off);
         const uint32_t idesc = make_idesc(L.hout, 0, 1);
@@ -418,7 +423,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         const uint64_t astep = 256 >> 4, bstep = (2 * b_lbo) >> 4;
         const int nk = L.kpad >> 4;
         for (int k = 0; k < nk; ++k) {
-          if (lead) mma3(R.tmem, dahi, dalo, dbhi, dblo, idesc, k ? 1u : 0u);
+          if (lead) mma3(tmem_u, dahi, dalo, dbhi, dblo, idesc, k ? 1u : 0u);
           dahi += astep;
           dalo += astep;
           dbhi += bstep;
@@ -427,6 +432,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         if (lead) commit(&R.bar[0]);
         __syncwarp();
       }
+      BFX_TICK(16);  // (forward MMA issue, warp 0)
       mbar_wait(&R.bar[0], R.par[0]);
       R.par[0] ^= 1;
       fence_after();
@@ -594,11 +600,14 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         R.glast[tid] += (R.gpart[tid] + R.gpart[65 + tid]) + (R.gpart[130 + tid] + R.gpart[195 + tid]);
       BFX_TICK(5);  // output layer + likelihood + delta tile
       // ---- backward ------------------------------------------------------------------------------
-      for (int l = nh - 1; l >= 0; --l) {
+      for (int lv = nh - 1; lv >= 0; --lv) {
+        const int l = lv;
         const TcLayer& L = T.L[l];
-        if (warp == 0) {
+        if (warp_u == 0) {
           fence_after();
           const bool lead = elect_one();
+          const int l = __shfl_sync(0xffffffffu, lv, 0);  // (uniform layer index: see warp_u)
+          const TcLayer& L = T.L[l];
           const uint32_t dhi = smem_u32(R.base + T.d_off), whi = smem_u32(R.base + L.w_off);
           const uint32_t xhi = smem_u32(R.base + L.a_off);
           if (l > 0) {
@@ -609,7 +618,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
             uint64_t dwhi = make_desc(whi, 128, w_sbo), dwlo = make_desc(whi + L.w_bytes, 128, w_sbo);
             const int nk = L.hout >> 4;
             for (int k = 0; k < nk; ++k) {
-              if (lead) mma3(R.tmem, ddhi, ddlo, dwhi, dwlo, idesc, k ? 1u : 0u);
+              if (lead) mma3(tmem_u, ddhi, ddlo, dwhi, dwlo, idesc, k ? 1u : 0u);
               ddhi += 16;  // 256 bytes
               ddlo += 16;
               dwhi += 16;
@@ -623,7 +632,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           uint64_t ddhi = make_desc(dhi, 1024, 128), ddlo = make_desc(dhi + T.d_bytes, 1024, 128);
           uint64_t dxhi = make_desc(xhi, x_lbo, 128), dxlo = make_desc(xhi + L.a_bytes, x_lbo, 128);
           const uint64_t xstep = (2 * x_lbo) >> 4;
-          const uint32_t dwacc = R.tmem + (uint32_t)L.dw_col;
+          const uint32_t dwacc = tmem_u + (uint32_t)L.dw_col;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (lead) mma3(dwacc, ddhi, ddlo, dxhi, dxlo, idesc, (k || acc_tiles > 0) ? 1u : 0u);
@@ -635,6 +644,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           if (lead) commit(&R.bar[2]);
           __syncwarp();
         }
+        BFX_TICK(17);  // (backward MMA issue, warp 0)
         if (l > 0) {
           mbar_wait(&R.bar[1], R.par[1]);
           R.par[1] ^= 1;

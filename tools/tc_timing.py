@@ -15,7 +15,8 @@ import numpy as np
 NAMES = ["step prologue (batch keys, dispatch)", "stage: indices + copy issue", "pack weights + copy wait", "fwd MMA issue+wait",
          "hidden epilogue", "output layer+like+delta", "bwd dA MMA wait", "bwd epilogue", "last dW wait",
          "gradient dump", "eval_finish", "sampler update pass", "chunk store+hand-over", "chunk fetch+load",
-         "  (update: setup before the pass)", "  (update: thread 0's own pass)"]
+         "  (update: setup before the pass)", "  (update: thread 0's own pass)",
+         "  (forward MMA issue by warp 0)", "  (backward MMA issue by warp 0)"]
 
 
 def main():
