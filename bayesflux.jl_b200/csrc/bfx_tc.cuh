@@ -422,14 +422,16 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         uint64_t dbhi = make_desc(bhi, b_lbo, 128), dblo = make_desc(bhi + L.w_bytes, b_lbo, 128);
         const uint64_t astep = 256 >> 4, bstep = (2 * b_lbo) >> 4;
         const int nk = L.kpad >> 4;
-        for (int k = 0; k < nk; ++k) {
-          if (lead) mma3(tmem_u, dahi, dalo, dbhi, dblo, idesc, k ? 1u : 0u);
-          dahi += astep;
-          dalo += astep;
-          dbhi += bstep;
-          dblo += bstep;
+        if (lead) {  // (the whole loop under the predicate: one branch, MMAs back to back)
+          for (int k = 0; k < nk; ++k) {
+            mma3(tmem_u, dahi, dalo, dbhi, dblo, idesc, k ? 1u : 0u);
+            dahi += astep;
+            dalo += astep;
+            dbhi += bstep;
+            dblo += bstep;
+          }
+          commit(&R.bar[0]);
         }
-        if (lead) commit(&R.bar[0]);
         __syncwarp();
       }
       BFX_TICK(16);  // (forward MMA issue, warp 0)
@@ -617,14 +619,16 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
             uint64_t ddhi = make_desc(dhi, 128, 1024), ddlo = make_desc(dhi + T.d_bytes, 128, 1024);
             uint64_t dwhi = make_desc(whi, 128, w_sbo), dwlo = make_desc(whi + L.w_bytes, 128, w_sbo);
             const int nk = L.hout >> 4;
-            for (int k = 0; k < nk; ++k) {
-              if (lead) mma3(tmem_u, ddhi, ddlo, dwhi, dwlo, idesc, k ? 1u : 0u);
-              ddhi += 16;  // 256 bytes
-              ddlo += 16;
-              dwhi += 16;
-              dwlo += 16;
+            if (lead) {  // (the whole loop under the predicate: one branch, MMAs back to back)
+              for (int k = 0; k < nk; ++k) {
+                mma3(tmem_u, ddhi, ddlo, dwhi, dwlo, idesc, k ? 1u : 0u);
+                ddhi += 16;  // 256 bytes
+                ddlo += 16;
+                dwhi += 16;
+                dwlo += 16;
+              }
+              commit(&R.bar[1]);
             }
-            if (lead) commit(&R.bar[1]);
           }
           // dW[o][c] += sum_b D[b][o] Ain[b][c]:  A = D tile MN-major (M = fan-out), B = Ain tile MN-major, K = batch
           const uint32_t x_lbo = (L.ccols >> 3) * 128;
@@ -633,15 +637,17 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           uint64_t dxhi = make_desc(xhi, x_lbo, 128), dxlo = make_desc(xhi + L.a_bytes, x_lbo, 128);
           const uint64_t xstep = (2 * x_lbo) >> 4;
           const uint32_t dwacc = tmem_u + (uint32_t)L.dw_col;
+          if (lead) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (lead) mma3(dwacc, ddhi, ddlo, dxhi, dxlo, idesc, (k || acc_tiles > 0) ? 1u : 0u);
-            ddhi += 128;  // 2048 bytes
-            ddlo += 128;
-            dxhi += xstep;
-            dxlo += xstep;
+            for (int k = 0; k < 4; ++k) {
+              mma3(dwacc, ddhi, ddlo, dxhi, dxlo, idesc, (k || acc_tiles > 0) ? 1u : 0u);
+              ddhi += 128;  // 2048 bytes
+              ddlo += 128;
+              dxhi += xstep;
+              dxlo += xstep;
+            }
+            commit(&R.bar[2]);
           }
-          if (lead) commit(&R.bar[2]);
           __syncwarp();
         }
         BFX_TICK(17);  // (backward MMA issue, warp 0)
