@@ -111,7 +111,10 @@ BFX_DEV ChainScalars load_scalars(const ChainScalars* p) {
 // of one chain run in order (the per-chain counter work[1 + c] is the hand-over), so a launch is balanced over
 // the SMs for any number of chains instead of running ceil(C / resident CTAs) full waves.
 template <int NT, int BT, int KIND, bool TC>
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1)) k_mcmc(const __grid_constant__ RunDev R) {
+// (at least 512 resident threads per SM for every launch shape = a 128-register cap, and 24 one-warp CTAs = an
+// 80-register cap for the 32-thread shape: without it the small shapes took 200+ registers and ran 10 CTAs per SM;
+// cfg1 127 M -> 200 M grad-evals/s)
+__global__ void __launch_bounds__(NT, (NT == 32 ? 24 : 512 / NT)) k_mcmc(const __grid_constant__ RunDev R) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_item;
   const ModelDev& M = R.M;
