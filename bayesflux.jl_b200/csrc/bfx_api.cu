@@ -326,7 +326,7 @@ static int32_t build_tc(bfx_model* m) {
   T.d_off = off;
   off += 2 * T.d_bytes;
   T.misc_off = off;
-  off += 2304;  // yh[128], glast[72], 4 barriers, tmem slot, gpart[4][65]
+  off += 2304 + 128 * T.nh;  // yh[128], glast[72], 4 barriers, tmem slot, gpart[4][65]; then one IssueDesc per layer
   T.total_bytes = off;
   int cols = 32;
   while (cols < col) cols <<= 1;

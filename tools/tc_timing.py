@@ -16,7 +16,8 @@ NAMES = ["step prologue (batch keys, dispatch)", "stage: indices + copy issue", 
          "hidden epilogue", "output layer+like+delta", "bwd dA MMA wait", "bwd epilogue", "last dW wait",
          "gradient dump", "eval_finish", "sampler update pass", "chunk store+hand-over", "chunk fetch+load",
          "  (update: setup before the pass)", "  (update: thread 0's own pass)",
-         "  (forward MMA issue by warp 0)", "  (backward MMA issue by warp 0)"]
+         "  (forward MMA issue by warp 0)", "  (backward MMA issue by warp 0)",
+         "  (forward issue block entry: fence, elect, descriptors)"]
 
 
 def main():
