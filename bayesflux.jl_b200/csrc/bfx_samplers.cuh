@@ -38,6 +38,12 @@ struct Ctx {
     else return chain_eval<NT, BT>(R.M, s, R.x, R.y, b, Bn, nbs, want_grad, gn2);
   }
   BFX_DEV double grad(float& gn2) { return eval(bs, Bk, R.num_batches, true, gn2); }
+  // tensor-core builds: the gradient with a shadow job (tc::chain_eval_tc)
+  template <class Shadow>
+  BFX_DEV double grad_shadow(float& gn2, Shadow job) {
+    static_assert(TC, "shadow jobs exist on the tensor-core path only");
+    return tc::chain_eval_tc<NT>(R.M, s, *tcr, R.x, R.xs, R.y, bs, Bk, R.num_batches, true, gn2, job);
+  }
   // loglikeprior(bnn, θ, bnn.x, bnn.y): full data, num_batches = 1 (ggmc.jl:147,176; hmc.jl:135-136)
   BFX_DEV double full_lp() {
     BatchSrc f = bs;
@@ -228,17 +234,38 @@ template <int NT, int BT, bool TC>
 BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
   const SamplerDev& S = X.R.S;
   // sgld.jl:12  a (b + t)^(-gamma): exp2(-gamma log2(b + t)) with the full-precision log2f / exp2f, within 2e-6
-  // relative of powf for t < 2^24 and a third of its instructions on the serial path of every step
-  float alpha = S.stepsize_a * exp2f(-S.stepsize_gamma * log2f(S.stepsize_b + (float)X.sc.t));
-  alpha = fmaxf(alpha, S.min_stepsize);
-  float gn2;
-  X.grad(gn2);
+  // relative of powf for t < 2^24 and a third of its instructions
+  auto stepsize = [&]() {
+    return fmaxf(S.stepsize_a * exp2f(-S.stepsize_gamma * log2f(S.stepsize_b + (float)X.sc.t)), S.min_stepsize);
+  };
+  float gn2, alpha;
+  Recorder rec;  // samples[:, t] = θ, written by the update pass itself
+  if constexpr (TC) {
+    // step size and sample slot do not depend on the gradient: warp 1 works them out while warp 0 issues the first
+    // MMAs, everybody picks them up from shared memory afterwards
+    float* sh = X.tcr->shadow;
+    X.grad_shadow(gn2, [&]() {
+      const float a = stepsize();
+      const Recorder r = make_recorder(X, X.sc.t);
+      if ((threadIdx.x & 31) == 0) {
+        sh[0] = a;
+        *reinterpret_cast<float**>(sh + 2) = r.dst;
+        *reinterpret_cast<float**>(sh + 4) = r.rdst;
+      }
+    });
+    alpha = sh[0];
+    rec.dst = *reinterpret_cast<float* const*>(sh + 2);
+    rec.rdst = *reinterpret_cast<float* const*>(sh + 4);
+  } else {
+    alpha = stepsize();
+    X.grad(gn2);
+    rec = make_recorder(X, X.sc.t);
+  }
   const float ha = 0.5f * alpha * clip_scale(gn2, S.maxnorm), sa = sqrtf(alpha);
   float* th = X.s.th;
   const float* g = X.s.g;
   const float* inj = X.inj(0);
   X.sc.nsampled += 1;
-  const Recorder rec = make_recorder(X, X.sc.t);  // samples[:, t] = θ, written by the update pass itself
   BFX_TICK(14);
   for_each_quad<NT>(X.R.M, [&](int k) {
     const unsigned m = X.s.mask[k >> 2];

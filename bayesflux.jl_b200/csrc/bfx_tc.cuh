@@ -160,6 +160,7 @@ static_assert(sizeof(IssueDesc) == 128, "one IssueDesc = 128 bytes of the misc a
 struct Region {
   unsigned char* base;  // 128-byte aligned tensor-core region
   const IssueDesc* idesc;  // [nh]
+  float* shadow;           // [8] results of the caller's shadow job (see chain_eval_tc)
   uint32_t tmem;        // TMEM base address (lane 0, column 0)
   float* yh;            // [2][64] partial network outputs of the two column halves
   float* glast;         // [72]    gradient of the output layer (weights, then bias at [64])
@@ -179,6 +180,7 @@ BFX_DEV Region region_of(const ModelDev& M, const ChainSmem& s) {
   R.tmem_slot = reinterpret_cast<uint32_t*>(f + 208);
   R.gpart = f + 256;
   R.idesc = reinterpret_cast<const IssueDesc*>(s.tc + M.tc.misc_off + 2304);
+  R.shadow = f + 520;
   R.tmem = 0;
   R.par[0] = R.par[1] = R.par[2] = 0;
   return R;
@@ -301,10 +303,16 @@ BFX_DEV void mma3(uint32_t d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t
 // ---------------------------------------------------------------------------------------------
 // value / gradient over a minibatch (loop over 64-row tiles).  NT must be 256.
 // ---------------------------------------------------------------------------------------------
-template <int NT>
+// `shadow`: a functor run once per evaluation by warp 1 while warp 0 issues the first MMAs (warps 1-7 only wait
+// there): the caller's scalar bookkeeping that does not depend on the gradient (step size, sample slot) leaves the
+// serial path this way; results travel through Region::shadow (shared memory, visible after the next barrier).
+struct NoShadow {
+  BFX_DEV void operator()() const {}
+};
+template <int NT, class Shadow = NoShadow>
 BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, const float* __restrict__ x,
                              const uint4* __restrict__ xs, const float* __restrict__ y, const BatchSrc& bs, long long B,
-                             float nb, bool want_grad, float& gn2) {
+                             float nb, bool want_grad, float& gn2, Shadow shadow = Shadow{}) {
   static_assert(NT == 256, "the tensor-core path uses 8 warps: 4 lane quadrants x 2 column halves");
   const TcDesc& T = M.tc;
   const int nh = T.nh;
@@ -477,6 +485,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         __syncwarp();
       }
       BFX_TICK(16);  // (forward MMA issue, warp 0)
+      if (warp_u == 1 && first_tile && l == 0) shadow();
       mbar_wait(&R.bar[0], R.par[0]);
       R.par[0] ^= 1;
       fence_after();
