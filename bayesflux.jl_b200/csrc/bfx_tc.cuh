@@ -59,12 +59,22 @@ BFX_DEV void mbar_init(uint64_t* bar, uint32_t count) {
 }
 BFX_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#ifdef BFX_WATCHDOG  // bring-up builds (tools/gemm_probe.cu): a barrier that never completes traps instead of hanging the GPU
+  const long long t0 = clock64();
+#endif
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#ifdef BFX_WATCHDOG
+    if (!ok && clock64() - t0 > 4000000000LL) {
+      printf("mbar_wait watchdog: block (%d,%d,%d) thread %d bar %x parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+#endif
   } while (!ok);
 }
 BFX_DEV void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -1,0 +1,417 @@
+// tcgen05 GEMM of the large-P ("stream") regime, second generation: C[M x N] = A * B with every operand stored in
+// HBM as two BF16 arrays (hi, lo = the 3-term split of the FP32 value, see bfx_tc.cuh), column-major.
+//
+//   * a CTA PAIR (cluster 2 x 1 x 1, tcgen05 cta_group::2) owns a 256 x 256 output tile: each CTA holds 128 rows of A
+//     and 128 of the 256 rows of B in its own shared memory, the leader CTA issues M = 256, N = 256, K = 16 MMAs that
+//     read both CTAs' operands, every CTA keeps its 128 x 256 FP32 accumulator in its own TMEM (256 columns);
+//   * operands arrive by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 3-stage ring of 64 KB per CTA
+//     (K = 64 per stage: A hi, A lo, B hi, B lo), producer = one lane of warp 0, full / empty mbarriers, the empty
+//     barriers are released by tcgen05.commit (multicast to both CTAs);
+//   * one lane of warp 1 of the leader issues hi*hi + hi*lo + lo*hi per k-step into the same accumulator;
+//   * all eight warps run the epilogue from tcgen05.ld.32x32b (thread = accumulator row): bias + activation with
+//     BF16 hi / lo stores, the act' multiply with the bias-gradient row sums, or the split-K partial store.
+//
+// Both operand majornesses are read straight from the natural column-major arrays (K-major: box 64 k x 128 rows;
+// MN-major: two boxes of 64 rows x 64 k), so the three GEMMs of a Dense layer (forward, input gradient, weight
+// gradient) need no transposed copies.  The single-CTA variant (CG = 1, 128 x 256 tile, 2 stages of 96 KB) is kept
+// for bring-up and for devices that cannot co-schedule the pair.
+//
+// Reference arithmetic replaced: Flux Dense forward (called at src/likelihoods/feedforward.jl:35,91) and its
+// Zygote pullbacks (src/model/BNN.jl:66) for layers wide enough to be real GEMMs (configs[2]: 512 x 512 x 8192).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "bfx_tc.cuh"
+
+namespace bfx {
+namespace tcg {
+
+constexpr int BM = 128;   // accumulator rows per CTA
+constexpr int BN = 256;   // accumulator columns
+constexpr int BK = 64;    // K per stage = one 128-byte swizzle span of BF16
+constexpr int TILE_A = BM * BK * 2;  // one half (hi or lo) of the A stage, 16 KB
+
+template <int CG>
+struct Cfg {
+  static constexpr int BROWS = BN / CG;               // rows of B staged by one CTA
+  static constexpr int TILE_B = BROWS * BK * 2;
+  static constexpr int STAGE = 2 * TILE_A + 2 * TILE_B;
+  static constexpr int STAGES = CG == 2 ? 3 : 2;
+  static constexpr int SMEM = STAGES * STAGE + 1024;  // + slack for the 1024-byte alignment of the swizzle atoms
+};
+
+enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1, EPI_PLAIN = 2 };
+
+struct Args {
+  int M, N, K;
+  float* C;              // FP32 output or nullptr.  EPI_PLAIN: the split-K partial / accumulate target
+  __nv_bfloat16* Chi;    // BF16 halves of the output (nullptr: not written)
+  __nv_bfloat16* Clo;
+  long long ldc;
+  const float* bias;     // EPI_BIAS_ACT
+  int act;
+  const __nv_bfloat16* aux_hi;  // EPI_MUL_DACT: multiply by act'(aux[m + ldaux * n]), aux = hi + lo
+  const __nv_bfloat16* aux_lo;
+  long long ldaux;
+  float* rowpart;        // EPI_MUL_DACT: per-row sums of the stored tile, slot (2 * blockIdx.y + half) * M + m
+  int accumulate;        // EPI_PLAIN, single split: C += acc
+  int kchunk;            // split-K: blockIdx.z handles k in [z * kchunk, ...), multiple of BK; writes C + z * part_stride
+  long long part_stride;
+};
+
+BFX_DEV uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+BFX_DEV void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+BFX_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load, completion on `bar` (for CG = 2 the barrier of the pair's leader CTA)
+template <int CG>
+BFX_DEV void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  const uint32_t d = tc::smem_u32(dst);
+  if (CG == 2) {
+    const uint32_t b = tc::smem_u32(bar) & 0xFEFFFFFFu;  // peer bit cleared: the transaction bytes land on CTA 0's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(d), "l"(map), "r"(b), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    const uint32_t b = tc::smem_u32(bar);
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(d), "l"(map), "r"(b), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+// shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), descriptor version 1
+BFX_DEV uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+template <int CG>
+BFX_DEV void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if (CG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+// all MMAs issued so far by this thread arrive on `bar` when they complete (CG = 2: on both CTAs' copies of it)
+template <int CG>
+BFX_DEV void mma_commit(uint64_t* bar) {
+  if (CG == 2) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            tc::smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(bar))
+                 : "memory");
+  }
+}
+template <int CG>
+BFX_DEV void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  if (CG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+BFX_DEV void tmem_free(uint32_t addr, uint32_t cols) {
+  if (CG == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// 32 consecutive accumulator columns of this thread's row
+BFX_DEV void ld_row32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// D = F32, A = B = BF16, M = 128 * CG, N = 256
+template <int CG>
+BFX_DEV uint32_t idesc_of(int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+}
+
+// stage `rows` rows (mn) x 64 k of one operand half at `dst`
+template <int CG, bool MN_MAJOR>
+BFX_DEV void load_operand(unsigned char* dst, const CUtensorMap* map, uint64_t* bar, int mn0, int k0, int rows) {
+  if (!MN_MAJOR) {
+    tma_load_2d<CG>(dst, map, bar, k0, mn0);  // box {64 k, rows}: row r at r * 128 bytes, 16-byte chunks XOR (r % 8)
+  } else {
+    for (int j = 0; j < rows / 64; ++j)  // boxes {64 mn, 64 k}: k-row r at r * 128 bytes inside its 8 KB box
+      tma_load_2d<CG>(dst + j * 8192, map, bar, mn0 + 64 * j, k0);
+  }
+}
+
+template <int CG, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(256, 1)
+k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+           const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo, const Args g) {
+  using C = Cfg<CG>;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[C::STAGES], bar_empty[C::STAGES], bar_acc;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int mtile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int m0 = mtile * (BM * CG) + (int)rank * BM;         // first accumulator row of this CTA
+  const int n0 = (int)blockIdx.y * BN;                        // first accumulator column
+  const int nb0 = n0 + (int)rank * C::BROWS;                  // first B row staged by this CTA
+  const int kbeg = (int)blockIdx.z * g.kchunk;
+  int kend = kbeg + g.kchunk;
+  if (kend > g.K) kend = g.K;
+  const int nkb = (kend - kbeg + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      tc::mbar_init(&bar_full[s], 1);
+      tc::mbar_init(&bar_empty[s], 1);
+    }
+    tc::mbar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mAhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mAlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mBhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mBlo) : "memory");
+  }
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // barrier inits visible (to the peer) before anything arrives
+  if (warp == 2) tmem_alloc<CG>(&tmem_slot, (uint32_t)BN);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (tc::elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (uint32_t)(kb / C::STAGES) & 1u;
+        tc::mbar_wait(&bar_empty[s], ph ^ 1u);
+        if (rank == 0) mbar_expect_tx(&bar_full[s], (uint32_t)(C::STAGE * CG));
+        unsigned char* st = smem + s * C::STAGE;
+        const int k0 = kbeg + kb * BK;
+        load_operand<CG, A_MN>(st, &mAhi, &bar_full[s], m0, k0, BM);
+        load_operand<CG, A_MN>(st + TILE_A, &mAlo, &bar_full[s], m0, k0, BM);
+        load_operand<CG, B_MN>(st + 2 * TILE_A, &mBhi, &bar_full[s], nb0, k0, C::BROWS);
+        load_operand<CG, B_MN>(st + 2 * TILE_A + C::TILE_B, &mBlo, &bar_full[s], nb0, k0, C::BROWS);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && rank == 0) {
+    // ---------------- MMA issuer (leader CTA) ----------------
+    const uint32_t idesc = idesc_of<CG>(A_MN ? 1 : 0, B_MN ? 1 : 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % C::STAGES;
+      const uint32_t ph = (uint32_t)(kb / C::STAGES) & 1u;
+      tc::mbar_wait(&bar_full[s], ph);
+      tc::fence_after();
+      if (tc::elect_one()) {
+        const uint32_t ahi = tc::smem_u32(smem + s * C::STAGE), alo = ahi + TILE_A;
+        const uint32_t bhi = ahi + 2 * TILE_A, blo = bhi + C::TILE_B;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          // K-major: 16 k = 32 bytes inside the 128-byte row, 8-row groups 1024 bytes apart (SBO), LBO unused
+          // MN-major: 16 k = two 8-row groups of 1024 bytes (SBO), 64-row (mn) groups 8192 bytes apart (LBO)
+          const uint64_t dah = A_MN ? desc_sw128(ahi + ks * 2048, 8192, 1024) : desc_sw128(ahi + ks * 32, 16, 1024);
+          const uint64_t dal = A_MN ? desc_sw128(alo + ks * 2048, 8192, 1024) : desc_sw128(alo + ks * 32, 16, 1024);
+          const uint64_t dbh = B_MN ? desc_sw128(bhi + ks * 2048, 8192, 1024) : desc_sw128(bhi + ks * 32, 16, 1024);
+          const uint64_t dbl = B_MN ? desc_sw128(blo + ks * 2048, 8192, 1024) : desc_sw128(blo + ks * 32, 16, 1024);
+          mma_bf16<CG>(tmem, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
+          mma_bf16<CG>(tmem, dah, dbl, idesc, 1u);
+          mma_bf16<CG>(tmem, dal, dbh, idesc, 1u);
+        }
+        mma_commit<CG>(&bar_empty[s]);               // stage s may be refilled once these MMAs have read it
+        if (kb == nkb - 1) mma_commit<CG>(&bar_acc); // accumulator complete
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---------------- epilogue: thread = accumulator row (lane quadrant of the warp), 128 columns per warp half ------
+  if (nkb >= 1) {
+    tc::mbar_wait(&bar_acc, 0u);
+    tc::fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const long long m = (long long)m0 + 32 * q + lane;
+    float* Cp = g.C ? g.C + (long long)blockIdx.z * g.part_stride : nullptr;
+    float bias = 0.f;
+    if (EPI == EPI_BIAS_ACT && m < g.M) bias = __ldg(g.bias + m);
+    float rsum = 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+      float v[32];
+      const int c0 = 128 * half + 32 * cb;
+      ld_row32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+      const long long nb = (long long)n0 + c0;
+      if (m < g.M && nb < g.N) {
+        const int ncols = (int)((g.N - nb) < 32 ? (g.N - nb) : 32);
+        if (EPI == EPI_MUL_DACT) {
+          const __nv_bfloat16* ah = g.aux_hi + m + g.ldaux * nb;
+          const __nv_bfloat16* al = g.aux_lo + m + g.ldaux * nb;
+          float a[32];
+          if (g.act == A_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = j < ncols ? __bfloat162float(ah[(long long)j * g.ldaux]) : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              a[j] = j < ncols ? __bfloat162float(ah[(long long)j * g.ldaux]) + __bfloat162float(al[(long long)j * g.ldaux]) : 0.f;
+          }
+          tc::with_act(g.act, [&](auto A) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = j < ncols ? v[j] * decltype(A)::d(a[j]) : 0.f;
+          });
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rsum += v[j];
+        } else if (EPI == EPI_BIAS_ACT) {
+          tc::with_act(g.act, [&](auto A) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = decltype(A)::f(v[j] + bias);
+          });
+        } else if (g.accumulate) {
+          const float* cp = Cp + m + g.ldc * nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += j < ncols ? cp[(long long)j * g.ldc] : 0.f;
+        }
+        if (Cp) {
+          float* cp = Cp + m + g.ldc * nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) cp[(long long)j * g.ldc] = v[j];
+        }
+        if (EPI != EPI_PLAIN && g.Chi) {
+          __nv_bfloat16* hp = g.Chi + m + g.ldc * nb;
+          __nv_bfloat16* lp = g.Clo + m + g.ldc * nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+              hp[(long long)j * g.ldc] = h;
+              lp[(long long)j * g.ldc] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+            }
+          }
+        }
+      }
+    }
+    if (EPI == EPI_MUL_DACT && g.rowpart && m < g.M) g.rowpart[(long long)(2 * blockIdx.y + half) * g.M + m] = rsum;
+  }
+  tc::fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_free<CG>(tmem, (uint32_t)BN);
+}
+
+// ---------------- host side ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// one operand half: element (mn, k) at base[mn * ld + k] (K-major) or base[k * ld + mn] (MN-major), extents MN x K
+inline cudaError_t make_map(CUtensorMap* map, const __nv_bfloat16* base, bool mn_major, long long MN, long long K, long long ld,
+                            int rows_per_box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  cuuint64_t dims[2], strides[1];
+  cuuint32_t box[2], estr[2] = {1, 1};
+  if (!mn_major) {
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)MN;
+    box[0] = BK; box[1] = (cuuint32_t)rows_per_box;
+  } else {
+    dims[0] = (cuuint64_t)MN; dims[1] = (cuuint64_t)K;
+    box[0] = 64; box[1] = BK;
+  }
+  strides[0] = (cuuint64_t)ld * 2;
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+struct Operand {
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;
+  long long ld;
+};
+
+template <int CG, bool A_MN, bool B_MN, int EPI>
+inline cudaError_t launch(const Args& g, const Operand& A, const Operand& B, int ksplit, cudaStream_t st) {
+  using C = Cfg<CG>;
+  CUtensorMap mAhi, mAlo, mBhi, mBlo;
+  cudaError_t e;
+  if ((e = make_map(&mAhi, A.hi, A_MN, g.M, g.K, A.ld, BM)) != cudaSuccess) return e;
+  if ((e = make_map(&mAlo, A.lo, A_MN, g.M, g.K, A.ld, BM)) != cudaSuccess) return e;
+  if ((e = make_map(&mBhi, B.hi, B_MN, g.N, g.K, B.ld, C::BROWS)) != cudaSuccess) return e;
+  if ((e = make_map(&mBlo, B.lo, B_MN, g.N, g.K, B.ld, C::BROWS)) != cudaSuccess) return e;
+  auto kern = k_tc_gemm2<CG, A_MN, B_MN, EPI>;
+  static bool attr_set = false;  // per template instance
+  if (!attr_set) {
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)) != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  const int mt = (g.M + BM * CG - 1) / (BM * CG);
+  cfg.gridDim = dim3((unsigned)(mt * CG), (unsigned)((g.N + BN - 1) / BN), (unsigned)ksplit);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, mAhi, mAlo, mBhi, mBlo, g);
+}
+
+}  // namespace tcg
+}  // namespace bfx
