@@ -23,7 +23,6 @@ CUDA engine; nothing here falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
-import sys
 import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
@@ -716,27 +715,14 @@ def _run_desc(batchsize, numsamples, shuffle, partial, continue_sampling, keep_e
                      L.BATCH_SHARED if batch_mode == "shared" else L.BATCH_PER_CHAIN, 0, seed, chain_offset)
 
 
-def _result_buffer(sampler, shape):
-    """Host array for the samples of one mcmc call.  A fresh 20 MB array costs milliseconds of page faults when the
-    device-to-host copy first touches it, so arrays handed out earlier are recycled once nobody but this pool
-    references them any more (a caller that keeps a result, or a view of it, keeps it untouched)."""
-    pool = sampler.__dict__.setdefault("_result_pool", [])
-    for a in pool:
-        # references: the pool list, the loop variable, getrefcount's argument
-        if a.shape == shape and sys.getrefcount(a) == 3:
-            return a
-    a = np.empty(shape, np.float32, order="F")
-    pool.append(a)
-    del pool[:-3]
-    return a
-
-
 def mcmc(bnn: BNN, batchsize: int, numsamples: int, sampler: MCMCState, shuffle=True, partial=True,
          showprogress=False, continue_sampling=False, theta_start=None, nchains: Optional[int] = None,
-         keep_every: int = 1, seed: int = 0, batch_mode: str = "per_chain", chain_offset: int = 0):
+         keep_every: int = 1, seed: int = 0, batch_mode: str = "per_chain", chain_offset: int = 0, out=None):
     """mcmc(bnn, batchsize, numsamples, sampler; shuffle, partial, continue_sampling, θstart)
     src/inference/mcmc/abstract.jl:74-127, run entirely on the device.  Engine extensions:
-    nchains (θstart may be P x C), keep_every, seed, batch_mode.  Returns sampler.samples."""
+    nchains (θstart may be P x C), keep_every, seed, batch_mode, and ``out``: a caller-owned Fortran-ordered
+    float32 array of shape (P, nkept, nchains) that receives the new samples instead of a fresh allocation
+    (repeated calls then pay no page faults under the device-to-host copy).  Returns sampler.samples."""
     if continue_sampling:
         if sampler._h is None or sampler.samples is None:
             raise ValueError("continue_sampling needs a sampler that has already sampled")
@@ -761,7 +747,13 @@ def mcmc(bnn: BNN, batchsize: int, numsamples: int, sampler: MCMCState, shuffle=
     L.check(L.lib.bfx_mcmc_num_kept(sampler._h, C.byref(run), C.byref(nnew), C.byref(nkept)))
     nnew, nkept = nnew.value, nkept.value
     P = bnn.num_total_params
-    new = _result_buffer(sampler, (P, nkept, nchains))
+    if out is not None:
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.f_contiguous
+                and out.shape == (P, nkept, nchains)):
+            raise ValueError(f"out must be a Fortran-ordered float32 array of shape {(P, nkept, nchains)}")
+        new = out
+    else:
+        new = np.empty((P, nkept, nchains), np.float32, order="F")
     kin = np.zeros((nnew, nchains), np.float32, order="F") if sampler.kind in (L.SGNHT, L.SGNHTS) else None
     acc = np.zeros((nnew, nchains), np.int32, order="F") if sampler.kind in (L.GGMC, L.HMC) else None
     code = L.lib.bfx_mcmc_run(sampler._h, C.byref(run), _ptr(th), _ptr(new), _ptr(kin), _ptr(acc))

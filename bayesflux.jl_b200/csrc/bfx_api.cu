@@ -94,6 +94,7 @@ struct bfx_sampler {
   long long launches = 0;
   bool initialised = false;
   cudaStream_t copy_stream = nullptr;
+  cudaEvent_t adv_event = nullptr;  // recorded behind every bfx_mcmc_advance (asynchronous: the host mirror lags behind it)
 };
 
 // ---------------------------------------------------------------------------------
@@ -894,6 +895,7 @@ static void free_sampler(bfx_sampler* s) {
   cudaFree(s->gbuf);
   if (s->progress_host) cudaFreeHost(s->progress_host);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  if (s->adv_event) cudaEventDestroy(s->adv_event);
   delete s;
 }
 
@@ -1259,12 +1261,45 @@ static int32_t status_after(bfx_sampler* s) {
   std::vector<ChainScalars> sc;
   int32_t st = fetch_scalars(s, sc);
   if (st) return st;
+  // the host mirror follows the chains that are still running (a chain stops counting at its NaN guard)
+  long long ns = -1;
+  int bad = -1;
+  for (int c = 0; c < s->C; ++c) {
+    if (sc[c].status != 0) {
+      if (bad < 0) bad = c;
+    } else if (sc[c].nsampled > ns) {
+      ns = sc[c].nsampled;
+    }
+  }
+  s->nsampled = ns >= 0 ? ns : sc[0].nsampled;
+  if (bad >= 0) {
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "NaN in %s (chain %d)", sc[bad].status == BFX_ERR_NAN_G ? "g" : "θ", bad);
+    return fail(sc[bad].status, buf);
+  }
+  return BFX_OK;
+}
+
+// continue_sampling starts from the DEVICE state: bfx_mcmc_advance is asynchronous and never touches the host
+// mirror of nsampled, and a run that ended in a NaN guard leaves it behind.  Synchronise, re-read the counters and
+// refuse to continue while a chain is stopped (the lock-step sample bookkeeping would no longer hold).
+static int32_t refresh_counters(bfx_sampler* s) {
+  if (!s->initialised) return BFX_OK;
+  CK(cudaSetDevice(s->device));
+  if (s->adv_event) CK(cudaEventSynchronize(s->adv_event));
+  if (s->m->stream) CK(cudaStreamSynchronize(s->m->stream));
+  std::vector<ChainScalars> sc;
+  int32_t st = fetch_scalars(s, sc);
+  if (st) return st;
   for (int c = 0; c < s->C; ++c)
     if (sc[c].status != 0) {
-      char buf[96];
-      std::snprintf(buf, sizeof buf, "NaN in %s (chain %d)", sc[c].status == BFX_ERR_NAN_G ? "g" : "θ", c);
-      return fail(sc[c].status, buf);
+      char buf[128];
+      std::snprintf(buf, sizeof buf, "continue_sampling: chain %d stopped at a NaN guard (status %d); re-initialise the sampler",
+                    c, sc[c].status);
+      return fail(BFX_ERR_STATE, buf);
     }
+  for (int c = 1; c < s->C; ++c)
+    if (sc[c].nsampled != sc[0].nsampled) return fail(BFX_ERR_STATE, "continue_sampling: chains are not in lock step");
   s->nsampled = sc[0].nsampled;
   return BFX_OK;
 }
@@ -1465,6 +1500,10 @@ static int32_t run_counts(const bfx_sampler* s, const bfx_run_desc* run, int64_t
 }
 
 int32_t bfx_mcmc_num_kept(const bfx_sampler* s, const bfx_run_desc* run, int64_t* nnew, int64_t* nkept) {
+  if (s && run && run->continue_sampling) {
+    int32_t st = refresh_counters(const_cast<bfx_sampler*>(s));  // the mirror is a cache of device state
+    if (st) return st;
+  }
   return run_counts(s, run, nnew, nkept);
 }
 
@@ -1491,7 +1530,13 @@ static int32_t prepare_schedule(bfx_sampler* s, const bfx_run_desc* run, RunDev&
 int32_t bfx_mcmc_run(bfx_sampler* s, const bfx_run_desc* run, const float* theta_start, float* samples_out,
                      float* kinetic_out, int32_t* accepted_out) {
   int64_t nnew = 0, nkept = 0;
-  int32_t st = run_counts(s, run, &nnew, &nkept);
+  if (!s || !run) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  int32_t st = BFX_OK;
+  if (run->continue_sampling) {
+    st = refresh_counters(s);
+    if (st) return st;
+  }
+  st = run_counts(s, run, &nnew, &nkept);
   if (st) return st;
   bfx_model* m = s->m;
   st = ensure_stream(m);
@@ -1718,6 +1763,12 @@ int32_t bfx_progress(const bfx_sampler* s, int64_t* nsampled) {
   return BFX_OK;
 }
 
+static int32_t mark_advance(bfx_sampler* s, cudaStream_t st) {
+  if (!s->adv_event) CK(cudaEventCreateWithFlags(&s->adv_event, cudaEventDisableTiming));
+  CK(cudaEventRecord(s->adv_event, st));
+  return BFX_OK;
+}
+
 int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, void* stream_handle,
                          float* samples_dev, int64_t ring_slots) {
   if (!s || !run) return fail(BFX_ERR_BAD_ARG, "NULL argument");
@@ -1729,7 +1780,9 @@ int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps
   if (m->stream_regime) {
     if (!m->x) return fail(BFX_ERR_NO_DATA, "bfx_model_set_data has not been called");
     cudaStream_t sst = stream_handle ? (cudaStream_t)stream_handle : m->stream;
-    return stream_run(s, run, nsteps, s->gstep, nullptr, 0, nullptr, 0, samples_dev, ring_slots, sst);
+    st = stream_run(s, run, nsteps, s->gstep, nullptr, 0, nullptr, 0, samples_dev, ring_slots, sst);
+    if (st) return st;
+    return mark_advance(s, sst);
   }
   RunDev R{};
   st = prepare_schedule(s, run, R);
@@ -1753,7 +1806,7 @@ int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps
     s->gstep += cs;
     done += cs;
   }
-  return BFX_OK;
+  return mark_advance(s, stream);
 }
 
 int32_t bfx_sampler_launch_count(const bfx_sampler* s, int64_t* n) {

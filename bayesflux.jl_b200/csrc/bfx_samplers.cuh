@@ -72,12 +72,20 @@ BFX_DEV float* sample_slot(const Ctx<NT, BT, TC>& X, long long ns) {
   fdivmod(R.fd_keep, (unsigned long long)ns, q, r);
   if (r != 0ull) return nullptr;
   long long slot = (long long)q - 1 - R.kept_origin;
+  // a slot outside the buffer of this launch is never written (stale host counters must not turn into stray stores)
+  if (slot < 0) return nullptr;
+  if (R.ring_slots <= 0 && (slot + 1) * (long long)R.M.P > R.samples_chain_stride) return nullptr;
   if (R.ring_slots > 0) {
     unsigned long long sq, sr;
     fdivmod(R.fd_slots, (unsigned long long)slot, sq, sr);
     slot = (long long)sr;
   }
   return R.samples + (long long)X.c * R.samples_chain_stride + slot * R.M.P;
+}
+// entry of the per-step history arrays (kinetic_out / accepted_out) for 1-based step i, or -1 outside this run
+BFX_DEV long long hist_index(const RunDev& R, int c, long long i) {
+  const long long k = i - 1 - R.hist_origin;
+  return (k < 0 || k >= R.hist_stride) ? -1 : (long long)c * R.hist_stride + k;
 }
 // row of the DiagCov window ring (padded layout) that takes the ns-th sample
 template <int NT, int BT, bool TC>
@@ -323,7 +331,8 @@ BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
   block_sum<NT, 2>(acc, X.s.red);
   const float kin = acc[0] / (float)R.M.P;
   if (R.kinetic_out) {
-    if (threadIdx.x == 0) R.kinetic_out[(long long)X.c * R.hist_stride + (X.sc.t - 1 - R.hist_origin)] = kin;
+    const long long hi_ = hist_index(R, X.c, X.sc.t);
+    if (threadIdx.x == 0 && hi_ >= 0) R.kinetic_out[hi_] = kin;
   }
   X.sc.xi = xi + (kin - 1.f) * l;
   if (acc[1] > 0.f) {
@@ -404,8 +413,10 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
     X.sc.status = 5;
     return;
   }
-  if (R.kinetic_out && threadIdx.x == 0)
-    R.kinetic_out[(long long)X.c * R.hist_stride + (X.sc.t - 1 - R.hist_origin)] = acc[0] / n;
+  if (R.kinetic_out && threadIdx.x == 0) {
+    const long long hi_ = hist_index(R, X.c, X.sc.t);
+    if (hi_ >= 0) R.kinetic_out[hi_] = acc[0] / n;
+  }
   X.sc.nsampled += 1;
   X.sc.t += 1;
 }
@@ -425,7 +436,10 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
   float* th = X.s.th;
   const float* g = X.s.g;
   if (X.sc.current_step == 1) {
-    X.sc.lMH = (float)(-X.full_lp());  // :146-148
+    // :146-148  lMH = -lπ_full(θ): the log posterior of the full data set is O(n) large, so the window's start value
+    // stays in double (start_lp) and only the kinetic-energy terms accumulate in the float lMH
+    X.sc.start_lp = X.full_lp();
+    X.sc.lMH = 0.f;
     // θ at the start of the window = samples[:, nsampled - steps] on a later reject
     for_each_quad<NT>(R.M, [&](int k) { st4(X.thold + k, ld4(th + k)); });
   }
@@ -488,15 +502,17 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
   record_sample(X, ns);  // samples[:, t] with t == nsampled for GGMC
   if (X.sc.current_step == S.steps && X.sc.t > S.steps) {
     __syncthreads();
-    X.sc.lMH += (float)X.full_lp();  // :176
+    X.sc.lMH = (float)((X.full_lp() - X.sc.start_lp) + (double)X.sc.lMH);  // :176, the difference formed in double
     const float pacc = mh_prob_of(X.sc.lMH);
     X.sc.l = stepsize_adapt(X.sc, S, pacc);
     mass_adapt(X, gn2);
     const float r = X.uniform();
     const bool accept = r < pacc;
     if (R.accepted_out && threadIdx.x == 0) {
-      for (int j = 0; j < S.steps; ++j)
-        R.accepted_out[(long long)X.c * R.hist_stride + (ns - 1 - j - R.hist_origin)] = accept ? 1 : 0;
+      for (int j = 0; j < S.steps; ++j) {
+        const long long hi_ = hist_index(R, X.c, ns - j);
+        if (hi_ >= 0) R.accepted_out[hi_] = accept ? 1 : 0;
+      }
     }
     if (accept) {
       X.sc.accepted_total += S.steps;
@@ -579,8 +595,10 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
     mass_adapt(X, gn2);
     const bool accept = lr < lMH;
     const long long ns = X.sc.nsampled + 1;
-    if (R.accepted_out && threadIdx.x == 0)
-      R.accepted_out[(long long)X.c * R.hist_stride + (ns - 1 - R.hist_origin)] = accept ? 1 : 0;
+    if (R.accepted_out && threadIdx.x == 0) {
+      const long long hi_ = hist_index(R, X.c, ns);
+      if (hi_ >= 0) R.accepted_out[hi_] = accept ? 1 : 0;
+    }
     if (accept) {
       X.sc.accepted_total += 1;
     } else {

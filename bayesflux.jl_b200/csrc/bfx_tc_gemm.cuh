@@ -23,6 +23,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "bfx_tc.cuh"
 
 namespace bfx {
@@ -47,18 +49,22 @@ enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1, EPI_PLAIN = 2 };
 struct Args {
   int M, N, K;
   float* C;              // FP32 output or nullptr.  EPI_PLAIN: the split-K partial / accumulate target
-  __nv_bfloat16* Chi;    // BF16 halves of the output (nullptr: not written)
-  __nv_bfloat16* Clo;
   long long ldc;
+  int store_split;       // 1: the BF16 hi / lo halves of the output go out through the tensor maps mChi / mClo
   const float* bias;     // EPI_BIAS_ACT
   int act;
   const __nv_bfloat16* aux_hi;  // EPI_MUL_DACT: multiply by act'(aux[m + ldaux * n]), aux = hi + lo
   const __nv_bfloat16* aux_lo;
   long long ldaux;
+  // ReLU fast path: the forward epilogue leaves one sign bit per output (word (n / 32) * M + m, bit n % 32), the
+  // input-gradient epilogue reads it back instead of 32 strided BF16 loads per word
+  uint32_t* mask_out;        // EPI_BIAS_ACT with act == A_RELU (nullptr: not written)
+  const uint32_t* mask_in;   // EPI_MUL_DACT with act == A_RELU (nullptr: use aux_hi)
   float* rowpart;        // EPI_MUL_DACT: per-row sums of the stored tile, slot (2 * blockIdx.y + half) * M + m
   int accumulate;        // EPI_PLAIN, single split: C += acc
   int kchunk;            // split-K: blockIdx.z handles k in [z * kchunk, ...), multiple of BK; writes C + z * part_stride
   long long part_stride;
+  long long* timing;     // BFX_GEMM_TIMING builds: [CTA][8] clock64 marks
 };
 
 BFX_DEV uint32_t cluster_ctarank() {
@@ -145,22 +151,38 @@ BFX_DEV void tmem_free(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 
-// 32 consecutive accumulator columns of this thread's row
-BFX_DEV void ld_row32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// 32 consecutive accumulator columns of this thread's row: asynchronous issue, then a wait that owns the registers
+// (so that no use of them can be scheduled above it)
+BFX_DEV void ld_row32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+BFX_DEV void ld_row32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+BFX_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(tc::smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+#ifdef BFX_GEMM_TIMING
+#define BFX_GT(i)                                                                                                       \
+  do {                                                                                                                  \
+    if (g.timing && threadIdx.x == 32 * ((i) == 1 || (i) == 2 ? 1 : 0))                                                 \
+      g.timing[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = clock64();                \
+  } while (0)
+#else
+#define BFX_GT(i) do { } while (0)
+#endif
 
 // D = F32, A = B = BF16, M = 128 * CG, N = 256
 template <int CG>
@@ -183,7 +205,8 @@ BFX_DEV void load_operand(unsigned char* dst, const CUtensorMap* map, uint64_t* 
 template <int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(256, 1)
 k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
-           const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo, const Args g) {
+           const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
+           const __grid_constant__ CUtensorMap mChi, const __grid_constant__ CUtensorMap mClo, const Args g) {
   using C = Cfg<CG>;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[C::STAGES], bar_empty[C::STAGES], bar_acc;
@@ -199,6 +222,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
   int kend = kbeg + g.kchunk;
   if (kend > g.K) kend = g.K;
   const int nkb = (kend - kbeg + BK - 1) / BK;
+  BFX_GT(0);
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -220,6 +244,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
   __syncthreads();
   tc::fence_after();
   const uint32_t tmem = tmem_slot;
+  BFX_GT(7);
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -246,6 +271,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
       const uint32_t ph = (uint32_t)(kb / C::STAGES) & 1u;
       tc::mbar_wait(&bar_full[s], ph);
       tc::fence_after();
+      if (kb == 0) BFX_GT(1);
       if (tc::elect_one()) {
         const uint32_t ahi = tc::smem_u32(smem + s * C::STAGE), alo = ahi + TILE_A;
         const uint32_t bhi = ahi + 2 * TILE_A, blo = bhi + C::TILE_B;
@@ -266,30 +292,43 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
       }
       __syncwarp();
     }
+    BFX_GT(2);
   }
 
   // ---------------- epilogue: thread = accumulator row (lane quadrant of the warp), 128 columns per warp half ------
   if (nkb >= 1) {
     tc::mbar_wait(&bar_acc, 0u);
     tc::fence_after();
+    BFX_GT(3);
     const int q = warp & 3, half = warp >> 2;
-    const long long m = (long long)m0 + 32 * q + lane;
+    const int mloc = 32 * q + lane;
+    const long long m = (long long)m0 + mloc;
     float* Cp = g.C ? g.C + (long long)blockIdx.z * g.part_stride : nullptr;
     float bias = 0.f;
     if (EPI == EPI_BIAS_ACT && m < g.M) bias = __ldg(g.bias + m);
     float rsum = 0.f;
-#pragma unroll 1
-    for (int cb = 0; cb < 4; ++cb) {
+    // the operand ring is idle now: the BF16 halves of this half's 128 x 128 block are staged there as [n][m]
+    // (m contiguous, 256 bytes per column) and leave through one TMA store each
+    unsigned char* stage_hi = smem + half * 65536;
+    unsigned char* stage_lo = stage_hi + 32768;
+    const bool split = EPI != EPI_PLAIN && g.store_split;
+    auto process = [&](int cb, const uint32_t (&r)[32]) {
       float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       const int c0 = 128 * half + 32 * cb;
-      ld_row32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
       const long long nb = (long long)n0 + c0;
-      if (m < g.M && nb < g.N) {
-        const int ncols = (int)((g.N - nb) < 32 ? (g.N - nb) : 32);
-        if (EPI == EPI_MUL_DACT) {
+      const bool inb = m < g.M && nb < g.N;
+      const int ncols = inb ? (int)((g.N - nb) < 32 ? (g.N - nb) : 32) : 0;
+      if (EPI == EPI_MUL_DACT) {
+        if (g.act == A_RELU && g.mask_in) {
+          const uint32_t w = inb ? __ldg(g.mask_in + (nb >> 5) * g.M + m) : 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (w >> j) & 1u ? v[j] : 0.f;
+        } else {
+          float a[32];
           const __nv_bfloat16* ah = g.aux_hi + m + g.ldaux * nb;
           const __nv_bfloat16* al = g.aux_lo + m + g.ldaux * nb;
-          float a[32];
           if (g.act == A_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) a[j] = j < ncols ? __bfloat162float(ah[(long long)j * g.ldaux]) : 0.f;
@@ -302,43 +341,76 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = j < ncols ? v[j] * decltype(A)::d(a[j]) : 0.f;
           });
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rsum += v[j];
-        } else if (EPI == EPI_BIAS_ACT) {
-          tc::with_act(g.act, [&](auto A) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = decltype(A)::f(v[j] + bias);
-          });
-        } else if (g.accumulate) {
-          const float* cp = Cp + m + g.ldc * nb;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += j < ncols ? cp[(long long)j * g.ldc] : 0.f;
         }
-        if (Cp) {
-          float* cp = Cp + m + g.ldc * nb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) cp[(long long)j * g.ldc] = v[j];
+        for (int j = 0; j < 32; ++j) rsum += v[j];
+      } else if (EPI == EPI_BIAS_ACT) {
+        tc::with_act(g.act, [&](auto A) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = decltype(A)::f(v[j] + bias);
+        });
+        if (g.act == A_RELU && g.mask_out && inb) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+          g.mask_out[(nb >> 5) * g.M + m] = w;
         }
-        if (EPI != EPI_PLAIN && g.Chi) {
-          __nv_bfloat16* hp = g.Chi + m + g.ldc * nb;
-          __nv_bfloat16* lp = g.Clo + m + g.ldc * nb;
+      } else if (g.accumulate && inb) {
+        const float* cp = Cp + m + g.ldc * nb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < ncols) {
-              const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-              hp[(long long)j * g.ldc] = h;
-              lp[(long long)j * g.ldc] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
-            }
-          }
+        for (int j = 0; j < 32; ++j) v[j] += j < ncols ? cp[(long long)j * g.ldc] : 0.f;
+      }
+      if (Cp && inb) {  // lanes = consecutive rows m: every store instruction is one full line
+        float* cp = Cp + m + g.ldc * nb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) cp[(long long)j * g.ldc] = v[j];
+      }
+      if (split) {
+        __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(stage_hi) + (32 * cb) * 128 + mloc;
+        __nv_bfloat16* sl = reinterpret_cast<__nv_bfloat16*>(stage_lo) + (32 * cb) * 128 + mloc;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+          sh[j * 128] = h;
+          sl[j * 128] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
         }
       }
+    };
+    {
+      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * half);
+      uint32_t ra[32], rb[32];
+      ld_row32_issue(tbase, ra);
+      ld_row32_wait(ra);
+      ld_row32_issue(tbase + 32, rb);   // block 1 streams out of TMEM while block 0 is processed
+      process(0, ra);
+      ld_row32_wait(rb);
+      ld_row32_issue(tbase + 64, ra);
+      process(1, rb);
+      ld_row32_wait(ra);
+      ld_row32_issue(tbase + 96, rb);
+      process(2, ra);
+      ld_row32_wait(rb);
+      process(3, rb);
     }
     if (EPI == EPI_MUL_DACT && g.rowpart && m < g.M) g.rowpart[(long long)(2 * blockIdx.y + half) * g.M + m] = rsum;
+    BFX_GT(4);
+    if (split) {
+      tc::fence_async_smem();  // generic-proxy stores -> visible to the TMA engine
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      if (q == 0 && lane == 0 && m0 < g.M && n0 + 128 * half < g.N) {  // rows / columns beyond M / N are clipped by the TMA
+        tma_store_2d(&mChi, stage_hi, m0, n0 + 128 * half);
+        tma_store_2d(&mClo, stage_lo, m0, n0 + 128 * half);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    }
+    BFX_GT(5);
   }
   tc::fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) tmem_free<CG>(tmem, (uint32_t)BN);
+  BFX_GT(6);
 }
 
 // ---------------- host side ----------------
@@ -382,21 +454,43 @@ struct Operand {
   long long ld;
 };
 
+// output halves: element (m, n) at base[m + ldc * n], box 128 rows x 128 columns, no swizzle
+inline cudaError_t make_store_map(CUtensorMap* map, __nv_bfloat16* base, long long M, long long N, long long ldc) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)N}, strides[1] = {(cuuint64_t)ldc * 2};
+  cuuint32_t box[2] = {128, 128}, estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+struct Output {
+  __nv_bfloat16* hi;  // nullptr: the BF16 halves are not written
+  __nv_bfloat16* lo;
+};
+
 template <int CG, bool A_MN, bool B_MN, int EPI>
-inline cudaError_t launch(const Args& g, const Operand& A, const Operand& B, int ksplit, cudaStream_t st) {
+inline cudaError_t launch(const Args& g0, const Operand& A, const Operand& B, const Output& O, int ksplit, cudaStream_t st) {
   using C = Cfg<CG>;
-  CUtensorMap mAhi, mAlo, mBhi, mBlo;
+  Args g = g0;
+  CUtensorMap mAhi, mAlo, mBhi, mBlo, mChi, mClo;
   cudaError_t e;
+  memset(&mChi, 0, sizeof mChi);
+  memset(&mClo, 0, sizeof mClo);
+  g.store_split = 0;
+  if (EPI != EPI_PLAIN && O.hi) {
+    if ((e = make_store_map(&mChi, O.hi, g.M, g.N, g.ldc)) != cudaSuccess) return e;
+    if ((e = make_store_map(&mClo, O.lo, g.M, g.N, g.ldc)) != cudaSuccess) return e;
+    g.store_split = 1;
+  }
   if ((e = make_map(&mAhi, A.hi, A_MN, g.M, g.K, A.ld, BM)) != cudaSuccess) return e;
   if ((e = make_map(&mAlo, A.lo, A_MN, g.M, g.K, A.ld, BM)) != cudaSuccess) return e;
   if ((e = make_map(&mBhi, B.hi, B_MN, g.N, g.K, B.ld, C::BROWS)) != cudaSuccess) return e;
   if ((e = make_map(&mBlo, B.lo, B_MN, g.N, g.K, B.ld, C::BROWS)) != cudaSuccess) return e;
   auto kern = k_tc_gemm2<CG, A_MN, B_MN, EPI>;
-  static bool attr_set = false;  // per template instance
-  if (!attr_set) {
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)) != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)) != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   const int mt = (g.M + BM * CG - 1) / (BM * CG);
   cfg.gridDim = dim3((unsigned)(mt * CG), (unsigned)((g.N + BN - 1) / BN), (unsigned)ksplit);
@@ -410,7 +504,7 @@ inline cudaError_t launch(const Args& g, const Operand& A, const Operand& B, int
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, mAhi, mAlo, mBhi, mBlo, g);
+  return cudaLaunchKernelEx(&cfg, kern, mAhi, mAlo, mBhi, mBlo, mChi, mClo, g);
 }
 
 }  // namespace tcg

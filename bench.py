@@ -271,12 +271,14 @@ def run_ours(args):
     s2 = bf.SGLD()
 
     e2e_calls = [0]
+    # caller-owned result buffers, alternated: the array of call i stays valid while call i+1 runs
+    e2e_out = [np.empty((P, 1, C), np.float32, order="F") for _ in range(2)]
 
     def e2e_step():
         nonlocal theta_h
         e2e_calls[0] += 1
         ch = bf.mcmc(bnn, B, U, s2, theta_start=theta_h, keep_every=U, seed=SEED + e2e_calls[0],
-                     chain_offset=chain_offset)
+                     chain_offset=chain_offset, out=e2e_out[e2e_calls[0] & 1])
         theta_h = np.asfortranarray(ch[:, -1, :]) if ch.ndim == 3 else np.asfortranarray(ch[:, -1:])
         return ch
 

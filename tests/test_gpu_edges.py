@@ -139,3 +139,37 @@ def test_sharding_invariance_of_the_mh_and_thermostat_samplers(bf, kind):
     assert np.array_equal(np.concatenate(parts, axis=2), whole)
     if acc is not None:
         assert np.array_equal(np.concatenate(accs, axis=1), acc)
+
+
+@pytest.mark.parametrize("kind", ["sgld", "sgnht", "hmc"])
+def test_continue_after_device_resident_advance(bf, kind):
+    """mcmc -> bfx_mcmc_advance (asynchronous, device only) -> mcmc(continue_sampling): the continued run must take
+    its sample / history origins from the DEVICE counters (the host mirror knows nothing of the advance).  With
+    stale origins the slots of the continued run would land past the per-chain stride of the sample buffer."""
+    rng = np.random.default_rng(SEED + 77)
+    bnn, m, x, y = _bnn(bf, 300, "fp32", seed=3)
+    C = 3
+    th0 = (0.1 * rng.standard_normal((m.n_total, C))).astype(np.float32)
+
+    def make():
+        if kind == "sgld":
+            return bf.SGLD()
+        if kind == "sgnht":
+            return bf.SGNHT(1e-3)
+        return bf.HMC(1e-3, 3, sadapter=bf.ConstantStepsize(1e-3), madapter=bf.FixedMassAdapter())
+
+    ups = 3 if kind == "hmc" else 1  # update! calls per sample
+    s = make()
+    first = np.array(bf.mcmc(bnn, 50, 10, s, theta_start=th0, seed=9))
+    bf.advance(s, 50, 7 * ups, seed=9)  # 7 more samples, nothing recorded, host mirror untouched
+    out = np.array(bf.mcmc(bnn, 50, 25, s, continue_sampling=True, seed=9))
+    assert s.nsampled == 25
+    assert out.shape == (m.n_total, 10 + 8, C)  # 10 old + (25 - 17) new columns
+    assert np.array_equal(out[:, :10], first)
+    assert np.all(np.isfinite(out))
+    if kind == "sgld":
+        # counter-based noise and schedule: samples 18..25 equal those of an uninterrupted run
+        ref = np.array(bf.mcmc(bnn, 50, 25, make(), theta_start=th0, seed=9))
+        assert np.array_equal(out[:, 10:], ref[:, 17:])
+    if s.kinetic is not None:
+        assert s.kinetic.shape[0] == 18 and np.all(np.isfinite(s.kinetic))

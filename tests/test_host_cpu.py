@@ -139,26 +139,11 @@ def test_sampler_descriptor_mirrors_reference_defaults():
     assert bf.HMC(1e-4, 5)._desc().madapter_kind == L.MASS_FULLCOV  # reference default, rejected by the engine
 
 
-def test_result_buffers_are_recycled_only_when_unreferenced():
-    """mcmc hands out host arrays from a small pool: an array the caller (or a view) still references is never
-    reused, a dropped one is."""
+def test_mcmc_has_no_hidden_result_pool():
+    """Results are fresh arrays unless the caller passes its own ``out=`` buffer (no refcount-based recycling)."""
+    import inspect
     from bayesflux_b200 import api
 
-    class Dummy:
-        pass
-
-    s = Dummy()
-    a = api._result_buffer(s, (7, 1, 3))
-    a[:] = 1.0
-    b = api._result_buffer(s, (7, 1, 3))  # `a` is still referenced here
-    assert b is not a
-    view = a[:, -1, :]
-    del a
-    c = api._result_buffer(s, (7, 1, 3))  # the view keeps the first array alive
-    assert c is not view.base and c is not b
-    first_id = id(view.base)
-    del view
-    d = api._result_buffer(s, (7, 1, 3))  # now it may come back
-    assert id(d) == first_id
-    e = api._result_buffer(s, (7, 2, 3))  # other shapes never alias
-    assert e.shape == (7, 2, 3) and e is not d
+    assert "out" in inspect.signature(api.mcmc).parameters
+    assert not hasattr(api, "_result_buffer")
+    assert "getrefcount" not in inspect.getsource(api)
