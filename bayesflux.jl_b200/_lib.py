@@ -22,6 +22,8 @@ MASS_FIXED, MASS_DIAGCOV, MASS_RMSPROP, MASS_FULLCOV = range(4)
 BATCH_PER_CHAIN, BATCH_SHARED = 0, 1
 COMPUTE_FP32, COMPUTE_TC_BF16X3 = 0, 1
 REGIME_SMEM, REGIME_STREAM = 0, 1
+SHARD_NONE, SHARD_CHAINS, SHARD_MINIBATCH = 0, 1, 2
+COMM_ID_BYTES = 128
 
 
 class LayerDesc(C.Structure):
@@ -58,7 +60,7 @@ class RunDesc(C.Structure):
     _fields_ = [("batchsize", C.c_int64), ("numsamples", C.c_int64), ("shuffle", C.c_int32),
                 ("partial", C.c_int32), ("continue_sampling", C.c_int32), ("keep_every", C.c_int32),
                 ("batch_mode", C.c_int32), ("_pad", C.c_int32), ("seed", C.c_uint64),
-                ("chain_offset", C.c_int64)]
+                ("chain_offset", C.c_int64), ("ngpus", C.c_int32), ("shard_mode", C.c_int32)]
 
 
 # every symbol include/bfx.h declares: name -> argtypes
@@ -95,6 +97,10 @@ SYMBOLS = {
     "bfx_model_regime": [_vp, _pi32],
     "bfx_stream_grad_local": [_vp, C.POINTER(RunDesc), _f32, _vp, _vp, _i64],
     "bfx_stream_apply_update": [_vp, C.POINTER(RunDesc), _f32, _vp, _vp, _vp],
+    "bfx_comm_unique_id": [_vp],
+    "bfx_sampler_comm_init": [_vp, _vp, _i32, _i32],
+    "bfx_sampler_comm_destroy": [_vp],
+    "bfx_sampler_graph_replays": [_vp, _pi64],
     "bfx_debug_batch_indices": [_vp, C.POINTER(RunDesc), _i64, _i64, _vp, _pi64],
     "bfx_debug_noise": [_vp, C.POINTER(RunDesc), _i64, _i64, _i32, _vp, _vp],
 }

@@ -709,15 +709,20 @@ def find_mode(bnn: BNN, batchsize: int, epochs: int, optimiser: FluxModeFinder, 
 
 
 # --------------------------------------------------------------------- mcmc ---
+_SHARD = {None: L.SHARD_NONE, "none": L.SHARD_NONE, "chains": L.SHARD_CHAINS, "minibatch": L.SHARD_MINIBATCH}
+
+
 def _run_desc(batchsize, numsamples, shuffle, partial, continue_sampling, keep_every, seed, batch_mode,
-              chain_offset=0):
+              chain_offset=0, ngpus=1, shard_mode=None):
     return L.RunDesc(batchsize, numsamples, int(shuffle), int(partial), int(continue_sampling), keep_every,
-                     L.BATCH_SHARED if batch_mode == "shared" else L.BATCH_PER_CHAIN, 0, seed, chain_offset)
+                     L.BATCH_SHARED if batch_mode == "shared" else L.BATCH_PER_CHAIN, 0, seed, chain_offset,
+                     int(ngpus), _SHARD[shard_mode])
 
 
 def mcmc(bnn: BNN, batchsize: int, numsamples: int, sampler: MCMCState, shuffle=True, partial=True,
          showprogress=False, continue_sampling=False, theta_start=None, nchains: Optional[int] = None,
-         keep_every: int = 1, seed: int = 0, batch_mode: str = "per_chain", chain_offset: int = 0, out=None):
+         keep_every: int = 1, seed: int = 0, batch_mode: str = "per_chain", chain_offset: int = 0, out=None,
+         ngpus: int = 1, shard_mode: Optional[str] = None):
     """mcmc(bnn, batchsize, numsamples, sampler; shuffle, partial, continue_sampling, θstart)
     src/inference/mcmc/abstract.jl:74-127, run entirely on the device.  Engine extensions:
     nchains (θstart may be P x C), keep_every, seed, batch_mode, and ``out``: a caller-owned Fortran-ordered
@@ -742,7 +747,7 @@ def mcmc(bnn: BNN, batchsize: int, numsamples: int, sampler: MCMCState, shuffle=
         nchains = th.shape[1]
         sampler._bind(bnn, nchains)
     run = _run_desc(batchsize, numsamples, shuffle, partial, continue_sampling, keep_every, seed, batch_mode,
-                    chain_offset)
+                    chain_offset, ngpus, shard_mode)
     nnew, nkept = C.c_int64(), C.c_int64()
     L.check(L.lib.bfx_mcmc_num_kept(sampler._h, C.byref(run), C.byref(nnew), C.byref(nkept)))
     nnew, nkept = nnew.value, nkept.value
@@ -775,15 +780,41 @@ def mcmc(bnn: BNN, batchsize: int, numsamples: int, sampler: MCMCState, shuffle=
 
 def advance(sampler: MCMCState, batchsize: int, nsteps: int, shuffle=True, partial=True, keep_every: int = 1,
             seed: int = 0, batch_mode: str = "per_chain", chain_offset: int = 0, stream: int = 0,
-            samples_dev: int = 0, ring_slots: int = 0):
+            samples_dev: int = 0, ring_slots: int = 0, ngpus: int = 1, shard_mode: Optional[str] = None):
     """Device-resident continuation of ``mcmc``: enqueue ``nsteps`` update! calls for every chain of an
     initialised sampler (``sampler.initialise(bnn, theta)``) on ``stream`` (a raw cudaStream_t, 0 = the
     engine's own stream) and return immediately.  Recorded samples (every ``keep_every``-th) are written
     to the caller's device ring ``samples_dev`` ([C][ring_slots][P] floats) when given.  Same loop body as
     mcmc (src/inference/mcmc/abstract.jl:117-124); nothing crosses PCIe."""
-    run = _run_desc(batchsize, 0, shuffle, partial, True, keep_every, seed, batch_mode, chain_offset)
+    run = _run_desc(batchsize, 0, shuffle, partial, True, keep_every, seed, batch_mode, chain_offset, ngpus,
+                    shard_mode)
     L.check(L.lib.bfx_mcmc_advance(sampler._h, C.byref(run), int(nsteps), C.c_void_p(stream),
                                    C.c_void_p(samples_dev), int(ring_slots)))
+
+
+def comm_unique_id() -> bytes:
+    """The 128-byte NCCL id of a new communicator (rank 0 creates it, the caller distributes it)."""
+    buf = C.create_string_buffer(L.COMM_ID_BYTES)
+    L.check(L.lib.bfx_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(sampler: MCMCState, comm_id: bytes, nranks: int, rank: int):
+    """Attach the in-library NCCL communicator of a minibatch-sharded chain to an initialised sampler replica
+    (collective over the ranks).  Afterwards ``mcmc`` / ``advance`` with ``shard_mode="minibatch"`` all-reduce the
+    gradient inside the engine's update graph."""
+    assert len(comm_id) == L.COMM_ID_BYTES
+    L.check(L.lib.bfx_sampler_comm_init(sampler._h, C.c_char_p(comm_id), int(nranks), int(rank)))
+
+
+def comm_destroy(sampler: MCMCState):
+    L.check(L.lib.bfx_sampler_comm_destroy(sampler._h))
+
+
+def graph_replays(sampler: MCMCState) -> int:
+    n = C.c_int64()
+    L.check(L.lib.bfx_sampler_graph_replays(sampler._h, C.byref(n)))
+    return n.value
 
 
 def launch_count(sampler: MCMCState) -> int:

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include "../../include/bfx.h"
 #include "bfx_common.cuh"
@@ -45,6 +46,52 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen): the library has no link-time dependency on it, a process that already carries
+// NCCL (torch, a Julia NCCL.jl session) shares that copy.  Only the minibatch-sharded chain uses it.
+// ---------------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.handle ? &api : nullptr;
+  tried = true;
+  const char* names[] = {std::getenv("BFX_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nme : names) {
+    if (!nme || !*nme) continue;
+    api.handle = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+    api.err = dlerror();
+  }
+  if (!api.handle) return nullptr;
+  api.GetUniqueId = (int (*)(NcclId*))dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
+  api.CommInitAll = (int (*)(void**, int, const int*))dlsym(api.handle, "ncclCommInitAll");
+  api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) {
+    api.err = "NCCL symbols missing";
+    api.handle = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+}  // namespace
+
+
 struct bfx_model {
   int device = 0;
   ModelDev M{};
@@ -64,6 +111,10 @@ struct bfx_model {
   bool stream_regime = false;
   StreamModel SM{};
   StreamWork W{};
+  // whose theta the BF16 halves W.w_hi / w_lo currently hold (tensor-core layers): a single-chain sampler keeps them
+  // current through its updates, every other evaluation overwrites them
+  const void* wsplit_owner = nullptr;
+  long long wsplit_gstep = -1;
   float* scratch = nullptr;  // recurrent path: per-CTA per-step records
   size_t scratch_ctas = 0;
   int* d_flat_pad = nullptr;
@@ -95,6 +146,13 @@ struct bfx_sampler {
   bool initialised = false;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t adv_event = nullptr;  // recorded behind every bfx_mcmc_advance (asynchronous: the host mirror lags behind it)
+  // stream regime: one update! as a CUDA graph (captured once per static description, see stream_run)
+  cudaGraphExec_t upd_graph = nullptr;
+  std::vector<unsigned char> upd_graph_key;
+  long long graph_replays = 0;
+  // minibatch-sharded chain: NCCL communicator of the ranks that hold the shards (bfx_sampler_comm_init)
+  void* comm = nullptr;
+  int comm_rank = 0, comm_nranks = 1;
 };
 
 // ---------------------------------------------------------------------------------
@@ -387,6 +445,7 @@ int32_t bfx_model_set_compute(bfx_model* m, int32_t mode) {
       if (m->stream) cudaStreamSynchronize(m->stream);
       stream_work_free(m->W);
     }
+    m->wsplit_owner = nullptr;
     return BFX_OK;
   }
   if (mode == BFX_COMPUTE_FP32) {
@@ -573,38 +632,28 @@ int32_t bfx_model_set_data_device(bfx_model* m, const float* x_dev, const int64_
 // ---------------------------------------------------------------------------------
 // stream regime helpers
 // ---------------------------------------------------------------------------------
-static void philox_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += W0;
-    k1 += W1;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-// the minibatch of global step gstep for chain `chainkey` (same schedule as make_batch in bfx_kernels.cu)
-static StreamBatch stream_batch(const bfx_model* m, const bfx_run_desc* run, unsigned chainkey, long long gstep) {
+// the scheduled minibatch of the update that follows `gstep` updates (abstract.jl:102-105): sized on the host, resolved
+// (positions, permutation keys) on the device.  device_step: the kernels read the chain's own step counter instead
+// of `gstep` (graph replays).
+static StreamBatch stream_batch(const bfx_model* m, const bfx_run_desc* run, unsigned chainkey, long long gstep,
+                                bool device_step = false) {
   StreamBatch b{};
   b.idx = nullptr;
   b.n = m->n;
   long long B = run->batchsize < m->n ? run->batchsize : m->n;
   long long nb = run->partial ? (m->n + B - 1) / B : m->n / B;
   if (nb < 1) nb = 1;
-  const unsigned long long epoch = (unsigned long long)gstep / (unsigned long long)nb, k = (unsigned long long)gstep % (unsigned long long)nb;
-  b.first = (long long)k * B;
-  const long long rem = m->n - b.first;
+  const unsigned long long k = (unsigned long long)gstep % (unsigned long long)nb;
+  const long long rem = m->n - (long long)k * B;
   b.B = rem < B ? rem : B;
+  b.Bsched = B;
+  b.scheduled = 1;
+  b.nbat = nb;
+  b.gstep = device_step ? -1 : gstep;
+  b.seed = run->seed;
+  b.chainkey = run->batch_mode == BFX_BATCH_SHARED ? 0xFFFFFFFFu : chainkey;
   b.shuffle = run->shuffle ? 1 : 0;
   b.full = 0;
-  uint32_t o[4];
-  philox_host((uint32_t)epoch, (uint32_t)(epoch >> 32), run->batch_mode == BFX_BATCH_SHARED ? 0xFFFFFFFFu : chainkey,
-              0x5eedba7cu, (uint32_t)run->seed, (uint32_t)(run->seed >> 32), o);
-  b.k0 = o[0];
-  b.k1 = o[1];
   return b;
 }
 
@@ -616,6 +665,7 @@ static int32_t ensure_work(bfx_model* m, long long B) {
     CK(cudaStreamSynchronize(m->stream));
     stream_work_free(m->W);
   }
+  m->wsplit_owner = nullptr;
   CK(stream_work_alloc(m->SM, Bc, m->W));
   return BFX_OK;
 }
@@ -625,9 +675,10 @@ static int32_t stream_eval_full(bfx_model* m, const float* theta_dev, const Stre
                                 float* g_dev, StreamScalars* ssc, cudaStream_t st) {
   int32_t rc = ensure_work(m, b.B);
   if (rc) return rc;
+  m->wsplit_owner = nullptr;
   CK(stream_zero(g_dev, m->M.P, ssc, st));
   CK(stream_eval_like(m->SM, m->W, theta_dev, m->x, m->y, b, nb, want_grad, g_dev, ssc, st));
-  CK(stream_finish(m->SM, theta_dev, g_dev, ssc, nb, want_grad, st));
+  CK(stream_finish(m->SM, theta_dev, g_dev, ssc, nb, want_grad, false, st));
   return BFX_OK;
 }
 
@@ -827,6 +878,7 @@ int32_t bfx_predict(bfx_model* m, const float* theta, int32_t C, const float* x_
     CKC(cudaMalloc(&d_theta, (size_t)P * 4));
     CKC(cudaMalloc(&d_g, ((size_t)P + 4) * 4));
     CKC(cudaMalloc(&d_sc, sizeof(StreamScalars)));
+    CKC(cudaMemsetAsync(d_sc, 0, sizeof(StreamScalars), m->stream));  // reduction tickets start at zero
     rc = ensure_work(m, n);
     for (int c = 0; c < C && !rc; ++c) {
       CKC(cudaMemcpyAsync(d_theta, theta + (size_t)c * P, (size_t)P * 4, cudaMemcpyHostToDevice, m->stream));
@@ -834,6 +886,7 @@ int32_t bfx_predict(bfx_model* m, const float* theta, int32_t C, const float* x_
       b.n = n;
       b.full = 1;
       b.B = n;
+      m->wsplit_owner = nullptr;
       CKC(stream_zero(d_g, P, d_sc, m->stream));
       CKC(stream_eval_like(m->SM, m->W, d_theta, xs, ys, b, 1.f, false, d_g, d_sc, m->stream, d_out + (size_t)c * n));
     }
@@ -896,6 +949,10 @@ static void free_sampler(bfx_sampler* s) {
   if (s->progress_host) cudaFreeHost(s->progress_host);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->adv_event) cudaEventDestroy(s->adv_event);
+  if (s->upd_graph) cudaGraphExecDestroy(s->upd_graph);
+  if (s->comm) {
+    if (NcclApi* api = nccl_api()) api->CommDestroy(s->comm);
+  }
   delete s;
 }
 
@@ -1306,9 +1363,14 @@ static int32_t refresh_counters(bfx_sampler* s) {
 
 
 // ---------------------------------------------------------------------------------
-// stream regime: one update! of chain c (grad on the local minibatch, optional hand-off for the
-// caller's all-reduce, update).  Everything is enqueued on `st`; nothing synchronises.
+// stream regime: one update! of chain c (grad on the local minibatch, all-reduce of the exchange buffer when the
+// chain is minibatch-sharded, update).  Everything is enqueued on `st`; nothing synchronises.
 // ---------------------------------------------------------------------------------
+static bool wsplit_valid(const bfx_sampler* s) {
+  const bfx_model* m = s->m;
+  return m->SM.tc && s->C == 1 && m->wsplit_owner == s && m->wsplit_gstep == s->gstep;
+}
+
 static int32_t stream_grad_local(bfx_sampler* s, int c, const StreamBatch& b, float nb, bool pack, cudaStream_t st,
                                  float* gb = nullptr) {
   if (!gb) gb = s->gbuf;
@@ -1316,19 +1378,32 @@ static int32_t stream_grad_local(bfx_sampler* s, int c, const StreamBatch& b, fl
   int32_t rc = ensure_work(m, b.B);
   if (rc) return rc;
   const float* th = s->theta + (size_t)c * s->Ps;
+  const bool valid = wsplit_valid(s);
+  if (!valid) m->wsplit_owner = nullptr;
   CK(stream_zero(gb, m->M.P, s->ssc + c, st));
-  CK(stream_eval_like(m->SM, m->W, th, m->x, m->y, b, nb, true, gb, s->ssc + c, st));
-  if (pack) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, true, st));
+  CK(stream_eval_like(m->SM, m->W, th, m->x, m->y, b, nb, true, gb, s->ssc + c, st, nullptr, valid));
+  if (pack) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, st));
   return BFX_OK;
 }
 
-static int32_t stream_apply(bfx_sampler* s, int c, float nb, bool unpack, unsigned long long seed, unsigned chainkey,
-                            const float* inj, float* sample_dev, float* kinetic_dev, cudaStream_t st, float* gb = nullptr) {
+// where an update records: explicit device slots (injected steps, the sharded-chain entry points) or the run's
+// buffers resolved on the device from the chain's counters
+struct StreamRecord {
+  float* sample_dev = nullptr;
+  float* kinetic_dev = nullptr;
+  float* samples_base = nullptr;
+  long long keep_every = 1, kept_origin = 0, ring_slots = 0;
+  float* kinetic_base = nullptr;
+  long long hist_origin = 0, hist_stride = 0;
+};
+
+static int32_t stream_apply(bfx_sampler* s, int c, float nb, bool from_buffer, unsigned long long seed, unsigned chainkey,
+                            const float* inj, const StreamRecord& rec, cudaStream_t st, float* gb = nullptr,
+                            bool device_step = false) {
   bfx_model* m = s->m;
   if (!gb) gb = s->gbuf;
   float* th = s->theta + (size_t)c * s->Ps;
-  if (unpack) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, false, st));
-  CK(stream_finish(m->SM, th, gb, s->ssc + c, nb, true, st));
+  CK(stream_finish(m->SM, th, gb, s->ssc + c, nb, true, from_buffer, st));
   StreamUpdate U{};
   U.S = &s->S;
   U.P = m->M.P;
@@ -1340,13 +1415,51 @@ static int32_t stream_apply(bfx_sampler* s, int c, float nb, bool unpack, unsign
   U.sc = s->ssc + c;
   U.seed = seed;
   U.chain = chainkey;
-  U.gstep = (unsigned long long)s->gstep;
+  U.gstep = device_step ? -1 : s->gstep;
   U.inj = inj;
-  U.sample_out = sample_dev;
-  U.kinetic_out = kinetic_dev;
+  U.sample_out = rec.sample_dev;
+  U.kinetic_out = rec.kinetic_dev;
+  U.samples_base = rec.samples_base;
+  U.keep_every = rec.keep_every; U.kept_origin = rec.kept_origin; U.ring_slots = rec.ring_slots;
+  U.kinetic_base = rec.kinetic_base; U.hist_origin = rec.hist_origin; U.hist_stride = rec.hist_stride;
+  const bool keep_split = m->SM.tc && s->C == 1 && m->W.w_hi;
+  U.w_hi = keep_split ? m->W.w_hi : nullptr;
+  U.w_lo = keep_split ? m->W.w_lo : nullptr;
   cudaError_t e = stream_update(U, st);
   if (e != cudaSuccess) return fail(BFX_ERR_CUDA, std::string("stream_update: ") + cudaGetErrorString(e));
+  if (keep_split) {
+    m->wsplit_owner = s;
+    m->wsplit_gstep = s->gstep + 1;  // valid for the evaluation of the next update (the caller advances gstep)
+  }
   return BFX_OK;
+}
+
+// the all-reduce of the exchange buffer [g ; sum1 ; sum2 ; B] of a minibatch-sharded chain
+static int32_t stream_allreduce(bfx_sampler* s, float* gb, cudaStream_t st) {
+  NcclApi* api = nccl_api();
+  if (!api || !s->comm) return fail(BFX_ERR_STATE, "minibatch-sharded update without a communicator");
+  const int r = api->AllReduce(gb, gb, (size_t)s->m->M.P + 3, kNcclFloat32, kNcclSum, s->comm, st);
+  if (r != 0) return fail(BFX_ERR_CUDA, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+  return BFX_OK;
+}
+
+// one whole update! of chain c, scheduled batch
+static int32_t stream_update_once(bfx_sampler* s, const bfx_run_desc* run, int c, float nbat, const StreamRecord& rec,
+                                  bool device_step, cudaStream_t st) {
+  bfx_model* m = s->m;
+  const bool sharded = run->shard_mode == BFX_SHARD_MINIBATCH && s->comm != nullptr;
+  const unsigned permkey = (unsigned)(run->chain_offset + c);
+  // a sharded chain draws its local batch with its own permutation stream (chain_offset = rank) and applies the
+  // update with the shared noise key 0: identical Philox streams keep theta / p / xi bit-identical on every rank
+  const unsigned noisekey = sharded ? 0u : permkey;
+  StreamBatch b = stream_batch(m, run, permkey, s->gstep, device_step);
+  int32_t rc = stream_grad_local(s, c, b, nbat, sharded, st);
+  if (rc) return rc;
+  if (sharded) {
+    rc = stream_allreduce(s, s->gbuf, st);
+    if (rc) return rc;
+  }
+  return stream_apply(s, c, nbat, sharded, run->seed, noisekey, nullptr, rec, st, nullptr, device_step);
 }
 
 static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, int64_t base, float* samples_host,
@@ -1359,35 +1472,117 @@ static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nstep
   long long B = run->batchsize < m->n ? run->batchsize : m->n;
   long long nbat = run->partial ? (m->n + B - 1) / B : m->n / B;
   if (nbat < 1) nbat = 1;
+  if (run->shard_mode == BFX_SHARD_MINIBATCH && !s->comm && run->ngpus > 1)
+    return fail(BFX_ERR_STATE, "shard_mode MINIBATCH needs bfx_sampler_comm_init on every rank");
+  if (run->shard_mode == BFX_SHARD_MINIBATCH && C != 1)
+    return fail(BFX_ERR_BAD_ARG, "a minibatch-sharded sampler carries exactly one chain");
   float* d_kin = nullptr;
   if (kinetic_host) {
     CK(cudaMalloc(&d_kin, (size_t)C * nnew * 4));
     CK(cudaMemsetAsync(d_kin, 0, (size_t)C * nnew * 4, st));
   }
+  const int64_t slots = ring_slots > 0 ? ring_slots : 1;
+  auto record_of = [&](int c) {
+    StreamRecord rec;
+    if (samples_dev) {
+      rec.samples_base = samples_dev + (size_t)c * slots * P;
+      rec.keep_every = ke;
+      rec.kept_origin = 0;
+      rec.ring_slots = slots;
+    }
+    if (d_kin) {
+      rec.kinetic_base = d_kin + (size_t)c * nnew;
+      rec.hist_origin = base;
+      rec.hist_stride = nnew;
+    }
+    return rec;
+  };
+  int32_t rc = ensure_work(m, B);
+  if (rc) return rc;
+  // One chain: the update is a fixed launch sequence whose per-step quantities are resolved on the device, so it is
+  // captured once as a CUDA graph and replayed; only the short last batch of an epoch is launched directly.
+  const bool use_graph = C == 1 && !std::getenv("BFX_NO_GRAPH");
+  if (use_graph) {
+    if (m->SM.tc && !wsplit_valid(s)) {  // the graph assumes current BF16 halves of theta
+      CK(stream_split_theta(m->SM, m->W, s->theta, st));
+      m->wsplit_owner = s;
+      m->wsplit_gstep = s->gstep;
+    }
+    CK(stream_set_gstep(s->ssc, s->gstep, st));
+    struct Key {
+      long long B, nbat, n, ke, slots, base, nnew;
+      int shuffle, batch_mode, shard, tc;
+      unsigned long long seed;
+      long long chain_offset;
+      const void *samples_dev, *d_kin, *comm, *x, *w;
+    } key{B, nbat, m->n, ke, samples_dev ? slots : 0, d_kin ? base : 0, d_kin ? nnew : 0, run->shuffle, run->batch_mode,
+          run->shard_mode, m->SM.tc, run->seed, run->chain_offset, samples_dev, d_kin, s->comm, m->x, m->W.w_hi};
+    std::vector<unsigned char> kb(sizeof key);
+    std::memcpy(kb.data(), &key, sizeof key);
+    if (!s->upd_graph || kb != s->upd_graph_key) {
+      if (s->upd_graph) {
+        cudaGraphExecDestroy(s->upd_graph);
+        s->upd_graph = nullptr;
+      }
+      // capture with a full-size batch (step index irrelevant: device_step)
+      const long long g_save = s->gstep;
+      s->gstep = 0;
+      const void* own_save = m->wsplit_owner;
+      const long long wg_save = m->wsplit_gstep;
+      m->wsplit_owner = s;
+      m->wsplit_gstep = 0;
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      rc = stream_update_once(s, run, 0, (float)nbat, record_of(0), true, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      s->gstep = g_save;
+      m->wsplit_owner = own_save;
+      m->wsplit_gstep = wg_save;
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (ce != cudaSuccess) return fail(BFX_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&s->upd_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return fail(BFX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+      s->upd_graph_key = kb;
+    }
+  }
   for (int64_t it = 0; it < nsteps; ++it) {
     const int64_t ns = base + it + 1;  // nsampled after this update (SGLD / SGNHT / SGNHTS: one sample per update)
-    for (int c = 0; c < C; ++c) {
-      const unsigned chainkey = (unsigned)(run->chain_offset + c);
-      StreamBatch b = stream_batch(m, run, chainkey, s->gstep);
-      int32_t rc = stream_grad_local(s, c, b, (float)nbat, false, st);
-      if (rc) return rc;
-      float* sdev = nullptr;
-      if (samples_dev && ns % ke == 0) {
-        int64_t slot = ns / ke - 1;
-        if (ring_slots > 0) slot %= ring_slots;
-        sdev = samples_dev + ((size_t)c * (ring_slots > 0 ? ring_slots : 1) + slot) * P;
+    if (use_graph) {
+      const long long k = s->gstep % nbat;
+      const bool full_batch = m->n - k * B >= B;
+      if (full_batch) {
+        CK(cudaGraphLaunch(s->upd_graph, st));
+        s->graph_replays += 1;
+        if (m->SM.tc) {
+          m->wsplit_owner = s;
+          m->wsplit_gstep = s->gstep + 1;
+        }
+      } else {
+        rc = stream_update_once(s, run, 0, (float)nbat, record_of(0), false, st);
+        if (rc) return rc;
       }
-      rc = stream_apply(s, c, (float)nbat, false, run->seed, chainkey, nullptr, sdev,
-                        d_kin ? d_kin + (size_t)c * nnew + it : nullptr, st);
-      if (rc) return rc;
       if (samples_host && ns % ke == 0) {
         const int64_t col = ns / ke - 1 - base / ke;
-        CK(cudaMemcpyAsync(samples_host + ((size_t)c * nkept + col) * P, s->theta + (size_t)c * s->Ps, (size_t)P * 4,
-                           cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(samples_host + (size_t)col * P, s->theta, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+      }
+    } else {
+      for (int c = 0; c < C; ++c) {
+        StreamRecord rec = record_of(c);
+        rc = stream_update_once(s, run, c, (float)nbat, rec, false, st);
+        if (rc) return rc;
+        if (samples_host && ns % ke == 0) {
+          const int64_t col = ns / ke - 1 - base / ke;
+          CK(cudaMemcpyAsync(samples_host + ((size_t)c * nkept + col) * P, s->theta + (size_t)c * s->Ps, (size_t)P * 4,
+                             cudaMemcpyDeviceToHost, st));
+        }
       }
     }
     s->gstep += 1;
-    s->launches += 12;
+    s->launches += use_graph ? 1 : 16;
     if ((it & 63) == 63) CK(cudaStreamSynchronize(st));  // bound the launch queue; also paces the progress counter
     *s->progress_host = (unsigned long long)s->gstep;
   }
@@ -1395,6 +1590,10 @@ static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nstep
     CK(cudaMemcpyAsync(kinetic_host, d_kin, (size_t)C * nnew * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     cudaFree(d_kin);
+    if (s->upd_graph) {  // the graph recorded into d_kin
+      cudaGraphExecDestroy(s->upd_graph);
+      s->upd_graph = nullptr;
+    }
   }
   return BFX_OK;
 }
@@ -1437,7 +1636,7 @@ int32_t bfx_sampler_step_injected(bfx_sampler* s, const int64_t* idx, int64_t B,
       b.idx = d_idx + (long long)c * stride;
       b.B = B;
       int32_t rc = stream_grad_local(s, c, b, num_batches, false, m->stream);
-      if (!rc) rc = stream_apply(s, c, num_batches, false, 0, (unsigned)c, d_n + (size_t)c * P, nullptr, nullptr, m->stream);
+      if (!rc) rc = stream_apply(s, c, num_batches, false, 0, (unsigned)c, d_n + (size_t)c * P, StreamRecord{}, m->stream);
       if (rc) {
         cleanup();
         return rc;
@@ -1841,10 +2040,75 @@ int32_t bfx_stream_apply_update(bfx_sampler* s, const bfx_run_desc* run, float n
   if (s->C != 1) return fail(BFX_ERR_BAD_ARG, "a minibatch-sharded sampler carries exactly one chain");
   cudaStream_t cs = stream_handle ? (cudaStream_t)stream_handle : m->stream;
   // chain key 0 on every rank: identical Philox streams keep the replicated theta / p / xi bit-identical
-  int32_t st = stream_apply(s, 0, num_batches, true, run->seed, 0u, nullptr, sample_dev, nullptr, cs, buf_dev);
+  StreamRecord rec;
+  rec.sample_dev = sample_dev;
+  int32_t st = stream_apply(s, 0, num_batches, true, run->seed, 0u, nullptr, rec, cs, buf_dev);
   if (st) return st;
   s->gstep += 1;
-  s->launches += 12;
+  s->launches += 16;
+  return BFX_OK;
+}
+
+// ---- communicator of a minibatch-sharded chain ----------------------------------------------------------
+int32_t bfx_comm_unique_id(void* id_out) {
+  if (!id_out) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(BFX_ERR_UNSUPPORTED, "NCCL could not be loaded (set BFX_NCCL_LIB to libnccl.so.2)");
+  NcclId id;
+  const int r = api->GetUniqueId(&id);
+  if (r != 0) return fail(BFX_ERR_CUDA, std::string("ncclGetUniqueId: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+  std::memcpy(id_out, &id, sizeof id);
+  return BFX_OK;
+}
+
+int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, int32_t rank) {
+  if (!s || !id) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(BFX_ERR_BAD_ARG, "bad rank / nranks");
+  if (!s->m->stream_regime) return fail(BFX_ERR_UNSUPPORTED, "minibatch sharding is implemented for the large-P (stream) regime");
+  if (s->C != 1) return fail(BFX_ERR_BAD_ARG, "a minibatch-sharded sampler carries exactly one chain");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(BFX_ERR_UNSUPPORTED, "NCCL could not be loaded (set BFX_NCCL_LIB to libnccl.so.2)");
+  CK(cudaSetDevice(s->device));
+  if (s->comm) {
+    api->CommDestroy(s->comm);
+    s->comm = nullptr;
+  }
+  NcclId nid;
+  std::memcpy(&nid, id, sizeof nid);
+  void* comm = nullptr;
+  const int r = api->CommInitRank(&comm, nranks, nid, rank);
+  if (r != 0) return fail(BFX_ERR_CUDA, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+  s->comm = comm;
+  s->comm_rank = rank;
+  s->comm_nranks = nranks;
+  if (s->upd_graph) {
+    cudaGraphExecDestroy(s->upd_graph);
+    s->upd_graph = nullptr;
+  }
+  return BFX_OK;
+}
+
+int32_t bfx_sampler_comm_destroy(bfx_sampler* s) {
+  if (!s) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (s->comm) {
+    CK(cudaSetDevice(s->device));
+    if (s->m->stream) cudaStreamSynchronize(s->m->stream);
+    if (s->adv_event) cudaEventSynchronize(s->adv_event);
+    if (NcclApi* api = nccl_api()) api->CommDestroy(s->comm);
+    s->comm = nullptr;
+  }
+  if (s->upd_graph) {
+    cudaGraphExecDestroy(s->upd_graph);
+    s->upd_graph = nullptr;
+  }
+  s->comm_rank = 0;
+  s->comm_nranks = 1;
+  return BFX_OK;
+}
+
+int32_t bfx_sampler_graph_replays(const bfx_sampler* s, int64_t* n) {
+  if (!s || !n) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  *n = s->graph_replays;
   return BFX_OK;
 }
 

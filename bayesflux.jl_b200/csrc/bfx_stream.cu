@@ -199,28 +199,109 @@ __global__ void k_rowsum_final(const float* __restrict__ part, int nout, int nsl
   g[o] += s;
 }
 
-__global__ void k_gather(const float* __restrict__ x, const float* __restrict__ y, StreamBatch b, long long c0, int nc,
-                         int d, float* __restrict__ X, float* __restrict__ yb, __nv_bfloat16* __restrict__ xhi,
-                         __nv_bfloat16* __restrict__ xlo) {
+
+// =====================================================================================================
+// deterministic grid-wide reductions: every block leaves its partial sums in sc->part[block], the last block to
+// arrive folds them in block order.  The ticket wraps to zero by itself (atomicInc), so consecutive kernels on the
+// stream reuse it.  Results are bit-identical from run to run and across the replicas of a sharded chain.
+// =====================================================================================================
+__device__ __forceinline__ bool grid_last(unsigned* ticket) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  return s_last != 0;
+}
+
+__device__ __forceinline__ bool grid_sum2(double v0, double v1, StreamScalars* sc, unsigned* ticket, double (&out)[2]) {
+  __shared__ double r0[32], r1[32], tot[2];
+  for (int o = 16; o > 0; o >>= 1) {
+    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { r0[w] = v0; r1[w] = v1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d0 = 0, d1 = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { d0 += r0[i]; d1 += r1[i]; }
+    sc->part[blockIdx.x][0] = d0;
+    sc->part[blockIdx.x][1] = d1;
+  }
+  if (!grid_last(ticket)) return false;
+  __threadfence();
+  if (w == 0) {
+    double d0 = 0, d1 = 0;
+    for (int i = lane; i < (int)gridDim.x; i += 32) {
+      d0 += __ldcg(&sc->part[i][0]);
+      d1 += __ldcg(&sc->part[i][1]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    }
+    if (lane == 0) { tot[0] = d0; tot[1] = d1; }
+  }
+  __syncthreads();
+  out[0] = tot[0];
+  out[1] = tot[1];
+  return true;
+}
+
+// permutation key of (seed, chain-or-shared, epoch): same derivation as perm_keys in bfx_kernels_impl.cuh
+__device__ __forceinline__ void stream_perm_keys(unsigned long long seed, unsigned chainkey, unsigned long long epoch,
+                                                 unsigned& k0, unsigned& k1) {
+  const uint4 r = philox4x32_10(make_uint4((unsigned)epoch, (unsigned)(epoch >> 32), chainkey, 0x5eedba7cu),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  k0 = r.x;
+  k1 = r.y;
+}
+
+// the observations of this evaluation; returns the number of valid columns (a scheduled batch may be the short
+// last one of its epoch)
+__device__ __forceinline__ long long resolve_batch(const StreamBatch& b, const StreamScalars* sc, BatchSrc& bs) {
+  bs.idx = b.idx;
+  bs.n = b.n;
+  bs.full = b.full;
+  bs.shuffle = b.shuffle;
+  bs.first = 0;
+  bs.k0 = bs.k1 = 0;
+  if (!b.scheduled) return b.B;
+  const unsigned long long g = b.gstep >= 0 ? (unsigned long long)b.gstep : (unsigned long long)sc->gstep;
+  const unsigned long long epoch = g / (unsigned long long)b.nbat, k = g % (unsigned long long)b.nbat;
+  bs.first = (long long)k * b.Bsched;
+  const long long rem = b.n - bs.first;
+  if (b.shuffle) stream_perm_keys(b.seed, b.chainkey, epoch, bs.k0, bs.k1);
+  return rem < b.Bsched ? rem : b.Bsched;
+}
+
+__global__ void k_gather(const float* __restrict__ x, const float* __restrict__ y, StreamBatch b, const StreamScalars* sc,
+                         long long c0, int nc, int d, float* __restrict__ X, float* __restrict__ yb,
+                         __nv_bfloat16* __restrict__ xhi, __nv_bfloat16* __restrict__ xlo) {
   // one warp per column: the d features of an observation are contiguous in x
   const int lane = threadIdx.x & 31;
   const long long col = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (col >= nc) return;
   BatchSrc bs;
-  bs.idx = b.idx; bs.n = b.n; bs.first = b.first; bs.k0 = b.k0; bs.k1 = b.k1; bs.shuffle = b.shuffle; bs.full = b.full;
-  const long long o = batch_obs(bs, c0 + col);
+  const long long Bk = resolve_batch(b, sc, bs);
+  const bool valid = c0 + col < Bk;  // columns past a short batch are zero (they carry no likelihood weight either)
+  const long long o = valid ? batch_obs(bs, c0 + col) : 0;
   for (int f = lane; f < d; f += 32) {
-    const float v = __ldg(x + o * d + f);
-    X[col * d + f] = v;
+    const float v = valid ? __ldg(x + o * d + f) : 0.f;
+    if (X) X[col * d + f] = v;
     if (xhi) {
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
       xhi[col * d + f] = h;
       xlo[col * d + f] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
   }
-  if (lane == 0) yb[col] = __ldg(y + o);
+  if (lane == 0) yb[col] = valid ? __ldg(y + o) : 0.f;
 }
 
+// likelihood on the network output (FP32 path; the tensor-core path fuses this into k_head)
 __global__ void k_like(StreamModel M, const float* __restrict__ theta, const float* __restrict__ out, const float* __restrict__ yb,
                        int nc, float nb, int out_act, float* __restrict__ dl, StreamScalars* sc) {
   const float inv_sigma = 1.f / expf(theta[M.P - 1]);
@@ -241,21 +322,148 @@ __global__ void k_like(StreamModel M, const float* __restrict__ theta, const flo
     }
     dl[b] = d * act_deriv_from_out(out_act, yh);
   }
-  __shared__ double r0[32], r1[32];
-  double d0 = s0, d1 = s1;
-  for (int o = 16; o > 0; o >>= 1) {
-    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+  double tot[2];
+  if (grid_sum2((double)s0, (double)s1, sc, &sc->ticket2, tot) && threadIdx.x == 0) {
+    sc->ds0 += tot[0];
+    sc->ds1 += tot[1];
+    sc->bcount += (double)nc;
   }
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Fused head of the tensor-core path: the 1-wide output layer on BF16-split activations, the likelihood, and
+// the delta of the last hidden layer.  Per batch column b (one warp per column, 8 columns per warp, 64 per block):
+//   yhat = act(w . a_b + b0),  dl = num_batches * dloglike/dyhat * act'(yhat)        (rows a8 / a9 of SURVEY.md 8a)
+//   D[i, b] = w[i] * dl * act_prev'(a[i, b])                                         (BF16 halves, for the GEMMs)
+// and per block the partial sums  dW_out[i] = sum_b dl a[i, b],  rs[i] = sum_b D[i, b] (bias gradient of the last
+// hidden layer),  db_out = sum_b dl  into part[block][2 nin + 1]; the likelihood sums go through the grid reduction.
+// -----------------------------------------------------------------------------------------------------
+constexpr int HEAD_COLS = 64, HEAD_R = 8;  // lane l owns i = 2 l + 64 r + {0, 1}, r < HEAD_R, per chunk of 512 inputs
+
+__global__ void __launch_bounds__(256) k_head(StreamModel M, const float* __restrict__ theta, const __nv_bfloat16* __restrict__ ahi,
+                                              const __nv_bfloat16* __restrict__ alo, const float* __restrict__ yb, int nin, int nc,
+                                              long long nvalid_host, StreamBatch bdesc, long long c0, float nb, int out_act,
+                                              int act_prev, long long w_off, long long b_off, int want_grad, float* __restrict__ yhat,
+                                              __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo,
+                                              float* __restrict__ part, StreamScalars* sc) {
+  extern __shared__ float red[];  // [8 warps][2 * 512]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { r0[w] = d0; r1[w] = d1; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    d0 = 0; d1 = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { d0 += r0[i]; d1 += r1[i]; }
-    atomicAdd(&sc->ds0, d0);
-    atomicAdd(&sc->ds1, d1);
-    if (blockIdx.x == 0) atomicAdd(&sc->bcount, (double)nc);
+  const float* wv = theta + w_off;
+  const float b0 = theta[b_off];
+  const float inv_sigma = 1.f / expf(theta[M.P - 1]);
+  long long nvalid = nvalid_host;
+  if (bdesc.scheduled) {  // a scheduled batch may be the short last one of its epoch
+    BatchSrc bs;
+    nvalid = resolve_batch(bdesc, sc, bs) - c0;
+  }
+  const int col0 = blockIdx.x * HEAD_COLS;
+  float dlc[8], s0 = 0.f, s1 = 0.f, sdl = 0.f;
+  // ---- phase A: network output and likelihood delta of this warp's 8 columns
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const int b = col0 + w + 8 * j;
+    dlc[j] = 0.f;
+    if (b >= nc) continue;
+    const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(ahi + (long long)b * nin);
+    const __nv_bfloat162* pl = reinterpret_cast<const __nv_bfloat162*>(alo + (long long)b * nin);
+    float acc = 0.f;
+    for (int i2 = lane; i2 < nin / 2; i2 += 32) {
+      const float2 h = __bfloat1622float2(ph[i2]), l = __bfloat1622float2(pl[i2]);
+      const float2 ww = *reinterpret_cast<const float2*>(wv + 2 * i2);
+      acc = fmaf(ww.x, h.x + l.x, acc);
+      acc = fmaf(ww.y, h.y + l.y, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float yh = act_apply(out_act, acc + b0);
+    if (lane == 0 && yhat) yhat[b] = yh;
+    if (b < nvalid) {
+      const float z = (yb[b] - yh) * inv_sigma;
+      float d;
+      if (M.like_kind == LK_NORMAL) {
+        s0 += z * z;
+        d = nb * z * inv_sigma;
+      } else {
+        const float zz = z * z;
+        const float tw = (M.nu + 1.f) * z / (M.nu + zz);
+        s0 += log1pf(zz / M.nu);
+        s1 += tw * z;
+        d = nb * tw * inv_sigma;
+      }
+      dlc[j] = d * act_deriv_from_out(out_act, yh);
+      sdl += dlc[j];
+    }
+  }
+  // ---- phase B: delta of the last hidden layer and the partial gradient sums, 512 inputs at a time
+  if (want_grad) {
+    float* mypart = part + (long long)blockIdx.x * (2 * nin + 1);
+    for (int ic = 0; ic < nin; ic += 64 * HEAD_R) {
+      float dw[2 * HEAD_R], rs[2 * HEAD_R];
+#pragma unroll
+      for (int r = 0; r < 2 * HEAD_R; ++r) dw[r] = rs[r] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        const int b = col0 + w + 8 * j;
+        if (b >= nc) continue;
+        const float dl = dlc[j];
+#pragma unroll
+        for (int r = 0; r < HEAD_R; ++r) {
+          const int i = ic + 2 * lane + 64 * r;
+          if (i < nin) {
+            const long long e = (long long)b * nin + i;
+            const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ahi + e));
+            const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(alo + e));
+            const float a0 = h.x + l.x, a1 = h.y + l.y;
+            const float2 ww = *reinterpret_cast<const float2*>(wv + i);
+            const float d0 = ww.x * dl * act_deriv_from_out(act_prev, a0), d1 = ww.y * dl * act_deriv_from_out(act_prev, a1);
+            const __nv_bfloat162 dh = __floats2bfloat162_rn(d0, d1);
+            const float2 dhf = __bfloat1622float2(dh);
+            *reinterpret_cast<__nv_bfloat162*>(dhi + e) = dh;
+            *reinterpret_cast<__nv_bfloat162*>(dlo + e) = __floats2bfloat162_rn(d0 - dhf.x, d1 - dhf.y);
+            dw[2 * r] = fmaf(dl, a0, dw[2 * r]);
+            dw[2 * r + 1] = fmaf(dl, a1, dw[2 * r + 1]);
+            rs[2 * r] += d0;
+            rs[2 * r + 1] += d1;
+          }
+        }
+      }
+      // cross-warp sums in warp order
+#pragma unroll
+      for (int r = 0; r < HEAD_R; ++r) {
+        const int il = 2 * lane + 64 * r;
+        red[w * 1024 + il] = dw[2 * r];
+        red[w * 1024 + il + 1] = dw[2 * r + 1];
+        red[w * 1024 + 512 + il] = rs[2 * r];
+        red[w * 1024 + 512 + il + 1] = rs[2 * r + 1];
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < 1024; e += 256) {
+        const int il = e & 511, which = e >> 9;
+        if (ic + il < nin) {
+          float s = 0.f;
+#pragma unroll
+          for (int ww2 = 0; ww2 < 8; ++ww2) s += red[ww2 * 1024 + e];
+          mypart[which * nin + ic + il] = s;
+        }
+      }
+      __syncthreads();
+    }
+    // db_out of the block (every lane of a warp carries the same dl values)
+    if (lane == 0) red[w] = sdl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i];
+      mypart[2 * nin] = s;
+    }
+  }
+  // likelihood sums: identical on the 32 lanes of a warp (all lanes ran the same scalar code), lane 0 contributes
+  double tot[2];
+  const bool mine = lane == 0;
+  if (grid_sum2(mine ? (double)s0 : 0.0, mine ? (double)s1 : 0.0, sc, &sc->ticket2, tot) && threadIdx.x == 0) {
+    sc->ds0 += tot[0];
+    sc->ds1 += tot[1];
+    const long long v = nvalid < (long long)nc ? (nvalid < 0 ? 0 : nvalid) : (long long)nc;  // valid columns of the chunk
+    sc->bcount += (double)v;
   }
 }
 
@@ -267,20 +475,28 @@ __global__ void k_zero(float* g, long long P, StreamScalars* sc) {
   }
 }
 
-__global__ void k_pack_sums(float* g, long long P, StreamScalars* sc, int to_buffer) {
-  if (to_buffer) {
-    g[P] = (float)sc->ds0;
-    g[P + 1] = (float)sc->ds1;
-    g[P + 2] = (float)sc->bcount;
-  } else {
-    sc->ds0 = g[P];
-    sc->ds1 = g[P + 1];
-    sc->bcount = g[P + 2];
-  }
+__global__ void k_pack_sums(float* g, long long P, const StreamScalars* sc) {
+  g[P] = (float)sc->ds0;
+  g[P + 1] = (float)sc->ds1;
+  g[P + 2] = (float)sc->bcount;
 }
 
-// sigma prior + d/d theta_like from the (globally reduced) likelihood sums: SURVEY.md 8a rows a8 / a9
-__global__ void k_scalar_like(StreamModel M, const float* theta, StreamScalars* sc, float nb) {
+__global__ void k_set_gstep(StreamScalars* sc, long long gstep) { sc->gstep = gstep; }
+
+// prior, sigma prior, d/d theta_like, the value and the norms in one pass:
+//   g_net -= c2 * theta_net;  g_like = glike;  value = nb * loglike + logprior
+__global__ void k_finish(StreamModel M, const float* __restrict__ theta, float* __restrict__ g, StreamScalars* sc, float nb,
+                         int want_grad, int from_buffer) {
+  double ds0, ds1, B;
+  if (from_buffer) {
+    ds0 = (double)g[M.P];
+    ds1 = (double)g[M.P + 1];
+    B = (double)g[M.P + 2];
+  } else {
+    ds0 = sc->ds0;
+    ds1 = sc->ds1;
+    B = sc->bcount;
+  }
   const float sl = theta[M.P - 1];
   const double sigma = (double)expf(sl);
   double lps, dlps;
@@ -291,25 +507,19 @@ __global__ void k_scalar_like(StreamModel M, const float* theta, StreamScalars* 
     lps = M.sprior_const - ((double)M.sprior_a + 1.0) * (double)sl - (double)M.sprior_b / sigma + (double)sl;
     dlps = -(double)M.sprior_a + (double)M.sprior_b / sigma;
   }
-  const double B = sc->bcount;
   double like, dlike;
   if (M.like_kind == LK_NORMAL) {
-    like = -0.5 * B * 1.8378770664093453 - 0.5 * sc->ds0;
-    dlike = sc->ds0;
+    like = -0.5 * B * 1.8378770664093453 - 0.5 * ds0;
+    dlike = ds0;
   } else {
-    like = B * M.tdist_const - 0.5 * ((double)M.nu + 1.0) * sc->ds0;
-    dlike = sc->ds1;
+    like = B * M.tdist_const - 0.5 * ((double)M.nu + 1.0) * ds0;
+    dlike = ds1;
   }
   like += -B * (double)sl + lps;
   dlike += -B + dlps;
-  sc->glike = (float)((double)nb * dlike);
-  sc->value = (double)nb * like;  // the prior is added by k_scalar_value
-}
-
-// g_net -= c2 * theta_net; g_like = glike; sums of theta_net^2 and g^2
-__global__ void k_finish(StreamModel M, const float* __restrict__ theta, float* __restrict__ g, StreamScalars* sc, int want_grad) {
+  const float glike = (float)((double)nb * dlike);
   float a0 = 0.f, a1 = 0.f;
-  const float c2 = M.prior_c2, glike = sc->glike;
+  const float c2 = M.prior_c2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M.P; i += (long long)gridDim.x * blockDim.x) {
     const float th = theta[i];
     float gg;
@@ -324,56 +534,111 @@ __global__ void k_finish(StreamModel M, const float* __restrict__ theta, float* 
       a1 += gg * gg;
     }
   }
-  __shared__ double r0[32], r1[32];
-  double d0 = a0, d1 = a1;
-  for (int o = 16; o > 0; o >>= 1) {
-    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-  }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { r0[w] = d0; r1[w] = d1; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    d0 = 0; d1 = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { d0 += r0[i]; d1 += r1[i]; }
-    atomicAdd(&sc->th2, d0);
-    atomicAdd(&sc->gn2, d1);
+  double tot[2];
+  if (grid_sum2((double)a0, (double)a1, sc, &sc->ticket, tot) && threadIdx.x == 0) {
+    sc->th2 = tot[0];
+    sc->gn2 = tot[1];
+    sc->glike = glike;
+    sc->value = (double)nb * like + M.prior_c0n - 0.5 * (double)M.prior_c2 * tot[0];
+    if (from_buffer) {
+      sc->ds0 = ds0;
+      sc->ds1 = ds1;
+      sc->bcount = B;
+    }
   }
 }
 
-__global__ void k_scalar_value(StreamModel M, StreamScalars* sc) {
-  sc->value += M.prior_c0n - 0.5 * (double)M.prior_c2 * sc->th2;
+// g[dst + e] += sum_z src[z * stride + e] for a list of vectors (split-K partials of the weight gradients, bias-
+// gradient row sums, the head's partial sums), summed in slot order
+struct ReduceItem {
+  long long dst, count, stride;
+  const float* src;
+  int nparts;
+};
+struct ReduceList {
+  int n;
+  long long total;
+  ReduceItem it[3 * BFX_MAX_LAYERS + 4];
+};
+
+__global__ void k_reduce_list(float* __restrict__ g, const ReduceList R) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < R.total; e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    int k = 0;
+    while (k < R.n - 1 && r >= R.it[k].count) {
+      r -= R.it[k].count;
+      ++k;
+    }
+    const ReduceItem& I = R.it[k];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = 0;
+    for (; z + 3 < I.nparts; z += 4) {  // four independent loads in flight, fixed association
+      s0 += I.src[(long long)z * I.stride + r];
+      s1 += I.src[(long long)(z + 1) * I.stride + r];
+      s2 += I.src[(long long)(z + 2) * I.stride + r];
+      s3 += I.src[(long long)(z + 3) * I.stride + r];
+    }
+    for (; z < I.nparts; ++z) s0 += I.src[(long long)z * I.stride + r];
+    g[I.dst + r] += (s0 + s1) + (s2 + s3);
+  }
 }
 
 // =====================================================================================================
 // host orchestration of one evaluation
 // =====================================================================================================
+static bool head_on_tc(const StreamModel& M) {  // 1-wide output layer fed by a tensor-core layer: fused head kernel
+  const int nl = M.nlayers;
+  return M.tc && nl >= 2 && M.L[nl - 1].nout == 1 && M.L[nl - 2].tc && M.L[nl - 1].nin % 8 == 0;
+}
+
+static int tc_ksplit_for(const StreamLayer& L, long long nc) {
+  const int tiles = ((L.nout + 255) / 256) * ((L.nin + 255) / 256);
+  int ks = 1;
+  while (ks < 32 && tiles * ks * 2 <= 74 && (nc / (ks * 2)) >= 256) ks *= 2;
+  return ks;
+}
+
 cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W) {
   W = StreamWork{};
   W.Bc = Bc;
   cudaError_t e = cudaSuccess;
+  const int nl = M.nlayers;
   int maxw = 1;
-  for (int l = 0; l < M.nlayers; ++l) maxw = M.L[l].nout > maxw ? M.L[l].nout : maxw;
-  e = cudaMalloc(&W.act[0], (size_t)M.d_in * Bc * sizeof(float));
-  for (int l = 0; l < M.nlayers && e == cudaSuccess; ++l) e = cudaMalloc(&W.act[l + 1], (size_t)M.L[l].nout * Bc * sizeof(float));
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&W.delta[i], (size_t)maxw * Bc * sizeof(float));
+  for (int l = 0; l < nl; ++l) maxw = M.L[l].nout > maxw ? M.L[l].nout : maxw;
+  const bool htc = head_on_tc(M);
+  // FP32 copies of the activations only where an FP32 kernel reads them
+  // (an FP32 layer reads its input in the forward, weight-gradient and act' kernels and always writes its output)
+  for (int j = 0; j < nl; ++j) W.need_f32[j] = !(M.L[j].tc || (htc && j == nl - 1)) || (j > 0 && !M.L[j - 1].tc);
+  W.need_f32[nl] = 1;
+  bool any_f32_delta = false;
+  for (int l = 0; l < nl; ++l) any_f32_delta |= !M.L[l].tc;
+  for (int j = 0; j <= nl && e == cudaSuccess; ++j) {
+    const long long rows = j == 0 ? M.d_in : M.L[j - 1].nout;
+    if (W.need_f32[j]) e = cudaMalloc(&W.act[j], (size_t)rows * Bc * sizeof(float));
+  }
+  if (any_f32_delta || !M.tc)
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&W.delta[i], (size_t)maxw * Bc * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&W.yb, (size_t)Bc * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&W.dl, (size_t)Bc * sizeof(float));
-  // split-K partials: up to 32 partial copies of the largest [W | b] block
+  // split-K partials of the FP32 weight-gradient GEMMs: up to 32 partial copies of the largest [W | b] block
   long long big = 0;
-  for (int l = 0; l < M.nlayers; ++l) {
+  for (int l = 0; l < nl; ++l) {
+    if (M.L[l].tc) continue;
     long long c = (long long)M.L[l].nout * (M.L[l].nin + 1);
     big = c > big ? c : big;
   }
   W.part_floats = big * 32;
-  if (e == cudaSuccess) e = cudaMalloc(&W.part, (size_t)W.part_floats * sizeof(float));
+  if (e == cudaSuccess && big) e = cudaMalloc(&W.part, (size_t)W.part_floats * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&W.rowpart, (size_t)64 * maxw * sizeof(float));
   if (M.tc) {
-    if (e == cudaSuccess) e = cudaMalloc(&W.act_hi[0], (size_t)M.d_in * Bc * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&W.act_lo[0], (size_t)M.d_in * Bc * 2);
-    for (int l = 0; l < M.nlayers && e == cudaSuccess; ++l) {
-      e = cudaMalloc(&W.act_hi[l + 1], (size_t)M.L[l].nout * Bc * 2);
-      if (e == cudaSuccess) e = cudaMalloc(&W.act_lo[l + 1], (size_t)M.L[l].nout * Bc * 2);
+    for (int j = 0; j < nl && e == cudaSuccess; ++j) {
+      const long long rows = j == 0 ? M.d_in : M.L[j - 1].nout;
+      // halves exist for every activation a tensor-core kernel reads
+      if (!(M.L[j].tc || (htc && j == nl - 1))) continue;
+      e = cudaMalloc(&W.act_hi[j], (size_t)rows * Bc * 2);
+      if (e == cudaSuccess) e = cudaMalloc(&W.act_lo[j], (size_t)rows * Bc * 2);
+      if (e == cudaSuccess && j > 0 && M.L[j - 1].tc && M.L[j - 1].act == A_RELU)
+        e = cudaMalloc(&W.mask[j], (size_t)((Bc + 31) / 32) * rows * sizeof(unsigned));
     }
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
       e = cudaMalloc(&W.delta_hi[i], (size_t)maxw * Bc * 2);
@@ -381,6 +646,17 @@ cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W)
     }
     if (e == cudaSuccess) e = cudaMalloc(&W.w_hi, (size_t)(M.P + 8) * 2);
     if (e == cudaSuccess) e = cudaMalloc(&W.w_lo, (size_t)(M.P + 8) * 2);
+    for (int l = 0; l < nl && e == cudaSuccess; ++l) {
+      if (!M.L[l].tc) continue;
+      W.tc_ksplit[l] = tc_ksplit_for(M.L[l], Bc);
+      e = cudaMalloc(&W.tc_part[l], (size_t)W.tc_ksplit[l] * M.L[l].nout * M.L[l].nin * sizeof(float));
+      W.tc_rowslots[l] = 2 * (int)((Bc + tcg::BN - 1) / tcg::BN);
+      if (e == cudaSuccess) e = cudaMalloc(&W.tc_rowpart[l], (size_t)W.tc_rowslots[l] * M.L[l].nout * sizeof(float));
+    }
+    if (htc && e == cudaSuccess) {
+      W.head_blocks = (int)((Bc + HEAD_COLS - 1) / HEAD_COLS);
+      e = cudaMalloc(&W.head_part, (size_t)W.head_blocks * (2 * M.L[nl - 1].nin + 1) * sizeof(float));
+    }
   }
   if (e != cudaSuccess) stream_work_free(W);
   return e;
@@ -397,6 +673,11 @@ void stream_work_free(StreamWork& W) {
   for (int l = 0; l <= BFX_MAX_LAYERS; ++l) {
     cudaFree(W.act_hi[l]);
     cudaFree(W.act_lo[l]);
+    cudaFree(W.mask[l]);
+  }
+  for (int l = 0; l < BFX_MAX_LAYERS; ++l) {
+    cudaFree(W.tc_part[l]);
+    cudaFree(W.tc_rowpart[l]);
   }
   for (int i = 0; i < 2; ++i) {
     cudaFree(W.delta_hi[i]);
@@ -404,6 +685,7 @@ void stream_work_free(StreamWork& W) {
   }
   cudaFree(W.w_hi);
   cudaFree(W.w_lo);
+  cudaFree(W.head_part);
   W = StreamWork{};
 }
 
@@ -418,16 +700,28 @@ cudaError_t stream_zero(float* g, long long P, StreamScalars* sc, cudaStream_t s
   return cudaGetLastError();
 }
 
-cudaError_t stream_pack_sums(float* g, long long P, StreamScalars* sc, bool to_buffer, cudaStream_t st) {
-  k_pack_sums<<<1, 1, 0, st>>>(g, P, sc, to_buffer ? 1 : 0);
+cudaError_t stream_pack_sums(float* g, long long P, StreamScalars* sc, cudaStream_t st) {
+  k_pack_sums<<<1, 1, 0, st>>>(g, P, sc);
+  return cudaGetLastError();
+}
+
+cudaError_t stream_split_theta(const StreamModel& M, StreamWork& W, const float* theta, cudaStream_t st) {
+  if (!M.tc || !W.w_hi) return cudaSuccess;
+  k_split<<<592, 256, 0, st>>>(theta, M.P, W.w_hi, W.w_lo);
+  return cudaGetLastError();
+}
+
+cudaError_t stream_set_gstep(StreamScalars* sc, long long gstep, cudaStream_t st) {
+  k_set_gstep<<<1, 1, 0, st>>>(sc, gstep);
   return cudaGetLastError();
 }
 
 cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* theta, const float* x, const float* y,
                              const StreamBatch& b, float nb, bool want_grad, float* g, StreamScalars* sc,
-                             cudaStream_t st, float* yhat_out) {
+                             cudaStream_t st, float* yhat_out, bool theta_split_valid) {
   const int nl = M.nlayers;
-  if (M.tc) {  // BF16 halves of theta for the tensor-core layers
+  const bool htc = head_on_tc(M);
+  if (M.tc && !theta_split_valid) {  // BF16 halves of theta for the tensor-core layers
     k_split<<<592, 256, 0, st>>>(theta, M.P, W.w_hi, W.w_lo);
     SCK(cudaGetLastError());
   }
@@ -435,22 +729,29 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
     const int nc = (int)((b.B - c0) < W.Bc ? (b.B - c0) : W.Bc);
     {
       const long long threads = (long long)nc * 32;
-      k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, y, b, c0, nc, M.d_in, W.act[0], W.yb,
-                                                               M.tc ? W.act_hi[0] : nullptr, M.tc ? W.act_lo[0] : nullptr);
+      k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, y, b, sc, c0, nc, M.d_in, W.act[0], W.yb, W.act_hi[0],
+                                                               W.act_lo[0]);
       SCK(cudaGetLastError());
     }
     // forward: act[l+1] (nout x nc) = act(W_l act[l] + b_l)
     for (int l = 0; l < nl; ++l) {
       const StreamLayer& L = M.L[l];
       if (L.tc) {
-        TcGemmArgs t{};
+        tcg::Args t{};
         t.M = L.nout; t.N = nc; t.K = L.nin;
-        t.A = TcOperand{W.w_hi + L.w_off, W.w_lo + L.w_off, L.nout};
-        t.B = TcOperand{W.act_hi[l], W.act_lo[l], L.nin};
-        t.C = W.act[l + 1]; t.Chi = W.act_hi[l + 1]; t.Clo = W.act_lo[l + 1]; t.ldc = L.nout;
+        t.C = W.need_f32[l + 1] ? W.act[l + 1] : nullptr; t.ldc = L.nout;
         t.bias = theta + L.b_off; t.act = L.act;
-        t.kchunk = L.nin; t.part_stride = 0;
-        SCK(tc_gemm_forward(t, st));
+        t.mask_out = W.mask[l + 1];
+        t.kchunk = (L.nin + tcg::BK - 1) / tcg::BK * tcg::BK; t.part_stride = 0;
+        SCK(tc2_forward(t, tcg::Operand{W.w_hi + L.w_off, W.w_lo + L.w_off, L.nout}, tcg::Operand{W.act_hi[l], W.act_lo[l], L.nin},
+                        tcg::Output{W.act_hi[l + 1], W.act_lo[l + 1]}, st));
+        continue;
+      }
+      if (l == nl - 1 && htc) {
+        k_head<<<(nc + HEAD_COLS - 1) / HEAD_COLS, 256, 8 * 1024 * sizeof(float), st>>>(
+            M, theta, W.act_hi[l], W.act_lo[l], W.yb, L.nin, nc, b.B - c0, b, c0, nb, L.act, M.L[l - 1].act, L.w_off, L.b_off,
+            want_grad ? 1 : 0, W.act[nl], W.delta_hi[0], W.delta_lo[0], W.head_part, sc);
+        SCK(cudaGetLastError());
         continue;
       }
       if (L.nout == 1) {
@@ -467,63 +768,82 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
       a.C = W.act[l + 1]; a.ldc = L.nout;
       a.bias = theta + L.b_off; a.act = L.act;
       a.kchunk = L.nin; a.part_stride = 0;
-      if (M.tc && l + 1 < nl && M.L[l + 1].tc) { a.chi = W.act_hi[l + 1]; a.clo = W.act_lo[l + 1]; }
+      if (W.act_hi[l + 1]) { a.chi = W.act_hi[l + 1]; a.clo = W.act_lo[l + 1]; }
       SCK((launch_gemm<true, true, EPI_BIAS_ACT>(a, 1, st)));
     }
-    k_like<<<148, 256, 0, st>>>(M, theta, W.act[nl], W.yb, nc, nb, M.L[nl - 1].act, W.dl, sc);
-    SCK(cudaGetLastError());
+    if (!htc) {
+      k_like<<<148, 256, 0, st>>>(M, theta, W.act[nl], W.yb, nc, nb, M.L[nl - 1].act, W.dl, sc);
+      SCK(cudaGetLastError());
+    }
     if (yhat_out) SCK(cudaMemcpyAsync(yhat_out + c0, W.act[nl], (size_t)nc * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (!want_grad) continue;
     // backward: delta of layer l in D (nout x nc); the output layer's delta is dl (1 x nc)
     const float* D = W.dl;
     const __nv_bfloat16 *Dhi = nullptr, *Dlo = nullptr;
     int ping = 0;
+    int bias_slots = 0;  // > 0: the producer of the current delta left bias-gradient partials in W.tc_rowpart[l]
+    ReduceList R{};
+    auto add_item = [&](long long dst, long long count, const float* src, int nparts, long long stride) {
+      ReduceItem& I = R.it[R.n++];
+      I.dst = dst; I.count = count; I.src = src; I.nparts = nparts; I.stride = stride;
+      R.total += count;
+    };
     for (int l = nl - 1; l >= 0; --l) {
       const StreamLayer& L = M.L[l];
+      if (l == nl - 1 && htc) {
+        // the fused head has produced the delta of layer nl-2 (BF16 halves) and its own partial sums
+        const int hb = (nc + HEAD_COLS - 1) / HEAD_COLS;
+        const long long hs = 2 * L.nin + 1;
+        add_item(L.w_off, L.nin, W.head_part, hb, hs);
+        add_item(M.L[l - 1].b_off, L.nin, W.head_part + L.nin, hb, hs);
+        add_item(L.b_off, 1, W.head_part + 2 * L.nin, hb, hs);
+        D = nullptr; Dhi = W.delta_hi[0]; Dlo = W.delta_lo[0];
+        ping = 1;
+        bias_slots = -1;  // bias gradient of layer nl-2 already listed
+        continue;
+      }
       if (L.tc) {
-        // dW (nout x nin) += D * act[l]^T on the tensor cores, split over the batch; db by a deterministic row sum
+        // dW (nout x nin) = D * act[l]^T on the tensor cores, split over the batch into partials
         const long long cnt = (long long)L.nout * L.nin;
-        int ksplit = 1;
-        const int tiles = ((L.nout + 127) / 128) * ((L.nin + 127) / 128);
-        while (ksplit < 32 && tiles * ksplit < 148 && (nc / (ksplit * 2)) >= 512) ksplit *= 2;
-        TcGemmArgs t{};
+        int ksplit = tc_ksplit_for(L, nc);
+        if (ksplit > W.tc_ksplit[l]) ksplit = W.tc_ksplit[l];
+        int kch = (nc + ksplit - 1) / ksplit;
+        kch = (kch + tcg::BK - 1) / tcg::BK * tcg::BK;
+        ksplit = (nc + kch - 1) / kch;
+        tcg::Args t{};
         t.M = L.nout; t.N = L.nin; t.K = nc;
-        t.A = TcOperand{Dhi, Dlo, L.nout};
-        t.B = TcOperand{W.act_hi[l], W.act_lo[l], L.nin};
-        t.ldc = L.nout;
-        if (ksplit == 1) {
-          t.C = g + L.w_off; t.accumulate = 1; t.kchunk = nc; t.part_stride = 0;
-          SCK(tc_gemm_dw(t, 1, st));
-        } else {
-          long long kch = (nc + ksplit - 1) / ksplit;
-          kch = (kch + 31) / 32 * 32;
-          t.C = W.part; t.accumulate = 0; t.kchunk = kch; t.part_stride = cnt;
-          SCK(tc_gemm_dw(t, ksplit, st));
-          k_reduce_parts<<<(unsigned)((cnt + 255) / 256 < 1184 ? (cnt + 255) / 256 : 1184), 256, 0, st>>>(g + L.w_off, W.part, cnt, ksplit, cnt, 1);
-          SCK(cudaGetLastError());
-        }
-        {
+        t.C = W.tc_part[l]; t.ldc = L.nout; t.accumulate = 0; t.kchunk = kch; t.part_stride = cnt;
+        SCK(tc2_dw(t, tcg::Operand{Dhi, Dlo, L.nout}, tcg::Operand{W.act_hi[l], W.act_lo[l], L.nin}, ksplit, st));
+        add_item(L.w_off, cnt, W.tc_part[l], ksplit, cnt);
+        if (bias_slots > 0) {
+          add_item(L.b_off, L.nout, W.tc_rowpart[l], bias_slots, L.nout);
+        } else if (bias_slots == 0) {  // delta came from an FP32 kernel: deterministic two-level row sum of its FP32 copy
           dim3 grid((L.nout + 31) / 32, 8);
           k_rowsum_part<<<grid, 256, 0, st>>>(D, L.nout, nc, nullptr, W.rowpart);
           SCK(cudaGetLastError());
           k_rowsum_final<<<(L.nout + 127) / 128, 128, 0, st>>>(W.rowpart, L.nout, 64, g + L.b_off);
           SCK(cudaGetLastError());
         }
+        bias_slots = 0;
         if (l > 0) {
           // delta_{l-1} (nin x nc) = (W_l^T D) .* act'(act[l])
-          TcGemmArgs u{};
+          const bool prev_tc = M.L[l - 1].tc;
+          tcg::Args u{};
           u.M = L.nin; u.N = nc; u.K = L.nout;
-          u.A = TcOperand{W.w_hi + L.w_off, W.w_lo + L.w_off, L.nout};
-          u.B = TcOperand{Dhi, Dlo, L.nout};
-          u.C = W.delta[ping]; u.Chi = W.delta_hi[ping]; u.Clo = W.delta_lo[ping]; u.ldc = L.nin;
-          u.aux = W.act[l]; u.ldaux = L.nin; u.act = M.L[l - 1].act;
-          u.kchunk = L.nout; u.part_stride = 0;
-          SCK(tc_gemm_dx(u, st));
+          u.C = prev_tc ? nullptr : W.delta[ping]; u.ldc = L.nin;
+          u.aux_hi = W.act_hi[l]; u.aux_lo = W.act_lo[l]; u.ldaux = L.nin; u.act = M.L[l - 1].act;
+          u.mask_in = W.mask[l];
+          u.rowpart = prev_tc ? W.tc_rowpart[l - 1] : nullptr;
+          u.kchunk = (L.nout + tcg::BK - 1) / tcg::BK * tcg::BK; u.part_stride = 0;
+          SCK(tc2_dx(u, tcg::Operand{W.w_hi + L.w_off, W.w_lo + L.w_off, L.nout}, tcg::Operand{Dhi, Dlo, L.nout},
+                     tcg::Output{prev_tc ? W.delta_hi[ping] : nullptr, prev_tc ? W.delta_lo[ping] : nullptr}, st));
           D = W.delta[ping]; Dhi = W.delta_hi[ping]; Dlo = W.delta_lo[ping];
+          bias_slots = prev_tc ? 2 * ((nc + tcg::BN - 1) / tcg::BN) : 0;
           ping ^= 1;
         }
         continue;
       }
+      const bool prev_tc = l > 0 && M.L[l - 1].tc;
       if (L.nout == 1 && W.rowpart) {
         // 1-wide output layer: dW[i] += sum_b dl[b] act[l][i, b], db += sum_b dl[b]; delta = w dl^T .* act'
         dim3 grid((L.nin + 31) / 32, 8);
@@ -536,11 +856,11 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
         k_rowsum_final<<<1, 32, 0, st>>>(W.rowpart, 1, 64, g + L.b_off);
         SCK(cudaGetLastError());
         if (l > 0) {
-          const bool tcn = M.tc && M.L[l - 1].tc;
           k_out_dx<<<1184, 256, 0, st>>>(theta + L.w_off, D, W.act[l], L.nin, nc, M.L[l - 1].act, W.delta[ping],
-                                        tcn ? W.delta_hi[ping] : nullptr, tcn ? W.delta_lo[ping] : nullptr);
+                                        prev_tc ? W.delta_hi[ping] : nullptr, prev_tc ? W.delta_lo[ping] : nullptr);
           SCK(cudaGetLastError());
           D = W.delta[ping]; Dhi = W.delta_hi[ping]; Dlo = W.delta_lo[ping];
+          bias_slots = 0;
           ping ^= 1;
         }
         continue;
@@ -575,28 +895,32 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
         a.C = W.delta[ping]; a.ldc = L.nin;
         a.aux = W.act[l]; a.ldaux = L.nin; a.act = M.L[l - 1].act;
         a.kchunk = L.nout; a.part_stride = 0;
-        if (M.tc && M.L[l - 1].tc) { a.chi = W.delta_hi[ping]; a.clo = W.delta_lo[ping]; }
+        if (prev_tc) { a.chi = W.delta_hi[ping]; a.clo = W.delta_lo[ping]; }
         SCK((launch_gemm<false, true, EPI_MUL_DACT>(a, 1, st)));
         D = W.delta[ping]; Dhi = W.delta_hi[ping]; Dlo = W.delta_lo[ping];
+        bias_slots = 0;
         ping ^= 1;
       }
+    }
+    if (R.n > 0) {
+      long long blocks = (R.total + 255) / 256;
+      if (blocks > 1184) blocks = 1184;
+      k_reduce_list<<<(unsigned)blocks, 256, 0, st>>>(g, R);
+      SCK(cudaGetLastError());
     }
   }
   return cudaSuccess;
 }
 
 cudaError_t stream_finish(const StreamModel& M, const float* theta, float* g, StreamScalars* sc, float nb, bool want_grad,
-                          cudaStream_t st) {
-  k_scalar_like<<<1, 1, 0, st>>>(M, theta, sc, nb);
-  SCK(cudaGetLastError());
-  k_finish<<<296, 256, 0, st>>>(M, theta, g, sc, want_grad ? 1 : 0);
-  SCK(cudaGetLastError());
-  k_scalar_value<<<1, 1, 0, st>>>(M, sc);
+                          bool from_buffer, cudaStream_t st) {
+  k_finish<<<STREAM_RED_BLOCKS, 256, 0, st>>>(M, theta, g, sc, nb, want_grad ? 1 : 0, from_buffer ? 1 : 0);
   return cudaGetLastError();
 }
 
 // =====================================================================================================
-// sampler updates (flat order, Philox quad q = J / 4)
+// sampler updates (flat order, Philox quad q = J / 4).  Scalars shared by all blocks (step counters, thermostat)
+// are read at the start of a pass and advanced by the last block to finish it.
 // =====================================================================================================
 struct UpdDev {
   SamplerDev S;
@@ -604,17 +928,56 @@ struct UpdDev {
   float *theta, *mom, *minv, *rmsv, *g;
   StreamScalars* sc;
   NoiseKey key;
-  unsigned long long gstep;
+  long long gstep;
   const float* inj;
   float* sample_out;
+  float* samples_base;
+  long long keep_every, kept_origin, ring_slots;
+  float* kinetic_base;
+  long long hist_origin, hist_stride;
   float* kinetic_out;
+  __nv_bfloat16 *w_hi, *w_lo;
 };
 
-__device__ __forceinline__ float noise_flat(const UpdDev& U, unsigned slot, long long J) {
+__device__ __forceinline__ unsigned long long upd_step(const UpdDev& U) {
+  return U.gstep >= 0 ? (unsigned long long)U.gstep : (unsigned long long)U.sc->gstep;
+}
+
+__device__ __forceinline__ float noise_flat(const UpdDev& U, unsigned long long step, unsigned slot, long long J) {
   if (U.inj) return U.inj[J];
-  const float4 z = normal_quad(U.key, U.gstep, slot, (unsigned)(J >> 2));
+  const float4 z = normal_quad(U.key, step, slot, (unsigned)(J >> 2));
   const int e = (int)(J & 3);
   return e == 0 ? z.x : e == 1 ? z.y : e == 2 ? z.z : z.w;
+}
+
+// where the sample recorded by this update goes (ns = nsampled after the update), or nullptr
+__device__ __forceinline__ float* sample_dst(const UpdDev& U, long long ns) {
+  if (U.sample_out) return U.sample_out;
+  if (!U.samples_base) return nullptr;
+  const long long ke = U.keep_every > 0 ? U.keep_every : 1;
+  if (ns % ke != 0) return nullptr;
+  long long slot = ns / ke - 1 - U.kept_origin;
+  if (slot < 0) return nullptr;
+  if (U.ring_slots > 0) slot %= U.ring_slots;
+  return U.samples_base + slot * U.P;
+}
+
+__device__ __forceinline__ void record_kinetic(const UpdDev& U, long long t, float kin) {
+  if (U.kinetic_out) *U.kinetic_out = kin;
+  if (U.kinetic_base) {
+    const long long k = t - 1 - U.hist_origin;
+    if (k >= 0 && k < U.hist_stride) U.kinetic_base[k] = kin;
+  }
+}
+
+__device__ __forceinline__ void store_theta(const UpdDev& U, float* sdst, long long i, float t) {
+  U.theta[i] = t;
+  if (sdst) sdst[i] = t;
+  if (U.w_hi) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(t);
+    U.w_hi[i] = h;
+    U.w_lo[i] = __float2bfloat16_rn(t - __bfloat162float(h));
+  }
 }
 
 template <class F>
@@ -622,63 +985,74 @@ __device__ __forceinline__ void for_flat(long long P, F f) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) f(i);
 }
 
-__device__ __forceinline__ void grid_acc(float a0, float a1, StreamScalars* sc) {
-  __shared__ double r0[32], r1[32];
-  double d0 = a0, d1 = a1;
-  for (int o = 16; o > 0; o >>= 1) {
-    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-  }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { r0[w] = d0; r1[w] = d1; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    d0 = 0; d1 = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { d0 += r0[i]; d1 += r1[i]; }
-    atomicAdd(&sc->acc0, d0);
-    atomicAdd(&sc->acc1, d1);
-  }
-}
-
 // SGLD (sgld.jl:96-112)
 __global__ void k_upd_sgld(UpdDev U) {
-  if (U.sc->status) return;
+  StreamScalars* sc = U.sc;
+  if (sc->status) return;
   const SamplerDev& S = U.S;
-  float alpha = S.stepsize_a * powf(S.stepsize_b + (float)U.sc->t, -S.stepsize_gamma);
+  const unsigned long long step = upd_step(U);
+  const long long t0 = sc->t, ns = sc->nsampled + 1;
+  float alpha = S.stepsize_a * powf(S.stepsize_b + (float)t0, -S.stepsize_gamma);
   alpha = fmaxf(alpha, S.min_stepsize);
-  const float ng = sqrtf((float)U.sc->gn2);
+  const float ng = sqrtf((float)sc->gn2);
   const float ha = 0.5f * alpha * (ng > S.maxnorm ? S.maxnorm / ng : 1.f), sa = sqrtf(alpha);
-  for_flat(U.P, [&](long long i) {
-    const float t = U.theta[i] + ha * U.g[i] + sa * noise_flat(U, 0, i);
-    U.theta[i] = t;
-    if (U.sample_out) U.sample_out[i] = t;
-  });
+  float* sdst = sample_dst(U, ns);
+  for_flat(U.P, [&](long long i) { store_theta(U, sdst, i, U.theta[i] + ha * U.g[i] + sa * noise_flat(U, step, 0, i)); });
+  if (grid_last(&sc->ticket) && threadIdx.x == 0) {
+    sc->nsampled = ns;
+    sc->t = t0 + 1;
+    sc->gstep = (long long)step + 1;
+  }
 }
 
 // SGNHT (sgnht.jl:64-90)
 __global__ void k_upd_sgnht(UpdDev U) {
-  if (U.sc->status) return;
+  StreamScalars* sc = U.sc;
+  if (sc->status) return;
   const SamplerDev& S = U.S;
-  const float l = S.l, xi = U.sc->xi, cn = sqrtf(l * 2.f * S.A);
+  const unsigned long long step = upd_step(U);
+  const long long t0 = sc->t, ns = sc->nsampled + 1;
+  const bool bad_g = sc->gn2 != sc->gn2;  // error("NaN in g") sgnht.jl:70-72: the state stays untouched
+  const float l = S.l, xi = sc->xi, cn = sqrtf(l * 2.f * S.A);
   float a0 = 0.f, a1 = 0.f;
-  for_flat(U.P, [&](long long i) {
-    float p = U.mom[i];
-    p = p - xi * l * p + l * U.g[i] + cn * noise_flat(U, 0, i);
-    U.mom[i] = p;
-    const float t = U.theta[i] + l * p;
-    U.theta[i] = t;
-    if (U.sample_out) U.sample_out[i] = t;
-    a0 += p * p;
-    a1 += (t != t) ? 1.f : 0.f;
-  });
-  grid_acc(a0, a1, U.sc);
+  float* sdst = sample_dst(U, ns);
+  if (!bad_g)
+    for_flat(U.P, [&](long long i) {
+      float p = U.mom[i];
+      p = p - xi * l * p + l * U.g[i] + cn * noise_flat(U, step, 0, i);
+      U.mom[i] = p;
+      const float t = U.theta[i] + l * p;
+      store_theta(U, sdst, i, t);
+      a0 += p * p;
+      a1 += (t != t) ? 1.f : 0.f;
+    });
+  double tot[2];
+  if (grid_sum2((double)a0, (double)a1, sc, &sc->ticket, tot) && threadIdx.x == 0) {
+    if (bad_g) {
+      sc->status = 4;
+    } else {
+      const float kin = (float)tot[0] / (float)U.P;
+      record_kinetic(U, t0, kin);
+      sc->kin = kin;
+      sc->xi = xi + (kin - 1.f) * S.l;
+      if (tot[1] > 0.0) {
+        sc->status = 5;  // error("NaN in θ") sgnht.jl:81-83
+      } else {
+        sc->nsampled = ns;
+        sc->t = t0 + 1;
+      }
+    }
+    sc->gstep = (long long)step + 1;
+  }
 }
 
 // RMSPropMassAdapter (rmspropmassadapter.jl:26-46) on the gradient already in g
 __global__ void k_upd_rmsprop(UpdDev U) {
-  if (U.sc->status || U.sc->ma_t > U.S.ma_adapt_steps) return;
-  const bool first = U.sc->ma_t == 1;
-  const float inv_ng = 1.f / sqrtf((float)U.sc->gn2);
+  StreamScalars* sc = U.sc;
+  if (sc->status || sc->ma_t > U.S.ma_adapt_steps) return;
+  const int ma_t = sc->ma_t;
+  const bool first = ma_t == 1;
+  const float inv_ng = 1.f / sqrtf((float)sc->gn2);
   for_flat(U.P, [&](long long i) {
     const float gg = U.g[i] * inv_ng;
     float V = first ? 1.f : U.rmsv[i];
@@ -686,83 +1060,78 @@ __global__ void k_upd_rmsprop(UpdDev U) {
     U.rmsv[i] = V;
     U.minv[i] = 1.f / (U.S.ma_lambda + sqrtf(V));
   });
+  if (grid_last(&sc->ticket) && threadIdx.x == 0) sc->ma_t = ma_t + 1;
 }
 
-// SGNHTS first half (sgnht-s.jl:95-97)
+// SGNHTS first half: B, A, C half steps (sgnht-s.jl:95-97)
 __global__ void k_upd_sgnhts_a(UpdDev U) {
-  if (U.sc->status) return;
-  const float hl = 0.5f * U.S.l;
+  StreamScalars* sc = U.sc;
+  if (sc->status) return;
+  const SamplerDev& S = U.S;
+  const bool bad_g = sc->gn2 != sc->gn2;  // error("NaN in g") sgnht-s.jl:90-92
+  const float hl = 0.5f * S.l, xi0 = sc->xi;
   float a0 = 0.f;
-  for_flat(U.P, [&](long long i) {
-    const float mi = U.minv ? U.minv[i] : 1.f;
-    const float p = U.mom[i] + hl * U.g[i];
-    U.mom[i] = p;
-    U.theta[i] += hl * mi * p;
-    a0 += p * p * mi;
-  });
-  grid_acc(a0, 0.f, U.sc);
+  if (!bad_g)
+    for_flat(U.P, [&](long long i) {
+      const float mi = U.minv ? U.minv[i] : 1.f;
+      const float p = U.mom[i] + hl * U.g[i];
+      U.mom[i] = p;
+      U.theta[i] += hl * mi * p;
+      a0 += p * p * mi;
+    });
+  double tot[2];
+  if (grid_sum2((double)a0, 0.0, sc, &sc->ticket, tot) && threadIdx.x == 0) {
+    if (bad_g) {
+      sc->status = 4;
+    } else {
+      const float xi = xi0 + S.l / (2.f * S.mu) * ((float)tot[0] - (float)U.P);
+      sc->xi = xi;
+      if (xi != 0.f) {
+        sc->e1 = expf(-xi * S.l);
+        sc->sc = S.sigmaA * sqrtf((1.f - expf(-2.f * xi * S.l)) / (2.f * xi));
+      } else {
+        sc->e1 = 1.f;
+        sc->sc = sqrtf(S.l) * S.sigmaA;
+      }
+    }
+  }
 }
 
-// SGNHTS second half (sgnht-s.jl:98-104)
+// SGNHTS second half: O, C, A (sgnht-s.jl:98-104), recording (:110-111)
 __global__ void k_upd_sgnhts_b(UpdDev U) {
-  if (U.sc->status) return;
-  const float hl = 0.5f * U.S.l, e1 = U.sc->e1, scl = U.sc->sc;
+  StreamScalars* sc = U.sc;
+  const unsigned long long step = upd_step(U);
+  if (sc->status) {  // stopped chain: only the step counter moves on (the host mirror counts every update!)
+    if (grid_last(&sc->ticket) && threadIdx.x == 0) sc->gstep = (long long)step + 1;
+    return;
+  }
+  const SamplerDev& S = U.S;
+  const long long t0 = sc->t, ns = sc->nsampled + 1;
+  const float hl = 0.5f * S.l, e1 = sc->e1, scl = sc->sc, xi0 = sc->xi;
   float a0 = 0.f, a1 = 0.f;
+  float* sdst = sample_dst(U, ns);
   for_flat(U.P, [&](long long i) {
     const float mi = U.minv ? U.minv[i] : 1.f;
-    const float p = e1 * U.mom[i] + scl * rsqrtf(mi) * noise_flat(U, 0, i);
+    const float p = e1 * U.mom[i] + scl * rsqrtf(mi) * noise_flat(U, step, 0, i);
     U.mom[i] = p;
     const float t = U.theta[i] + hl * mi * p;
-    U.theta[i] = t;
-    if (U.sample_out) U.sample_out[i] = t;
+    store_theta(U, sdst, i, t);
     a0 += p * p * mi;
     a1 += (t != t) ? 1.f : 0.f;
   });
-  grid_acc(a0, a1, U.sc);
-}
-
-// scalar bookkeeping between / after the passes.  phase: 0 NaN-in-g check, 1 after SGLD, 2 after SGNHT,
-// 3 between the SGNHTS halves, 4 after SGNHTS, 5 after RMSProp
-__global__ void k_upd_scalar(UpdDev U, int phase) {
-  StreamScalars* sc = U.sc;
-  const SamplerDev& S = U.S;
-  if (sc->status) return;
-  const float n = (float)U.P;
-  if (phase == 0) {
-    if (sc->gn2 != sc->gn2) sc->status = 4;  // error("NaN in g")
-  } else if (phase == 1) {
-    sc->nsampled += 1;
-    sc->t += 1;
-  } else if (phase == 2) {
-    const float kin = (float)sc->acc0 / n;
-    if (U.kinetic_out) *U.kinetic_out = kin;
-    sc->kin = kin;
-    sc->xi = sc->xi + (kin - 1.f) * S.l;
-    if (sc->acc1 > 0.0) { sc->status = 5; return; }
-    sc->nsampled += 1;
-    sc->t += 1;
-  } else if (phase == 3) {
-    const float xi = sc->xi + S.l / (2.f * S.mu) * ((float)sc->acc0 - n);
-    sc->xi = xi;
-    if (xi != 0.f) {
-      sc->e1 = expf(-xi * S.l);
-      sc->sc = S.sigmaA * sqrtf((1.f - expf(-2.f * xi * S.l)) / (2.f * xi));
+  double tot[2];
+  if (grid_sum2((double)a0, (double)a1, sc, &sc->ticket, tot) && threadIdx.x == 0) {
+    sc->xi = xi0 + S.l / (2.f * S.mu) * ((float)tot[0] - (float)U.P);
+    if (tot[1] > 0.0) {
+      sc->status = 5;
     } else {
-      sc->e1 = 1.f;
-      sc->sc = sqrtf(S.l) * S.sigmaA;
+      const float kin = (float)tot[0] / (float)U.P;
+      record_kinetic(U, t0, kin);
+      sc->kin = kin;
+      sc->nsampled = ns;
+      sc->t = t0 + 1;
     }
-    sc->acc0 = 0.0;
-    sc->acc1 = 0.0;
-  } else if (phase == 4) {
-    sc->xi = sc->xi + S.l / (2.f * S.mu) * ((float)sc->acc0 - n);
-    if (sc->acc1 > 0.0) { sc->status = 5; return; }
-    const float kin = (float)sc->acc0 / n;
-    if (U.kinetic_out) *U.kinetic_out = kin;
-    sc->kin = kin;
-    sc->nsampled += 1;
-    sc->t += 1;
-  } else if (phase == 5) {
-    if (sc->ma_t <= S.ma_adapt_steps) sc->ma_t += 1;
+    sc->gstep = (long long)step + 1;
   }
 }
 
@@ -777,28 +1146,23 @@ cudaError_t stream_update(const StreamUpdate& su, cudaStream_t st) {
   U.gstep = su.gstep;
   U.inj = su.inj;
   U.sample_out = su.sample_out;
+  U.samples_base = su.samples_base;
+  U.keep_every = su.keep_every; U.kept_origin = su.kept_origin; U.ring_slots = su.ring_slots;
+  U.kinetic_base = su.kinetic_base; U.hist_origin = su.hist_origin; U.hist_stride = su.hist_stride;
   U.kinetic_out = su.kinetic_out;
-  const int grid = 592;
+  U.w_hi = su.w_hi; U.w_lo = su.w_lo;
+  const int grid = STREAM_RED_BLOCKS;
   switch (U.S.kind) {
     case S_SGLD:
       k_upd_sgld<<<grid, 256, 0, st>>>(U);
-      k_upd_scalar<<<1, 1, 0, st>>>(U, 1);
       break;
     case S_SGNHT:
-      k_upd_scalar<<<1, 1, 0, st>>>(U, 0);
       k_upd_sgnht<<<grid, 256, 0, st>>>(U);
-      k_upd_scalar<<<1, 1, 0, st>>>(U, 2);
       break;
     case S_SGNHTS:
-      if (U.S.madapter_kind == MA_RMSPROP) {
-        k_upd_rmsprop<<<grid, 256, 0, st>>>(U);
-        k_upd_scalar<<<1, 1, 0, st>>>(U, 5);
-      }
-      k_upd_scalar<<<1, 1, 0, st>>>(U, 0);
+      if (U.S.madapter_kind == MA_RMSPROP) k_upd_rmsprop<<<grid, 256, 0, st>>>(U);
       k_upd_sgnhts_a<<<grid, 256, 0, st>>>(U);
-      k_upd_scalar<<<1, 1, 0, st>>>(U, 3);
       k_upd_sgnhts_b<<<grid, 256, 0, st>>>(U);
-      k_upd_scalar<<<1, 1, 0, st>>>(U, 4);
       break;
     default:
       return cudaErrorNotSupported;

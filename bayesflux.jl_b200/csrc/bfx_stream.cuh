@@ -1,18 +1,24 @@
 // Large-P ("stream") regime: theta, gradient and sampler state live in HBM in the reference's flat
-// order, the network is evaluated layer by layer with tiled FP32 GEMMs over the whole minibatch, and
-// every sampler update is one or two fused element-wise passes over theta with grid-wide reductions
-// through double atomics.  Used when theta + gradient + one batch tile do not fit the 227 KB of shared
-// memory of a CTA (configs[2]: P = 559 106), one chain at a time, optionally with the minibatch sharded
-// over ranks (the caller all-reduces the P + 3 floats of StreamState::gbuf between grad and update).
+// order, the network is evaluated layer by layer with GEMMs over the whole minibatch (tcgen05 for the wide
+// layers, bfx_tc_gemm.cuh; a tiled FP32 kernel for the rest), and every sampler update is one or two fused
+// element-wise passes over theta with deterministic grid-wide reductions.  Used when theta + gradient + one
+// batch tile do not fit the 227 KB of shared memory of a CTA (configs[2]: P = 559 106), one chain at a time,
+// optionally with the minibatch sharded over ranks (the P + 3 floats of the gradient buffer are all-reduced
+// between the likelihood part of the evaluation and the update).
+//
+// Everything an update needs beyond its static description is derived ON THE DEVICE from the chain's scalars
+// (global step -> epoch, batch position, permutation keys, Philox counter, sample slot), so that one update is a
+// fixed launch sequence: it is captured once in a CUDA graph and replayed (bfx_api.cu: stream_run).
 //
 // Reference arithmetic: the same rows of SURVEY.md section 8a as the shared-memory regime
 // (src/model/BNN.jl:50-69, src/likelihoods/feedforward.jl:30-43,86-97, src/netpriors/*.jl,
-// src/inference/mcmc/sgld.jl:96-112, sgnht.jl:64-90, sgnht-s.jl:81-116).
+// src/inference/mcmc/sgld.jl:96-112, sgnht.jl:64-90, sgnht-s.jl:81-116, abstract.jl:102-124).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "bfx_common.cuh"
+#include "bfx_tc_gemm_args.cuh"
 
 namespace bfx {
 
@@ -34,6 +40,8 @@ struct StreamModel {
   int tc;  // any layer on the tensor cores
 };
 
+constexpr int STREAM_RED_BLOCKS = 592;  // grid of every element-wise pass (4 x 148); also the partial-sum slots
+
 // device-side scalars of one chain in the stream regime
 struct StreamScalars {
   double ds0, ds1, bcount;   // likelihood sums of the current evaluation (local to this rank before the all-reduce)
@@ -48,17 +56,23 @@ struct StreamScalars {
   int status;
   long long t, nsampled;
   int ma_t;
+  long long gstep;           // update! calls done (device mirror of bfx_sampler::gstep; graph replays count here)
+  unsigned ticket;           // arrival counter of the grid-wide reductions (wraps to 0 by itself)
+  unsigned ticket2;          // same, head kernel
+  double part[STREAM_RED_BLOCKS][2];  // per-block partial sums, folded in block order by the last block to arrive
 };
 
 struct StreamWork {
   long long Bc;               // batch-chunk capacity (columns)
-  float* act[BFX_MAX_LAYERS + 1];  // act[0] = gathered x (d x Bc); act[l+1] = output of layer l (nout x Bc)
-  float* delta[2];            // ping-pong deltas (max width x Bc)
+  float* act[BFX_MAX_LAYERS + 1];  // act[0] = gathered x (d x Bc); act[l+1] = output of layer l (nout x Bc); FP32 copies
+                                   // exist only where an FP32 kernel consumes them (need_f32)
+  int need_f32[BFX_MAX_LAYERS + 1];
+  float* delta[2];            // ping-pong deltas (max width x Bc), FP32 (consumers on the FP32 path only)
   float* yb;                  // [Bc] targets
   float* dl;                  // [Bc] likelihood deltas (scaled by num_batches)
-  float* part;                // split-K partials of the weight-gradient GEMMs
+  float* part;                // split-K partials of the FP32 weight-gradient GEMMs
   long long part_floats;
-  float* rowpart;             // [64][max width] partial row sums (bias gradients of the tensor-core layers)
+  float* rowpart;             // [64][max width] partial row sums (1-wide output layer on the FP32 path)
   // tensor-core mode: BF16 hi / lo halves of the activations, the deltas and theta
   __nv_bfloat16* act_hi[BFX_MAX_LAYERS + 1];
   __nv_bfloat16* act_lo[BFX_MAX_LAYERS + 1];
@@ -66,58 +80,56 @@ struct StreamWork {
   __nv_bfloat16* delta_lo[2];
   __nv_bfloat16* w_hi;
   __nv_bfloat16* w_lo;
+  unsigned* mask[BFX_MAX_LAYERS + 1];   // ReLU sign bits of act[l] (word (b / 32) * width + i), tensor-core layers
+  float* tc_part[BFX_MAX_LAYERS];       // per tensor-core layer: split-K partials of [dW] (ksplit x nout x nin)
+  int tc_ksplit[BFX_MAX_LAYERS];
+  float* tc_rowpart[BFX_MAX_LAYERS];    // per layer: bias-gradient partials (slots x nout) left by whoever produced its delta
+  int tc_rowslots[BFX_MAX_LAYERS];
+  float* head_part;                     // fused head kernel: [blocks][2 * nin + 1] (dW_out, row sums of its delta, db_out)
+  int head_blocks;
 };
 
-// ---- tcgen05 GEMM (bfx_stream_tc.cu) ---------------------------------------------------------------------
-enum { EPI_BIAS_ACT_TC = 0, EPI_MUL_DACT_TC = 1, EPI_PLAIN_TC = 2 };
-// one operand: element (mn, k) lives at hi[mn * ld + k] (K-major) or hi[k * ld + mn] (MN-major)
-struct TcOperand {
-  const __nv_bfloat16* hi;
-  const __nv_bfloat16* lo;
-  long long ld;
-};
-struct TcGemmArgs {
-  int M, N, K;
-  TcOperand A, B;
-  float* C;              // FP32 output; EPI_PLAIN: the split-K partial / accumulate target
-  __nv_bfloat16* Chi;    // BF16 halves of the output (nullptr: not written)
-  __nv_bfloat16* Clo;
-  long long ldc;
-  const float* bias;
-  int act;
-  const float* aux;      // EPI_MUL_DACT: multiply by act'(aux[m + ldaux * n])
-  long long ldaux;
-  int accumulate;        // EPI_PLAIN, single split: C += acc
-  long long kchunk;      // split-K: blockIdx.z handles k in [z * kchunk, ...), writes C + z * part_stride
-  long long part_stride;
-  int debug;             // timing experiments only (env BFX_GEMM_DEBUG): 1 no epilogue stores, 2 no MMA, 4 no loads
-};
-cudaError_t tc_gemm_forward(const TcGemmArgs& g, cudaStream_t st);          // A MN-major (W), B K-major (activations)
-cudaError_t tc_gemm_dx(const TcGemmArgs& g, cudaStream_t st);               // A K-major (W^T), B K-major (delta)
-cudaError_t tc_gemm_dw(const TcGemmArgs& g, int ksplit, cudaStream_t st);   // A MN-major (delta), B MN-major (activations)
+// tcgen05 GEMMs of a Dense layer (bfx_stream_tc.cu)
+cudaError_t tc2_forward(const tcg::Args& g, const tcg::Operand& A, const tcg::Operand& B, const tcg::Output& O, cudaStream_t st);
+cudaError_t tc2_dx(const tcg::Args& g, const tcg::Operand& A, const tcg::Operand& B, const tcg::Output& O, cudaStream_t st);
+cudaError_t tc2_dw(const tcg::Args& g, const tcg::Operand& A, const tcg::Operand& B, int ksplit, cudaStream_t st);
 
 cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W);
 void stream_work_free(StreamWork& W);
 
-// minibatch description for the stream regime
+// The minibatch of one evaluation.  Either explicit (idx / full) or the scheduled one of DataLoader semantics
+// (abstract.jl:102-105): global step g -> epoch g / nbat, batch k = g % nbat = positions [k B, min(n, (k+1) B)) of
+// the epoch's keyed permutation.  gstep >= 0 fixes g on the host, gstep < 0 reads the chain's device counter.
 struct StreamBatch {
   const long long* idx;  // explicit indices or nullptr
-  long long n, first, B; // data-set size, first position inside the epoch permutation, batch size
-  unsigned k0, k1;
-  int shuffle, full;
+  long long n;           // data-set size
+  long long B;           // columns of this evaluation (what the host sizes the launches for)
+  long long Bsched;      // scheduled: the DataLoader batch size (B < Bsched only for the short last batch of an epoch)
+  int full;              // 1: batch = [0, n) in order
+  int scheduled;         // 1: derive first / keys from the step counter
+  long long nbat;
+  long long gstep;
+  unsigned long long seed;
+  unsigned chainkey;
+  int shuffle;
 };
 
 // likelihood part of the evaluation on one minibatch: g[0..Pnet) += num_batches * d loglike / d theta_net
-// (g must be zeroed by the caller when accumulate == 0), sc->ds0/ds1/bcount += sums.
+// (g must be zeroed by the caller), sc->ds0/ds1/bcount += sums.  theta_split_valid: W.w_hi / w_lo already hold
+// the BF16 halves of theta (the sampler updates keep them current).
 cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* theta, const float* x, const float* y,
                              const StreamBatch& b, float nb, bool want_grad, float* g, StreamScalars* sc,
-                             cudaStream_t st, float* yhat_out = nullptr);
-// prior + sigma prior + value + ||g||^2 (all on the device; nothing is synchronised)
+                             cudaStream_t st, float* yhat_out = nullptr, bool theta_split_valid = false);
+// prior + sigma prior + value + ||g||^2 (one kernel; nothing is synchronised).  from_buffer: the likelihood sums are
+// taken from g[P .. P+2] (the all-reduced exchange buffer) instead of the scalars.
 cudaError_t stream_finish(const StreamModel& M, const float* theta, float* g, StreamScalars* sc, float nb, bool want_grad,
-                          cudaStream_t st);
-// gbuf tail <-> scalars (minibatch-sharded chains all-reduce [g ; ds0 ; ds1 ; bcount] as P + 3 floats)
-cudaError_t stream_pack_sums(float* g, long long P, StreamScalars* sc, bool to_buffer, cudaStream_t st);
+                          bool from_buffer, cudaStream_t st);
+// scalars -> gbuf tail (minibatch-sharded chains all-reduce [g ; ds0 ; ds1 ; bcount] as P + 3 floats)
+cudaError_t stream_pack_sums(float* g, long long P, StreamScalars* sc, cudaStream_t st);
 cudaError_t stream_zero(float* g, long long P, StreamScalars* sc, cudaStream_t st);
+cudaError_t stream_set_gstep(StreamScalars* sc, long long gstep, cudaStream_t st);
+// BF16 halves of theta for the tensor-core layers (the sampler updates keep them current afterwards)
+cudaError_t stream_split_theta(const StreamModel& M, StreamWork& W, const float* theta, cudaStream_t st);
 
 struct StreamUpdate {
   const SamplerDev* S;   // host copy
@@ -128,11 +140,19 @@ struct StreamUpdate {
   float* rmsv;
   float* g;
   StreamScalars* sc;
-  unsigned long long seed, gstep;
+  unsigned long long seed;
+  long long gstep;       // >= 0: Philox step on the host's count; < 0: the chain's device counter
   unsigned chain;
   const float* inj;      // injected normals (P floats) or nullptr
+  // recording (all optional): explicit slot, or the device-derived slot of a ring / run buffer
   float* sample_out;     // where to record theta after the update (device, P floats) or nullptr
-  float* kinetic_out;    // device scalar slot or nullptr
+  float* samples_base;   // [slots][P]: sample ns (1-based) with ns % keep_every == 0 goes to slot ns / keep_every - 1 - kept_origin
+  long long keep_every, kept_origin, ring_slots;  // ring_slots > 0: slot modulo ring_slots
+  float* kinetic_base;   // [hist_stride]: entry t - 1 - hist_origin
+  long long hist_origin, hist_stride;
+  float* kinetic_out;    // explicit device scalar slot or nullptr
+  __nv_bfloat16* w_hi;   // BF16 halves of the updated theta for the tensor-core layers (nullptr: not kept)
+  __nv_bfloat16* w_lo;
 };
 cudaError_t stream_update(const StreamUpdate& U, cudaStream_t st);
 

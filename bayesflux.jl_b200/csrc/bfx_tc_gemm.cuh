@@ -26,14 +26,10 @@
 #include <cstring>
 
 #include "bfx_tc.cuh"
+#include "bfx_tc_gemm_args.cuh"
 
 namespace bfx {
 namespace tcg {
-
-constexpr int BM = 128;   // accumulator rows per CTA
-constexpr int BN = 256;   // accumulator columns
-constexpr int BK = 64;    // K per stage = one 128-byte swizzle span of BF16
-constexpr int TILE_A = BM * BK * 2;  // one half (hi or lo) of the A stage, 16 KB
 
 template <int CG>
 struct Cfg {
@@ -42,29 +38,6 @@ struct Cfg {
   static constexpr int STAGE = 2 * TILE_A + 2 * TILE_B;
   static constexpr int STAGES = CG == 2 ? 3 : 2;
   static constexpr int SMEM = STAGES * STAGE + 1024;  // + slack for the 1024-byte alignment of the swizzle atoms
-};
-
-enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1, EPI_PLAIN = 2 };
-
-struct Args {
-  int M, N, K;
-  float* C;              // FP32 output or nullptr.  EPI_PLAIN: the split-K partial / accumulate target
-  long long ldc;
-  int store_split;       // 1: the BF16 hi / lo halves of the output go out through the tensor maps mChi / mClo
-  const float* bias;     // EPI_BIAS_ACT
-  int act;
-  const __nv_bfloat16* aux_hi;  // EPI_MUL_DACT: multiply by act'(aux[m + ldaux * n]), aux = hi + lo
-  const __nv_bfloat16* aux_lo;
-  long long ldaux;
-  // ReLU fast path: the forward epilogue leaves one sign bit per output (word (n / 32) * M + m, bit n % 32), the
-  // input-gradient epilogue reads it back instead of 32 strided BF16 loads per word
-  uint32_t* mask_out;        // EPI_BIAS_ACT with act == A_RELU (nullptr: not written)
-  const uint32_t* mask_in;   // EPI_MUL_DACT with act == A_RELU (nullptr: use aux_hi)
-  float* rowpart;        // EPI_MUL_DACT: per-row sums of the stored tile, slot (2 * blockIdx.y + half) * M + m
-  int accumulate;        // EPI_PLAIN, single split: C += acc
-  int kchunk;            // split-K: blockIdx.z handles k in [z * kchunk, ...), multiple of BK; writes C + z * part_stride
-  long long part_stride;
-  long long* timing;     // BFX_GEMM_TIMING builds: [CTA][8] clock64 marks
 };
 
 BFX_DEV uint32_t cluster_ctarank() {
@@ -377,7 +350,16 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
         }
       }
     };
-    {
+    if (EPI == EPI_PLAIN) {  // FP32 stores only: the plain loop keeps 32 stores in flight per load
+      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * half);
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t ra[32];
+        ld_row32_issue(tbase + 32 * cb, ra);
+        ld_row32_wait(ra);
+        process(cb, ra);
+      }
+    } else {
       const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * half);
       uint32_t ra[32], rb[32];
       ld_row32_issue(tbase, ra);
@@ -448,12 +430,6 @@ inline cudaError_t make_map(CUtensorMap* map, const __nv_bfloat16* base, bool mn
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-struct Operand {
-  const __nv_bfloat16* hi;
-  const __nv_bfloat16* lo;
-  long long ld;
-};
-
 // output halves: element (m, n) at base[m + ldc * n], box 128 rows x 128 columns, no swizzle
 inline cudaError_t make_store_map(CUtensorMap* map, __nv_bfloat16* base, long long M, long long N, long long ldc) {
   EncodeTiledFn fn = encode_fn();
@@ -465,11 +441,6 @@ inline cudaError_t make_store_map(CUtensorMap* map, __nv_bfloat16* base, long lo
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
-
-struct Output {
-  __nv_bfloat16* hi;  // nullptr: the BF16 halves are not written
-  __nv_bfloat16* lo;
-};
 
 template <int CG, bool A_MN, bool B_MN, int EPI>
 inline cudaError_t launch(const Args& g0, const Operand& A, const Operand& B, const Output& O, int ksplit, cudaStream_t st) {
@@ -490,7 +461,15 @@ inline cudaError_t launch(const Args& g0, const Operand& A, const Operand& B, co
   if ((e = make_map(&mBhi, B.hi, B_MN, g.N, g.K, B.ld, C::BROWS)) != cudaSuccess) return e;
   if ((e = make_map(&mBlo, B.lo, B_MN, g.N, g.K, B.ld, C::BROWS)) != cudaSuccess) return e;
   auto kern = k_tc_gemm2<CG, A_MN, B_MN, EPI>;
-  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)) != cudaSuccess) return e;
+  {  // once per device and template instance (function attributes are per context)
+    static unsigned long long done = 0ull;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((done >> (dev & 63)) & 1ull)) {
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)) != cudaSuccess) return e;
+      done |= 1ull << (dev & 63);
+    }
+  }
   cudaLaunchConfig_t cfg{};
   const int mt = (g.M + BM * CG - 1) / (BM * CG);
   cfg.gridDim = dim3((unsigned)(mt * CG), (unsigned)((g.N + BN - 1) / BN), (unsigned)ksplit);

@@ -172,7 +172,19 @@ typedef struct bfx_run_desc {
   uint64_t seed;        /* Philox key */
   int64_t chain_offset; /* global id of this handle's chain 0: chains sharded over several GPUs / ranks
                            keep distinct noise and batch streams (chain c uses stream chain_offset + c) */
+  /* multi-GPU partitioning of the run (no reference counterpart: the reference is one process).
+   *   BFX_SHARD_CHAINS     every rank / device runs its own chains (chain_offset = first global chain id), the data
+   *                        set is replicated, NO collective
+   *   BFX_SHARD_MINIBATCH  ONE chain, every rank holds an equal shard of the data and a replica of the sampler
+   *                        (bfx_sampler_comm_init); batchsize is the LOCAL batch size, chain_offset the rank; each
+   *                        update! all-reduces the P + 3 floats [gradient ; likelihood sums] over NCCL / NVLink inside
+   *                        bfx_mcmc_run / bfx_mcmc_advance, theta stays bit-identical on all ranks
+   * ngpus = number of ranks / devices taking part (informational for CHAINS, checked for MINIBATCH). */
+  int32_t ngpus;      /* default 1 */
+  int32_t shard_mode; /* BFX_SHARD_NONE | BFX_SHARD_CHAINS | BFX_SHARD_MINIBATCH */
 } bfx_run_desc;
+
+enum { BFX_SHARD_NONE = 0, BFX_SHARD_CHAINS = 1, BFX_SHARD_MINIBATCH = 2 };
 
 /* ---- library ----------------------------------------------------------- */
 int32_t bfx_version(void);
@@ -305,6 +317,20 @@ int32_t bfx_stream_grad_local(bfx_sampler* s, const bfx_run_desc* run, float num
                               float* buf_dev, int64_t count);
 int32_t bfx_stream_apply_update(bfx_sampler* s, const bfx_run_desc* run, float num_batches, void* stream_handle,
                                 float* buf_dev, float* sample_dev /* P floats on the device, or NULL */);
+
+/* In-library collective of the minibatch-sharded chain: one NCCL communicator per sampler replica.  NCCL is bound at
+ * run time (dlopen of libnccl.so.2, or the path in $BFX_NCCL_LIB), so a process that already carries NCCL (torch,
+ * NCCL.jl) shares that copy.  Rank 0 creates the 128-byte id, the caller distributes it (MPI, torch.distributed, a
+ * file ...), every rank calls bfx_sampler_comm_init (collective).  With a communicator attached and
+ * run->shard_mode == BFX_SHARD_MINIBATCH, bfx_mcmc_run / bfx_mcmc_advance perform
+ *     local gradient  ->  ncclAllReduce(P + 3 floats) on the engine's stream  ->  replicated update
+ * for every update!, captured together in one CUDA graph per update. */
+#define BFX_COMM_ID_BYTES 128
+int32_t bfx_comm_unique_id(void* id_out /* BFX_COMM_ID_BYTES */);
+int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, int32_t rank);
+int32_t bfx_sampler_comm_destroy(bfx_sampler* s);
+/* number of update! graphs replayed by this sampler so far (stream regime: one cudaGraphLaunch per update!) */
+int32_t bfx_sampler_graph_replays(const bfx_sampler* s, int64_t* n);
 
 /* ---- test hooks: expose the engine's own random streams so the oracle can
  * replay a device run draw for draw -------------------------------------- */
