@@ -97,6 +97,7 @@ SYMBOLS = {
     "bfx_model_regime": [_vp, _pi32],
     "bfx_stream_grad_local": [_vp, C.POINTER(RunDesc), _f32, _vp, _vp, _i64],
     "bfx_stream_apply_update": [_vp, C.POINTER(RunDesc), _f32, _vp, _vp, _vp],
+    "bfx_stream_allreduce": [_vp, _vp, _vp],
     "bfx_comm_unique_id": [_vp],
     "bfx_sampler_comm_init": [_vp, _vp, _i32, _i32],
     "bfx_sampler_comm_destroy": [_vp],

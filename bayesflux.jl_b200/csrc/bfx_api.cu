@@ -2049,6 +2049,15 @@ int32_t bfx_stream_apply_update(bfx_sampler* s, const bfx_run_desc* run, float n
   return BFX_OK;
 }
 
+int32_t bfx_stream_allreduce(bfx_sampler* s, void* stream_handle, float* buf_dev) {
+  if (!s || !buf_dev) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  if (!s->comm) return BFX_OK;  // a single rank: nothing to exchange
+  int32_t st = ensure_stream(s->m);
+  if (st) return st;
+  cudaStream_t cs = stream_handle ? (cudaStream_t)stream_handle : s->m->stream;
+  return stream_allreduce(s, buf_dev, cs);
+}
+
 // ---- communicator of a minibatch-sharded chain ----------------------------------------------------------
 int32_t bfx_comm_unique_id(void* id_out) {
   if (!id_out) return fail(BFX_ERR_BAD_ARG, "NULL argument");

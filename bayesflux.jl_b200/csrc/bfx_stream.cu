@@ -1,6 +1,8 @@
 // Kernels of the large-P ("stream") regime, see bfx_stream.cuh.
 #include "bfx_stream.cuh"
 
+#include <algorithm>
+
 #include "bfx_device.cuh"
 
 namespace bfx {
@@ -234,10 +236,21 @@ __device__ __forceinline__ bool grid_sum2(double v0, double v1, StreamScalars* s
   if (!grid_last(ticket)) return false;
   __threadfence();
   if (w == 0) {
+    // all loads first (independent, in flight together), then a fixed-order sum: lane l owns slots l, l + 32, ...
+    constexpr int NS = (STREAM_RED_BLOCKS + 31) / 32;
+    double a0[NS], a1[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int i = lane + 32 * j;
+      const bool ok = i < (int)gridDim.x;
+      a0[j] = ok ? __ldcg(&sc->part[i][0]) : 0.0;
+      a1[j] = ok ? __ldcg(&sc->part[i][1]) : 0.0;
+    }
     double d0 = 0, d1 = 0;
-    for (int i = lane; i < (int)gridDim.x; i += 32) {
-      d0 += __ldcg(&sc->part[i][0]);
-      d1 += __ldcg(&sc->part[i][1]);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      d0 += a0[j];
+      d1 += a1[j];
     }
     for (int o = 16; o > 0; o >>= 1) {
       d0 += __shfl_xor_sync(0xffffffffu, d0, o);
@@ -338,7 +351,9 @@ __global__ void k_like(StreamModel M, const float* __restrict__ theta, const flo
 // and per block the partial sums  dW_out[i] = sum_b dl a[i, b],  rs[i] = sum_b D[i, b] (bias gradient of the last
 // hidden layer),  db_out = sum_b dl  into part[block][2 nin + 1]; the likelihood sums go through the grid reduction.
 // -----------------------------------------------------------------------------------------------------
-constexpr int HEAD_COLS = 64, HEAD_R = 8;  // lane l owns i = 2 l + 64 r + {0, 1}, r < HEAD_R, per chunk of 512 inputs
+constexpr int HEAD_COLS = 32, HEAD_CPW = 4, HEAD_R = 8;  // 8 warps x 4 columns; lane l owns i = 2 l + 64 r + {0, 1}, r < HEAD_R
+
+__host__ __device__ inline long long head_part_stride(int nin) { return 2LL * nin + 4; }  // [dW_out | row sums | db_out, pad]
 
 __global__ void __launch_bounds__(256) k_head(StreamModel M, const float* __restrict__ theta, const __nv_bfloat16* __restrict__ ahi,
                                               const __nv_bfloat16* __restrict__ alo, const float* __restrict__ yb, int nin, int nc,
@@ -356,73 +371,90 @@ __global__ void __launch_bounds__(256) k_head(StreamModel M, const float* __rest
     BatchSrc bs;
     nvalid = resolve_batch(bdesc, sc, bs) - c0;
   }
-  const int col0 = blockIdx.x * HEAD_COLS;
-  float dlc[8], s0 = 0.f, s1 = 0.f, sdl = 0.f;
-  // ---- phase A: network output and likelihood delta of this warp's 8 columns
-#pragma unroll 1
-  for (int j = 0; j < 8; ++j) {
-    const int b = col0 + w + 8 * j;
-    dlc[j] = 0.f;
-    if (b >= nc) continue;
-    const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(ahi + (long long)b * nin);
-    const __nv_bfloat162* pl = reinterpret_cast<const __nv_bfloat162*>(alo + (long long)b * nin);
-    float acc = 0.f;
+  const int bw = blockIdx.x * HEAD_COLS + HEAD_CPW * w;  // first column of this warp
+  long long colbase[HEAD_CPW];
+#pragma unroll
+  for (int j = 0; j < HEAD_CPW; ++j) colbase[j] = (long long)(bw + j < nc ? bw + j : nc - 1) * nin;  // clamped: loads stay in bounds
+  float dlc[HEAD_CPW], s0 = 0.f, s1 = 0.f, sdl = 0.f;
+  // ---- phase A: network output and likelihood delta of this warp's columns (their loads in flight together)
+  {
+    float acc[HEAD_CPW];
+#pragma unroll
+    for (int j = 0; j < HEAD_CPW; ++j) acc[j] = 0.f;
     for (int i2 = lane; i2 < nin / 2; i2 += 32) {
-      const float2 h = __bfloat1622float2(ph[i2]), l = __bfloat1622float2(pl[i2]);
       const float2 ww = *reinterpret_cast<const float2*>(wv + 2 * i2);
-      acc = fmaf(ww.x, h.x + l.x, acc);
-      acc = fmaf(ww.y, h.y + l.y, acc);
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    const float yh = act_apply(out_act, acc + b0);
-    if (lane == 0 && yhat) yhat[b] = yh;
-    if (b < nvalid) {
-      const float z = (yb[b] - yh) * inv_sigma;
-      float d;
-      if (M.like_kind == LK_NORMAL) {
-        s0 += z * z;
-        d = nb * z * inv_sigma;
-      } else {
-        const float zz = z * z;
-        const float tw = (M.nu + 1.f) * z / (M.nu + zz);
-        s0 += log1pf(zz / M.nu);
-        s1 += tw * z;
-        d = nb * tw * inv_sigma;
+      float2 h[HEAD_CPW], l[HEAD_CPW];
+#pragma unroll
+      for (int j = 0; j < HEAD_CPW; ++j) {
+        h[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ahi + colbase[j] + 2 * i2));
+        l[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(alo + colbase[j] + 2 * i2));
       }
-      dlc[j] = d * act_deriv_from_out(out_act, yh);
-      sdl += dlc[j];
+#pragma unroll
+      for (int j = 0; j < HEAD_CPW; ++j) {
+        acc[j] = fmaf(ww.x, h[j].x + l[j].x, acc[j]);
+        acc[j] = fmaf(ww.y, h[j].y + l[j].y, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HEAD_CPW; ++j) {
+      float a = acc[j];
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      const int b = bw + j;
+      dlc[j] = 0.f;
+      if (b < nc) {
+        const float yh = act_apply(out_act, a + b0);
+        if (lane == 0 && yhat) yhat[b] = yh;
+        if (b < nvalid) {
+          const float z = (yb[b] - yh) * inv_sigma;
+          float d;
+          if (M.like_kind == LK_NORMAL) {
+            s0 += z * z;
+            d = nb * z * inv_sigma;
+          } else {
+            const float zz = z * z;
+            const float tw = (M.nu + 1.f) * z / (M.nu + zz);
+            s0 += log1pf(zz / M.nu);
+            s1 += tw * z;
+            d = nb * tw * inv_sigma;
+          }
+          dlc[j] = d * act_deriv_from_out(out_act, yh);
+          sdl += dlc[j];
+        }
+      }
     }
   }
   // ---- phase B: delta of the last hidden layer and the partial gradient sums, 512 inputs at a time
   if (want_grad) {
-    float* mypart = part + (long long)blockIdx.x * (2 * nin + 1);
+    float* mypart = part + (long long)blockIdx.x * head_part_stride(nin);
     for (int ic = 0; ic < nin; ic += 64 * HEAD_R) {
       float dw[2 * HEAD_R], rs[2 * HEAD_R];
 #pragma unroll
-      for (int r = 0; r < 2 * HEAD_R; ++r) dw[r] = rs[r] = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < 8; ++j) {
-        const int b = col0 + w + 8 * j;
-        if (b >= nc) continue;
-        const float dl = dlc[j];
+      for (int r = 0; r < HEAD_R; ++r) {
+        dw[2 * r] = dw[2 * r + 1] = rs[2 * r] = rs[2 * r + 1] = 0.f;
+        const int i = ic + 2 * lane + 64 * r;
+        if (i < nin) {
+          const float2 ww = *reinterpret_cast<const float2*>(wv + i);
+          float2 h[HEAD_CPW], l[HEAD_CPW];
 #pragma unroll
-        for (int r = 0; r < HEAD_R; ++r) {
-          const int i = ic + 2 * lane + 64 * r;
-          if (i < nin) {
-            const long long e = (long long)b * nin + i;
-            const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ahi + e));
-            const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(alo + e));
-            const float a0 = h.x + l.x, a1 = h.y + l.y;
-            const float2 ww = *reinterpret_cast<const float2*>(wv + i);
-            const float d0 = ww.x * dl * act_deriv_from_out(act_prev, a0), d1 = ww.y * dl * act_deriv_from_out(act_prev, a1);
-            const __nv_bfloat162 dh = __floats2bfloat162_rn(d0, d1);
-            const float2 dhf = __bfloat1622float2(dh);
-            *reinterpret_cast<__nv_bfloat162*>(dhi + e) = dh;
-            *reinterpret_cast<__nv_bfloat162*>(dlo + e) = __floats2bfloat162_rn(d0 - dhf.x, d1 - dhf.y);
-            dw[2 * r] = fmaf(dl, a0, dw[2 * r]);
-            dw[2 * r + 1] = fmaf(dl, a1, dw[2 * r + 1]);
-            rs[2 * r] += d0;
-            rs[2 * r + 1] += d1;
+          for (int j = 0; j < HEAD_CPW; ++j) {
+            h[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ahi + colbase[j] + i));
+            l[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(alo + colbase[j] + i));
+          }
+#pragma unroll
+          for (int j = 0; j < HEAD_CPW; ++j) {
+            if (bw + j < nc) {
+              const float dl = dlc[j];
+              const float a0 = h[j].x + l[j].x, a1 = h[j].y + l[j].y;
+              const float d0 = ww.x * dl * act_deriv_from_out(act_prev, a0), d1 = ww.y * dl * act_deriv_from_out(act_prev, a1);
+              const __nv_bfloat162 dh = __floats2bfloat162_rn(d0, d1);
+              const float2 dhf = __bfloat1622float2(dh);
+              *reinterpret_cast<__nv_bfloat162*>(dhi + colbase[j] + i) = dh;
+              *reinterpret_cast<__nv_bfloat162*>(dlo + colbase[j] + i) = __floats2bfloat162_rn(d0 - dhf.x, d1 - dhf.y);
+              dw[2 * r] = fmaf(dl, a0, dw[2 * r]);
+              dw[2 * r + 1] = fmaf(dl, a1, dw[2 * r + 1]);
+              rs[2 * r] += d0;
+              rs[2 * r + 1] += d1;
+            }
           }
         }
       }
@@ -430,10 +462,8 @@ __global__ void __launch_bounds__(256) k_head(StreamModel M, const float* __rest
 #pragma unroll
       for (int r = 0; r < HEAD_R; ++r) {
         const int il = 2 * lane + 64 * r;
-        red[w * 1024 + il] = dw[2 * r];
-        red[w * 1024 + il + 1] = dw[2 * r + 1];
-        red[w * 1024 + 512 + il] = rs[2 * r];
-        red[w * 1024 + 512 + il + 1] = rs[2 * r + 1];
+        *reinterpret_cast<float2*>(red + w * 1024 + il) = make_float2(dw[2 * r], dw[2 * r + 1]);
+        *reinterpret_cast<float2*>(red + w * 1024 + 512 + il) = make_float2(rs[2 * r], rs[2 * r + 1]);
       }
       __syncthreads();
       for (int e = threadIdx.x; e < 1024; e += 256) {
@@ -520,18 +550,41 @@ __global__ void k_finish(StreamModel M, const float* __restrict__ theta, float* 
   const float glike = (float)((double)nb * dlike);
   float a0 = 0.f, a1 = 0.f;
   const float c2 = M.prior_c2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M.P; i += (long long)gridDim.x * blockDim.x) {
-    const float th = theta[i];
-    float gg;
-    if (i < M.Pnet) {
-      a0 += th * th;
-      gg = g[i] - c2 * th;
+  const long long nq = (M.P + 3) >> 2;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    const long long i = q << 2;
+    const int cnt = M.P - i < 4 ? (int)(M.P - i) : 4;
+    float th[4], gg[4];
+    if (cnt == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(theta + i);
+      const float4 gv = *reinterpret_cast<const float4*>(g + i);
+      th[0] = t.x; th[1] = t.y; th[2] = t.z; th[3] = t.w;
+      gg[0] = gv.x; gg[1] = gv.y; gg[2] = gv.z; gg[3] = gv.w;
     } else {
-      gg = glike;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        th[j] = j < cnt ? theta[i + j] : 0.f;
+        gg[j] = j < cnt ? g[i + j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < cnt) {
+        if (i + j < M.Pnet) {
+          a0 += th[j] * th[j];
+          gg[j] = gg[j] - c2 * th[j];
+        } else {
+          gg[j] = glike;
+        }
+        if (want_grad) a1 += gg[j] * gg[j];
+      }
     }
     if (want_grad) {
-      g[i] = gg;
-      a1 += gg * gg;
+      if (cnt == 4) {
+        *reinterpret_cast<float4*>(g + i) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      } else {
+        for (int j = 0; j < cnt; ++j) g[i + j] = gg[j];
+      }
     }
   }
   double tot[2];
@@ -561,25 +614,47 @@ struct ReduceList {
   ReduceItem it[3 * BFX_MAX_LAYERS + 4];
 };
 
-__global__ void k_reduce_list(float* __restrict__ g, const ReduceList R) {
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < R.total; e += (long long)gridDim.x * blockDim.x) {
-    long long r = e;
-    int k = 0;
-    while (k < R.n - 1 && r >= R.it[k].count) {
-      r -= R.it[k].count;
-      ++k;
+// (the list is a __grid_constant__: indexing a by-value parameter dynamically would copy it to local memory per thread)
+__global__ void __launch_bounds__(256) k_reduce_list(float* __restrict__ g, const __grid_constant__ ReduceList R) {
+  const ReduceItem& I = R.it[blockIdx.y];
+  const bool vec = (I.count & 3) == 0 && (I.stride & 3) == 0 && (I.dst & 3) == 0 &&
+                   (reinterpret_cast<unsigned long long>(I.src) & 15ull) == 0;
+  if (vec) {
+    const long long nq = I.count >> 2;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+      const float4* src = reinterpret_cast<const float4*>(I.src) + q;
+      const long long sq = I.stride >> 2;
+      float4 acc = *reinterpret_cast<const float4*>(g + I.dst + 4 * q);
+      int z = 0;
+      for (; z + 7 < I.nparts; z += 8) {  // eight independent 16-byte loads in flight, summed in slot order
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcs(src + (long long)(z + j) * sq);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+      }
+      for (; z < I.nparts; ++z) {
+        const float4 v = __ldcs(src + (long long)z * sq);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(g + I.dst + 4 * q) = acc;
     }
-    const ReduceItem& I = R.it[k];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int z = 0;
-    for (; z + 3 < I.nparts; z += 4) {  // four independent loads in flight, fixed association
-      s0 += I.src[(long long)z * I.stride + r];
-      s1 += I.src[(long long)(z + 1) * I.stride + r];
-      s2 += I.src[(long long)(z + 2) * I.stride + r];
-      s3 += I.src[(long long)(z + 3) * I.stride + r];
+  } else if (I.count <= 8) {
+    // a handful of scalars with many partials (the head's db): one warp per element, lanes take slots l, l + 32, ...
+    if (blockIdx.x != 0) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (long long r = w; r < I.count; r += blockDim.x >> 5) {
+      float acc = 0.f;
+      for (int z = lane; z < I.nparts; z += 32) acc += I.src[(long long)z * I.stride + r];
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) g[I.dst + r] += acc;
     }
-    for (; z < I.nparts; ++z) s0 += I.src[(long long)z * I.stride + r];
-    g[I.dst + r] += (s0 + s1) + (s2 + s3);
+  } else {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < I.count; r += (long long)gridDim.x * blockDim.x) {
+      float acc = g[I.dst + r];
+      for (int z = 0; z < I.nparts; ++z) acc += I.src[(long long)z * I.stride + r];
+      g[I.dst + r] = acc;
+    }
   }
 }
 
@@ -655,7 +730,7 @@ cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W)
     }
     if (htc && e == cudaSuccess) {
       W.head_blocks = (int)((Bc + HEAD_COLS - 1) / HEAD_COLS);
-      e = cudaMalloc(&W.head_part, (size_t)W.head_blocks * (2 * M.L[nl - 1].nin + 1) * sizeof(float));
+      e = cudaMalloc(&W.head_part, (size_t)W.head_blocks * head_part_stride(M.L[nl - 1].nin) * sizeof(float));
     }
   }
   if (e != cudaSuccess) stream_work_free(W);
@@ -793,7 +868,7 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
       if (l == nl - 1 && htc) {
         // the fused head has produced the delta of layer nl-2 (BF16 halves) and its own partial sums
         const int hb = (nc + HEAD_COLS - 1) / HEAD_COLS;
-        const long long hs = 2 * L.nin + 1;
+        const long long hs = head_part_stride(L.nin);
         add_item(L.w_off, L.nin, W.head_part, hb, hs);
         add_item(M.L[l - 1].b_off, L.nin, W.head_part + L.nin, hb, hs);
         add_item(L.b_off, 1, W.head_part + 2 * L.nin, hb, hs);
@@ -903,9 +978,11 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
       }
     }
     if (R.n > 0) {
-      long long blocks = (R.total + 255) / 256;
-      if (blocks > 1184) blocks = 1184;
-      k_reduce_list<<<(unsigned)blocks, 256, 0, st>>>(g, R);
+      long long maxq = 1;
+      for (int k = 0; k < R.n; ++k) maxq = std::max(maxq, (R.it[k].count + 3) / 4);
+      long long blocks = (maxq + 255) / 256;
+      if (blocks > 296) blocks = 296;
+      k_reduce_list<<<dim3((unsigned)blocks, (unsigned)R.n), 256, 0, st>>>(g, R);
       SCK(cudaGetLastError());
     }
   }
@@ -943,11 +1020,35 @@ __device__ __forceinline__ unsigned long long upd_step(const UpdDev& U) {
   return U.gstep >= 0 ? (unsigned long long)U.gstep : (unsigned long long)U.sc->gstep;
 }
 
-__device__ __forceinline__ float noise_flat(const UpdDev& U, unsigned long long step, unsigned slot, long long J) {
-  if (U.inj) return U.inj[J];
-  const float4 z = normal_quad(U.key, step, slot, (unsigned)(J >> 2));
-  const int e = (int)(J & 3);
-  return e == 0 ? z.x : e == 1 ? z.y : e == 2 ? z.z : z.w;
+// ---- quad-wise access: thread = four consecutive parameters (one Philox call, 16-byte loads / stores); the last
+// quad of an odd-sized theta is handled element-wise ------------------------------------------------------------
+__device__ __forceinline__ void ldq(const float* p, long long i, int cnt, float (&v)[4]) {
+  if (cnt == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + i);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = j < cnt ? p[i + j] : 0.f;
+  }
+}
+__device__ __forceinline__ void stq(float* p, long long i, int cnt, const float (&v)[4]) {
+  if (cnt == 4 && (reinterpret_cast<unsigned long long>(p + i) & 15ull) == 0) {
+    *reinterpret_cast<float4*>(p + i) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < cnt) p[i + j] = v[j];
+  }
+}
+__device__ __forceinline__ void noise_quad(const UpdDev& U, unsigned long long step, unsigned slot, long long i, int cnt,
+                                           float (&z)[4]) {
+  if (U.inj) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = j < cnt ? U.inj[i + j] : 0.f;
+    return;
+  }
+  const float4 n = normal_quad(U.key, step, slot, (unsigned)(i >> 2));
+  z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w;
 }
 
 // where the sample recorded by this update goes (ns = nsampled after the update), or nullptr
@@ -970,34 +1071,64 @@ __device__ __forceinline__ void record_kinetic(const UpdDev& U, long long t, flo
   }
 }
 
-__device__ __forceinline__ void store_theta(const UpdDev& U, float* sdst, long long i, float t) {
-  U.theta[i] = t;
-  if (sdst) sdst[i] = t;
+// the updated theta: state, optional recorded sample, optional BF16 halves for the tensor-core layers
+__device__ __forceinline__ void store_theta(const UpdDev& U, float* sdst, long long i, int cnt, const float (&t)[4]) {
+  stq(U.theta, i, cnt, t);
+  if (sdst) stq(sdst, i, cnt, t);
   if (U.w_hi) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(t);
-    U.w_hi[i] = h;
-    U.w_lo[i] = __float2bfloat16_rn(t - __bfloat162float(h));
+    if (cnt == 4) {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(t[0] - f0.x, t[1] - f0.y), l1 = __floats2bfloat162_rn(t[2] - f1.x, t[3] - f1.y);
+      uint2 hw, lw;
+      hw.x = *reinterpret_cast<const unsigned*>(&h0); hw.y = *reinterpret_cast<const unsigned*>(&h1);
+      lw.x = *reinterpret_cast<const unsigned*>(&l0); lw.y = *reinterpret_cast<const unsigned*>(&l1);
+      *reinterpret_cast<uint2*>(U.w_hi + i) = hw;
+      *reinterpret_cast<uint2*>(U.w_lo + i) = lw;
+    } else {
+      for (int j = 0; j < cnt; ++j) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(t[j]);
+        U.w_hi[i + j] = h;
+        U.w_lo[i + j] = __float2bfloat16_rn(t[j] - __bfloat162float(h));
+      }
+    }
   }
 }
 
 template <class F>
-__device__ __forceinline__ void for_flat(long long P, F f) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) f(i);
+__device__ __forceinline__ void for_quads(long long P, F f) {
+  const long long nq = (P + 3) >> 2;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    const long long i = q << 2;
+    const long long rem = P - i;
+    f(i, rem < 4 ? (int)rem : 4);
+  }
 }
 
 // SGLD (sgld.jl:96-112)
-__global__ void k_upd_sgld(UpdDev U) {
+__global__ void __launch_bounds__(256) k_upd_sgld(UpdDev U) {
   StreamScalars* sc = U.sc;
-  if (sc->status) return;
-  const SamplerDev& S = U.S;
   const unsigned long long step = upd_step(U);
+  if (sc->status) {  // stopped chain: only the step counter moves on (the host mirror counts every update!)
+    if (grid_last(&sc->ticket) && threadIdx.x == 0) sc->gstep = (long long)step + 1;
+    return;
+  }
+  const SamplerDev& S = U.S;
   const long long t0 = sc->t, ns = sc->nsampled + 1;
   float alpha = S.stepsize_a * powf(S.stepsize_b + (float)t0, -S.stepsize_gamma);
   alpha = fmaxf(alpha, S.min_stepsize);
   const float ng = sqrtf((float)sc->gn2);
   const float ha = 0.5f * alpha * (ng > S.maxnorm ? S.maxnorm / ng : 1.f), sa = sqrtf(alpha);
   float* sdst = sample_dst(U, ns);
-  for_flat(U.P, [&](long long i) { store_theta(U, sdst, i, U.theta[i] + ha * U.g[i] + sa * noise_flat(U, step, 0, i)); });
+  for_quads(U.P, [&](long long i, int cnt) {
+    float th[4], g[4], z[4];
+    ldq(U.theta, i, cnt, th);
+    ldq(U.g, i, cnt, g);
+    noise_quad(U, step, 0, i, cnt, z);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) th[j] = th[j] + ha * g[j] + sa * z[j];
+    store_theta(U, sdst, i, cnt, th);
+  });
   if (grid_last(&sc->ticket) && threadIdx.x == 0) {
     sc->nsampled = ns;
     sc->t = t0 + 1;
@@ -1006,25 +1137,37 @@ __global__ void k_upd_sgld(UpdDev U) {
 }
 
 // SGNHT (sgnht.jl:64-90)
-__global__ void k_upd_sgnht(UpdDev U) {
+__global__ void __launch_bounds__(256) k_upd_sgnht(UpdDev U) {
   StreamScalars* sc = U.sc;
-  if (sc->status) return;
-  const SamplerDev& S = U.S;
   const unsigned long long step = upd_step(U);
+  if (sc->status) {
+    if (grid_last(&sc->ticket) && threadIdx.x == 0) sc->gstep = (long long)step + 1;
+    return;
+  }
+  const SamplerDev& S = U.S;
   const long long t0 = sc->t, ns = sc->nsampled + 1;
   const bool bad_g = sc->gn2 != sc->gn2;  // error("NaN in g") sgnht.jl:70-72: the state stays untouched
   const float l = S.l, xi = sc->xi, cn = sqrtf(l * 2.f * S.A);
   float a0 = 0.f, a1 = 0.f;
   float* sdst = sample_dst(U, ns);
   if (!bad_g)
-    for_flat(U.P, [&](long long i) {
-      float p = U.mom[i];
-      p = p - xi * l * p + l * U.g[i] + cn * noise_flat(U, step, 0, i);
-      U.mom[i] = p;
-      const float t = U.theta[i] + l * p;
-      store_theta(U, sdst, i, t);
-      a0 += p * p;
-      a1 += (t != t) ? 1.f : 0.f;
+    for_quads(U.P, [&](long long i, int cnt) {
+      float th[4], g[4], p[4], z[4];
+      ldq(U.theta, i, cnt, th);
+      ldq(U.g, i, cnt, g);
+      ldq(U.mom, i, cnt, p);
+      noise_quad(U, step, 0, i, cnt, z);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p[j] = p[j] - xi * l * p[j] + l * g[j] + cn * z[j];
+        th[j] = th[j] + l * p[j];
+        if (j < cnt) {
+          a0 += p[j] * p[j];
+          a1 += (th[j] != th[j]) ? 1.f : 0.f;
+        }
+      }
+      stq(U.mom, i, cnt, p);
+      store_theta(U, sdst, i, cnt, th);
     });
   double tot[2];
   if (grid_sum2((double)a0, (double)a1, sc, &sc->ticket, tot) && threadIdx.x == 0) {
@@ -1047,24 +1190,31 @@ __global__ void k_upd_sgnht(UpdDev U) {
 }
 
 // RMSPropMassAdapter (rmspropmassadapter.jl:26-46) on the gradient already in g
-__global__ void k_upd_rmsprop(UpdDev U) {
+__global__ void __launch_bounds__(256) k_upd_rmsprop(UpdDev U) {
   StreamScalars* sc = U.sc;
   if (sc->status || sc->ma_t > U.S.ma_adapt_steps) return;
   const int ma_t = sc->ma_t;
   const bool first = ma_t == 1;
   const float inv_ng = 1.f / sqrtf((float)sc->gn2);
-  for_flat(U.P, [&](long long i) {
-    const float gg = U.g[i] * inv_ng;
-    float V = first ? 1.f : U.rmsv[i];
-    V = U.S.ma_alpha * V + (1.f - U.S.ma_alpha) * gg * gg;
-    U.rmsv[i] = V;
-    U.minv[i] = 1.f / (U.S.ma_lambda + sqrtf(V));
+  for_quads(U.P, [&](long long i, int cnt) {
+    float g[4], V[4], mi[4];
+    ldq(U.g, i, cnt, g);
+    ldq(U.rmsv, i, cnt, V);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gg = g[j] * inv_ng;
+      const float v0 = first ? 1.f : V[j];
+      V[j] = U.S.ma_alpha * v0 + (1.f - U.S.ma_alpha) * gg * gg;
+      mi[j] = 1.f / (U.S.ma_lambda + sqrtf(V[j]));
+    }
+    stq(U.rmsv, i, cnt, V);
+    stq(U.minv, i, cnt, mi);
   });
   if (grid_last(&sc->ticket) && threadIdx.x == 0) sc->ma_t = ma_t + 1;
 }
 
 // SGNHTS first half: B, A, C half steps (sgnht-s.jl:95-97)
-__global__ void k_upd_sgnhts_a(UpdDev U) {
+__global__ void __launch_bounds__(256) k_upd_sgnhts_a(UpdDev U) {
   StreamScalars* sc = U.sc;
   if (sc->status) return;
   const SamplerDev& S = U.S;
@@ -1072,12 +1222,20 @@ __global__ void k_upd_sgnhts_a(UpdDev U) {
   const float hl = 0.5f * S.l, xi0 = sc->xi;
   float a0 = 0.f;
   if (!bad_g)
-    for_flat(U.P, [&](long long i) {
-      const float mi = U.minv ? U.minv[i] : 1.f;
-      const float p = U.mom[i] + hl * U.g[i];
-      U.mom[i] = p;
-      U.theta[i] += hl * mi * p;
-      a0 += p * p * mi;
+    for_quads(U.P, [&](long long i, int cnt) {
+      float th[4], g[4], p[4], mi[4] = {1.f, 1.f, 1.f, 1.f};
+      ldq(U.theta, i, cnt, th);
+      ldq(U.g, i, cnt, g);
+      ldq(U.mom, i, cnt, p);
+      if (U.minv) ldq(U.minv, i, cnt, mi);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p[j] = p[j] + hl * g[j];
+        th[j] += hl * mi[j] * p[j];
+        if (j < cnt) a0 += p[j] * p[j] * mi[j];
+      }
+      stq(U.mom, i, cnt, p);
+      stq(U.theta, i, cnt, th);
     });
   double tot[2];
   if (grid_sum2((double)a0, 0.0, sc, &sc->ticket, tot) && threadIdx.x == 0) {
@@ -1098,10 +1256,10 @@ __global__ void k_upd_sgnhts_a(UpdDev U) {
 }
 
 // SGNHTS second half: O, C, A (sgnht-s.jl:98-104), recording (:110-111)
-__global__ void k_upd_sgnhts_b(UpdDev U) {
+__global__ void __launch_bounds__(256) k_upd_sgnhts_b(UpdDev U) {
   StreamScalars* sc = U.sc;
   const unsigned long long step = upd_step(U);
-  if (sc->status) {  // stopped chain: only the step counter moves on (the host mirror counts every update!)
+  if (sc->status) {
     if (grid_last(&sc->ticket) && threadIdx.x == 0) sc->gstep = (long long)step + 1;
     return;
   }
@@ -1110,14 +1268,23 @@ __global__ void k_upd_sgnhts_b(UpdDev U) {
   const float hl = 0.5f * S.l, e1 = sc->e1, scl = sc->sc, xi0 = sc->xi;
   float a0 = 0.f, a1 = 0.f;
   float* sdst = sample_dst(U, ns);
-  for_flat(U.P, [&](long long i) {
-    const float mi = U.minv ? U.minv[i] : 1.f;
-    const float p = e1 * U.mom[i] + scl * rsqrtf(mi) * noise_flat(U, step, 0, i);
-    U.mom[i] = p;
-    const float t = U.theta[i] + hl * mi * p;
-    store_theta(U, sdst, i, t);
-    a0 += p * p * mi;
-    a1 += (t != t) ? 1.f : 0.f;
+  for_quads(U.P, [&](long long i, int cnt) {
+    float th[4], p[4], z[4], mi[4] = {1.f, 1.f, 1.f, 1.f};
+    ldq(U.theta, i, cnt, th);
+    ldq(U.mom, i, cnt, p);
+    if (U.minv) ldq(U.minv, i, cnt, mi);
+    noise_quad(U, step, 0, i, cnt, z);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p[j] = e1 * p[j] + scl * rsqrtf(mi[j]) * z[j];
+      th[j] = th[j] + hl * mi[j] * p[j];
+      if (j < cnt) {
+        a0 += p[j] * p[j] * mi[j];
+        a1 += (th[j] != th[j]) ? 1.f : 0.f;
+      }
+    }
+    stq(U.mom, i, cnt, p);
+    store_theta(U, sdst, i, cnt, th);
   });
   double tot[2];
   if (grid_sum2((double)a0, (double)a1, sc, &sc->ticket, tot) && threadIdx.x == 0) {
@@ -1151,7 +1318,7 @@ cudaError_t stream_update(const StreamUpdate& su, cudaStream_t st) {
   U.kinetic_base = su.kinetic_base; U.hist_origin = su.hist_origin; U.hist_stride = su.hist_stride;
   U.kinetic_out = su.kinetic_out;
   U.w_hi = su.w_hi; U.w_lo = su.w_lo;
-  const int grid = STREAM_RED_BLOCKS;
+  const int grid = STREAM_RED_BLOCKS;  // 592 x 256 threads = one quad per thread for P up to 606 208, grid-stride beyond
   switch (U.S.kind) {
     case S_SGLD:
       k_upd_sgld<<<grid, 256, 0, st>>>(U);

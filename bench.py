@@ -183,6 +183,223 @@ def run_reference(args):
     emit(json.dumps(out))
 
 
+
+# ----------------------------------------------------------------------------------------------
+# secondary workloads measured in the same run (BASELINE.json configs[0], [2], [3], [4]); the headline stays configs[1]
+# ----------------------------------------------------------------------------------------------
+def _ev(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _max_over_ranks(torch, dist, world, ms):
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
+    """configs[2]: ONE chain, wide MLP 64-512-512-512-1 (ReLU), FeedforwardTDist(nu=5) + MixtureScalePrior, SGNHTS,
+    the minibatch sharded over the ranks (8 192 observations per GPU per update, 2^20 per GPU in the shard), the
+    gradient all-reduced over NCCL INSIDE the library's update graph (bfx_mcmc_advance, shard_mode MINIBATCH)."""
+    import ctypes as C
+    from bayesflux_b200 import _lib as L
+    from bayesflux_b200 import api as A
+    W, Bl, n_loc = 512, 8192, 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(SEED + rank)
+    x = torch.randn((n_loc, 64), generator=g, device="cuda", dtype=torch.float32)   # = 64 x n_loc column-major
+    y = torch.randn((n_loc,), generator=g, device="cuda", dtype=torch.float32)
+    nc = bf.destruct(bf.Chain(bf.Dense(64, W, bf.relu), bf.Dense(W, W, bf.relu), bf.Dense(W, W, bf.relu), bf.Dense(W, 1)))
+    bnn = bf.BNN(None, None, bf.FeedforwardTDist(nc, bf.Gamma(2.0, 0.5), 5.0), bf.MixtureScalePrior(nc, 1.0, 0.1, 0.5),
+                 device=local, compute="tc")
+    bnn.set_data_device(x.data_ptr(), (64, n_loc), y.data_ptr())
+    P = bnn.num_total_params
+    th0 = (0.03 * np.random.default_rng(SEED).standard_normal((P, 1))).astype(np.float32)   # the same on every rank
+    s = bf.SGNHTS(1e-3, 1.0)
+    s.initialise(bnn, th0)
+    shard = "minibatch" if world > 1 else None
+    if world > 1:
+        idt = torch.zeros(L.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(bf.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        bf.comm_init(s, bytes(idt.cpu().numpy().tobytes()), world, rank)
+    st = torch.cuda.Stream()
+    kw = dict(seed=SEED, chain_offset=rank, stream=st.cuda_stream, ngpus=world, shard_mode=shard)
+    bf.advance(s, Bl, 5, **kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = _ev(torch)
+    e0.record(st)
+    bf.advance(s, Bl, steps, **kw)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / steps
+    replays = bf.graph_replays(s)
+    # phase split through the three-call form of the same update (direct launches, one event between the phases)
+    run = A._run_desc(Bl, 0, True, True, True, 1, SEED, "per_chain", rank, world, shard)
+    buf = torch.empty(P + 3, dtype=torch.float32, device="cuda")
+    nb = float((n_loc + Bl - 1) // Bl)
+    tg = tc = tu = 0.0
+    ksplit = 10
+    with torch.cuda.stream(st):
+        for it in range(ksplit + 2):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(st)
+            L.check(L.lib.bfx_stream_grad_local(s._h, C.byref(run), nb, C.c_void_p(st.cuda_stream), C.c_void_p(buf.data_ptr()), P + 3))
+            ev[1].record(st)
+            L.check(L.lib.bfx_stream_allreduce(s._h, C.c_void_p(st.cuda_stream), C.c_void_p(buf.data_ptr())))
+            ev[2].record(st)
+            L.check(L.lib.bfx_stream_apply_update(s._h, C.byref(run), nb, C.c_void_p(st.cuda_stream), C.c_void_p(buf.data_ptr()), None))
+            ev[3].record(st)
+            torch.cuda.synchronize()
+            if it >= 2:
+                tg += ev[0].elapsed_time(ev[1]); tc += ev[1].elapsed_time(ev[2]); tu += ev[2].elapsed_time(ev[3])
+    theta = s.theta[:, 0]
+    ok = bool(np.isfinite(theta).all()) and not s.get_state(L.STATE_STATUS, np.int32, False).any()
+    # replicas must be bit-identical: compare a checksum of theta's bit pattern across ranks
+    chk = torch.tensor([float(np.frombuffer(theta.tobytes(), dtype=np.uint32).astype(np.uint64).sum() % (1 << 52))],
+                       dtype=torch.float64, device="cuda")
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    identical = bool((lo == hi).item())
+    if world > 1:
+        bf.comm_destroy(s)
+    flop = 3279872.0 * Bl                      # per rank per update (SURVEY.md section 8 sizes table)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1355.0) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+    ar_bytes = 4 * (P + 3)
+    ar_ms = tc / ksplit
+    out = {"workload": f"configs[2]: wide MLP 64-512-512-512-1 relu, FeedforwardTDist(5) + MixtureScalePrior(1,0.1,0.5), "
+                       f"SGNHTS(l=1e-3), ONE chain, minibatch {Bl}/GPU x {world} GPUs (shard n={n_loc}/GPU), tcgen05 3-term BF16 split",
+           "n_gpus": world, "updates": steps, "ms_per_update": ms, "updates_per_s": 1e3 / ms,
+           "observations_per_s": Bl * world * 1e3 / ms,
+           "tflops_fp32_equiv_per_gpu": flop / (ms * 1e-3) / 1e12,
+           "frac_of_bf16x3_tensor_roofline": 3 * flop / (ms * 1e-3) / 1e12 / peak,
+           "tensor_peak_tflops": peak,
+           "one_cuda_graph_per_update": replays >= steps, "graph_replays": int(replays),
+           "split_ms_direct_launches": {"grad_local": tg / ksplit, "allreduce": ar_ms, "update": tu / ksplit,
+                                        "sum": (tg + tc + tu) / ksplit},
+           "allreduce_bytes": ar_bytes,
+           "allreduce_busbw_gbs": (2.0 * (world - 1) / world * ar_bytes / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
+           "collective": "ncclAllReduce(P+3 floats) issued by libbfx on the engine's stream, inside the update graph" if world > 1
+                         else "none (single rank)",
+           "replicas_bit_identical": identical, "finite": ok}
+    bnn.close() if hasattr(bnn, "close") else None
+    return out
+
+
+def secondary_cfg1(bf, torch, dist, world, rank, local, updates=200):
+    """configs[0]: README linear regression Dense(5,1), n=500, FeedforwardNormal + GaussianPrior(0.5), SGLD B=50;
+    65 536 chains per GPU (chains sharded, no collective)."""
+    rng = np.random.default_rng(SEED)
+    n, C = 500, 1 << 16
+    x = rng.standard_normal((5, n)).astype(np.float32)
+    beta = rng.standard_normal(5).astype(np.float32)
+    y = (x.T @ beta + rng.standard_normal(n)).astype(np.float32)
+    ncn = bf.destruct(bf.Chain(bf.Dense(5, 1)))
+    bnn = bf.BNN(x, y, bf.FeedforwardNormal(ncn, bf.Gamma(2.0, 0.5)), bf.GaussianPrior(ncn, 0.5), device=local)
+    th0 = (0.5 * np.random.default_rng(SEED + rank).standard_normal((7, C))).astype(np.float32)
+    s = bf.SGLD(stepsize_a=0.1, stepsize_b=0.0, stepsize_gamma=0.55)
+    s.initialise(bnn, th0)
+    ring = torch.empty((C, 4, 7), dtype=torch.float32, device="cuda")
+    st = torch.cuda.Stream()
+    kw = dict(seed=SEED, chain_offset=rank * C, stream=st.cuda_stream, samples_dev=ring.data_ptr(), ring_slots=4)
+    for _ in range(2):
+        bf.advance(s, 50, updates, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = _ev(torch)
+    e0.record(st)
+    bf.advance(s, 50, updates, **kw)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1))
+    v = world * C * updates / ms * 1e3
+    q = 4 * 7 * 3 + 4 * 50 * 6     # streaming-model bytes per chain-step (theta read + write + sample, one minibatch)
+    hbm, _, _ = peaks()
+    return {"workload": "configs[0]: README linreg Dense(5,1), n=500, B=50, SGLD(a=0.1,b=0,gamma=0.55), 65536 chains per GPU",
+            "n_gpus": world, "grad_evals_per_s": v, "ms": ms, "chains_per_gpu": C, "updates": updates,
+            "roofline": {"bound": "hbm", "bytes_per_chain_step": q, "achieved_gbs": v / world * q / 1e9, "peak_gbs": hbm,
+                         "frac": v / world * q / 1e9 / hbm}}
+
+
+def secondary_cfg4(bf, torch, dist, world, rank, local, updates=8, chains=256, ggmc_steps=8):
+    """configs[3]: LSTM(4,64)+Dense(64,1) seq-to-one, T=50, n=16 384, B=64, SeqToOneNormal, GGMC with the reference
+    test's adapters; 256 chains per GPU."""
+    rng = np.random.default_rng(SEED)
+    T, n, B, C = 50, 16384, 64, chains
+    series = (np.cumsum(rng.standard_normal((T + n, 4)), axis=0) * 0.05).astype(np.float32)
+    win = np.lib.stride_tricks.sliding_window_view(series[:T + n - 1], (T, 4))[:n, 0]    # n x T x 4
+    x = np.asfortranarray(np.transpose(win, (1, 2, 0)))                                   # T x d x n
+    y = series[T:T + n, 0].copy()
+    ncn = bf.destruct(bf.Chain(bf.LSTM(4, 64), bf.Dense(64, 1)))
+    bnn = bf.BNN(x, y, bf.SeqToOneNormal(ncn, bf.Gamma(2.0, 0.5)), bf.GaussianPrior(ncn, 0.5), device=local)
+    P = bnn.num_total_params
+    th0 = (0.05 * np.random.default_rng(SEED + rank).standard_normal((P, C))).astype(np.float32)
+    s = bf.GGMC(beta=0.1, l=1e-2, steps=ggmc_steps,
+                sadapter=bf.DualAveragingStepSize(1e-2, target_accept=0.25, adapt_steps=1000),
+                madapter=bf.DiagCovMassAdapter(1000, 100, kappa=0.1, epsilon=1e-8))
+    s.initialise(bnn, th0)
+    st = torch.cuda.Stream()
+    kw = dict(seed=SEED, chain_offset=rank * C, stream=st.cuda_stream)
+    bf.advance(s, B, 2, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = _ev(torch)
+    e0.record(st)
+    bf.advance(s, B, updates, **kw)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1))
+    ok = not s.get_state(bf._lib.STATE_STATUS, np.int32, False).any()
+    fl = 2 * B * 5120384.0 * C * updates          # two minibatch gradients per GGMC update
+    sm_max = peaks()[1]
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    return {"workload": f"configs[3]: LSTM(4,64)+Dense(64,1), T=50, n=16384, B=64, SeqToOneNormal, GGMC(beta=0.1,l=1e-2,steps={ggmc_steps}) "
+                        f"+ DualAveraging + DiagCov, {C} chains per GPU",
+            "n_gpus": world, "ms": ms, "updates": updates, "grad_evals_per_s": world * 2 * C * updates / ms * 1e3,
+            "samples_per_s": world * C * updates / ms * 1e3,
+            "minibatch_tflops_fp32_per_gpu": fl / (ms * 1e-3) / 1e12,
+            "roofline": {"bound": "fp32 pipe (the recurrent kernel is CUDA-core FMA)", "peak_tflops": fp32_peak,
+                         "frac_minibatch_only": fl / (ms * 1e-3) / 1e12 / fp32_peak,
+                         "note": "the full-data MH forwards of each GGMC window (2 x 16384 sequences per chain) are extra work "
+                                 "not counted in the numerator"},
+            "finite": bool(ok)}
+
+
+def secondary_cfg5(bf, torch, dist, world, rank, local, nsamp=1, chains=4096):
+    """configs[4]: many-chain HMC (path_len 5, DualAveraging, DiagCov) on the cfg2 MLP, full batch n = 1e5,
+    4 096 chains per GPU (chains sharded, no collective)."""
+    rng = np.random.default_rng(SEED)
+    n, C, path = 100_000, chains, 5
+    x = rng.standard_normal((10, n)).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    ncn = bf.destruct(bf.Chain(bf.Dense(10, 64, bf.relu), bf.Dense(64, 64, bf.relu), bf.Dense(64, 1)))
+    bnn = bf.BNN(x, y, bf.FeedforwardNormal(ncn, bf.Gamma(2.0, 0.5)), bf.GaussianPrior(ncn, 1.0), device=local, compute="tc")
+    P = bnn.num_total_params
+    th0 = (0.1 * np.random.default_rng(SEED + rank).standard_normal((P, C))).astype(np.float32)
+    s = bf.HMC(1e-4, path, sadapter=bf.DualAveragingStepSize(1e-4, target_accept=0.5),
+               madapter=bf.DiagCovMassAdapter(1000, 100, kappa=0.1))
+    s.initialise(bnn, th0)
+    st = torch.cuda.Stream()
+    e0, e1 = _ev(torch)
+    e0.record(st)
+    bf.advance(s, n, nsamp * path, seed=SEED, chain_offset=rank * C, stream=st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1))
+    flop = (path * 27520.0 + 2 * 9600.0) * n * C * nsamp
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1355.0) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+    tf = flop / (ms * 1e-3) / 1e12
+    return {"workload": f"configs[4]: HMC path_len 5 + DualAveraging + DiagCov, MLP 10-64-64-1, full batch n={n}, {C} chains per GPU, "
+                        f"tcgen05 3-term BF16 split (first sample, includes the lazy BF16 copy of x)",
+            "n_gpus": world, "ms": ms, "hmc_samples": nsamp, "full_batch_grad_evals_per_s": world * C * path * nsamp / ms * 1e3,
+            "tflops_fp32_equiv_per_gpu": tf,
+            "roofline": {"bound": "tensor", "peak_tflops": peak, "issued_bf16_tflops": 3 * tf, "frac": 3 * tf / peak}}
+
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
@@ -252,7 +469,8 @@ def run_ours(args):
     barrier()
     t1 = time.time()
     clk = clocks.stop(t0, t1)
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    per_launch = [a.elapsed_time(b) for a, b in evs]
+    dev_ms = sum(per_launch)
     gpu_launches = bf.launch_count(s) - launches_w
     st = s.get_state(bf._lib.STATE_STATUS, np.int32, False)
     assert not st.any(), "a chain hit a NaN guard during the benchmark"
@@ -296,6 +514,37 @@ def run_ours(args):
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     e2e_value = world * C * U * e2e_steps / float(tw.item())
 
+    # reference semantics of the egress: EVERY sample crosses to the host (sgld.jl:106 keeps all of them)
+    e2e_all = None
+    if not args.no_secondary:
+        s3 = bf.SGLD()
+        out_all = np.empty((P, U, C), np.float32, order="F")
+        bf.mcmc(bnn, B, U, s3, theta_start=theta_h, keep_every=1, seed=SEED, chain_offset=chain_offset, out=out_all)
+        barrier()
+        w0 = time.perf_counter()
+        for i in range(2):
+            bf.mcmc(bnn, B, U, s3, theta_start=theta_h, keep_every=1, seed=SEED + 100 + i, chain_offset=chain_offset, out=out_all)
+        barrier()
+        tall = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tall, op=dist.ReduceOp.MAX)
+        e2e_all = {"value": world * C * U * 2 / float(tall.item()), "unit": "grad-evals/s",
+                   "d2h_bytes_per_step": int(out_all.nbytes), "h2d_bytes_per_step": int(theta0.nbytes),
+                   "note": "keep_every = 1: all 128 samples of every chain are copied to the host each call (PCIe-bound)"}
+        del out_all, s3
+
+    # secondary workloads (every rank takes part: chains sharded, or the minibatch-sharded chain of configs[2])
+    secondary = {}
+    if not args.no_secondary:
+        del ring
+        torch.cuda.empty_cache()
+        for name, fn in (("cfg3", secondary_cfg3), ("cfg1", secondary_cfg1), ("cfg5", secondary_cfg5), ("cfg4", secondary_cfg4)):
+            try:
+                secondary[name] = fn(bf, torch, dist, world, rank, local)
+            except Exception as exc:  # a secondary leg never takes the headline down
+                secondary[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            barrier()
+
     if rank == 0:
         flops, q = algorithmic(B)
         hbm, sm_max, src = peaks()
@@ -325,6 +574,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(ch.nbytes), "steps": e2e_steps,
                     "api": "mcmc(bnn, 64, U, SGLD(); theta_start=host, nchains, keep_every=U) -> host samples"},
             "gpu_launches": int(gpu_launches),
+            "ms_per_launch": {"min": float(np.min(per_launch)), "median": float(np.median(per_launch)),
+                              "max": float(np.max(per_launch)), "n": len(per_launch)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "peak_source": src, "kernel": kernel,
                          "bytes_per_chain_step": q, "chain_steps_per_launch": C * U,
@@ -334,6 +585,10 @@ def run_ours(args):
                                         "frac_of_fp32_pipe": per_gpu * flops / 1e12 / fp32_peak,
                                         "tensor_flops_issued_tflops": (3 if tc else 0) * per_gpu * flops / 1e12}},
         }
+        if e2e_all is not None:
+            out["e2e"]["every_sample_to_host"] = e2e_all
+        if secondary:
+            out["secondary"] = secondary
         if not args.no_cpu and world == 1:
             cb = cpu_sgld(B, args.cpu_seconds)
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -381,6 +636,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_DATA)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (configs[0], [2], [3], [4])")
     ap.add_argument("--compute", default="tc", choices=["fp32", "tc", "auto"],
                     help="contraction arithmetic: tc = tcgen05 tensor cores (3-term BF16 split), fp32 = CUDA-core gate path")
     args = ap.parse_args()

@@ -317,6 +317,11 @@ int32_t bfx_stream_grad_local(bfx_sampler* s, const bfx_run_desc* run, float num
                               float* buf_dev, int64_t count);
 int32_t bfx_stream_apply_update(bfx_sampler* s, const bfx_run_desc* run, float num_batches, void* stream_handle,
                                 float* buf_dev, float* sample_dev /* P floats on the device, or NULL */);
+/* the same exchange done by the library: ncclAllReduce(sum) of buf_dev over the sampler's communicator
+ * (bfx_sampler_comm_init below) on stream_handle; a no-op without a communicator.  bfx_mcmc_run / bfx_mcmc_advance
+ * with shard_mode MINIBATCH issue exactly this between the two halves; the three-call form exists for callers that
+ * want to time or interleave the phases. */
+int32_t bfx_stream_allreduce(bfx_sampler* s, void* stream_handle, float* buf_dev);
 
 /* In-library collective of the minibatch-sharded chain: one NCCL communicator per sampler replica.  NCCL is bound at
  * run time (dlopen of libnccl.so.2, or the path in $BFX_NCCL_LIB), so a process that already carries NCCL (torch,

@@ -275,3 +275,73 @@ def test_stream_tc_sgnhts_tracks_fp32(bf):
         out.append(bf.mcmc(bnn, 256, 8, bf.SGNHTS(1e-3, 1.0), theta_start=th0, seed=3))
     rel = np.linalg.norm(out[0] - out[1]) / np.linalg.norm(out[0])
     assert rel < 1e-4, rel
+
+
+# ---------------------------------------------------------------------------------------------------------
+# in-library collective and the update graph (bfx_sampler_comm_init, run desc shard_mode / ngpus)
+# ---------------------------------------------------------------------------------------------------------
+def _cfg3_small(bf, rng, n=2048, tc=True):
+    layers = NETS["cfg3_small"]
+    x = rng.standard_normal((64, n)).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    like = O.Likelihood(O.TDIST, nu=5.0, prior_a=2.0, prior_b=0.5)
+    prior = O.NetPrior(O.NETPRIOR_MIXTURE, sigma1=1.0, sigma2=0.1, pi1=0.5)
+    bnn, m = build(bf, layers, like, prior, x, y)
+    if tc:
+        _tc(bf, bnn)
+    return bnn, m
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_update_graph_equals_direct_launches(bf, tc, monkeypatch):
+    """One update! of a single stream-regime chain is replayed from a CUDA graph whose per-step quantities (batch
+    position, permutation keys, Philox counter, sample slot) are resolved on the device: bit-identical to the direct
+    launches with host-side step parameters, including the short last batch of every epoch (launched directly)."""
+    rng = np.random.default_rng(SEED + 20)
+    bnn, m = _cfg3_small(bf, rng, n=2048 + 100, tc=tc)      # 8 full batches of 256 + a short one of 100 per epoch
+    th0 = (0.05 * rng.standard_normal(m.n_total)).astype(np.float32)
+    s1 = bf.SGNHTS(1e-3, 1.0)
+    a = np.array(bf.mcmc(bnn, 256, 22, s1, theta_start=th0, seed=3))
+    assert bf.graph_replays(s1) == 20                          # steps 9 and 18 are the short batches
+    monkeypatch.setenv("BFX_NO_GRAPH", "1")
+    s2 = bf.SGNHTS(1e-3, 1.0)
+    b = np.array(bf.mcmc(bnn, 256, 22, s2, theta_start=th0, seed=3))
+    assert bf.graph_replays(s2) == 0
+    assert np.array_equal(a, b)
+    assert np.array_equal(s1.kinetic, s2.kinetic)
+    monkeypatch.delenv("BFX_NO_GRAPH")
+    # a second run on the same handle replays again and reproduces the first (deterministic reductions)
+    c = np.array(bf.mcmc(bnn, 256, 22, s1, theta_start=th0, seed=3))
+    assert np.array_equal(a, c)
+
+
+def test_minibatch_shard_mode_needs_a_communicator(bf):
+    rng = np.random.default_rng(SEED + 21)
+    bnn, m = _cfg3_small(bf, rng, n=512, tc=False)
+    th0 = (0.05 * rng.standard_normal(m.n_total)).astype(np.float32)
+    with pytest.raises(bf.BfxError) as e:
+        bf.mcmc(bnn, 64, 4, bf.SGNHTS(1e-3, 1.0), theta_start=th0, seed=1, ngpus=2, shard_mode="minibatch")
+    assert e.value.code == bf._lib.ERR_STATE
+
+
+def test_in_library_allreduce_single_rank(bf):
+    """The sharded path end to end on ONE rank (an NCCL communicator of size 1): gradient -> pack -> ncclAllReduce
+    inside the captured update graph -> update from the exchange buffer.  Equals the unsharded run up to the float
+    rounding of the three likelihood sums that travel through the buffer."""
+    rng = np.random.default_rng(SEED + 22)
+    bnn, m = _cfg3_small(bf, rng, n=2048, tc=True)
+    th0 = (0.05 * rng.standard_normal(m.n_total)).astype(np.float32)
+    ref = np.array(bf.mcmc(bnn, 256, 12, bf.SGNHTS(1e-3, 1.0), theta_start=th0, seed=3))
+    s = bf.SGNHTS(1e-3, 1.0)
+    s.initialise(bnn, th0.reshape(-1, 1))
+    try:
+        cid = bf.comm_unique_id()
+    except bf.BfxError as exc:
+        pytest.skip(f"NCCL not loadable here: {exc}")
+    bf.comm_init(s, cid, 1, 0)
+    # (the handle, and with it the communicator, is kept: same model, same number of chains)
+    out = np.array(bf.mcmc(bnn, 256, 12, s, theta_start=th0, seed=3, ngpus=1, shard_mode="minibatch"))
+    assert bf.graph_replays(s) == 12
+    bf.comm_destroy(s)
+    rel = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    assert rel < 1e-5, rel
