@@ -153,6 +153,8 @@ struct bfx_sampler {
   // minibatch-sharded chain: NCCL communicator of the ranks that hold the shards (bfx_sampler_comm_init)
   void* comm = nullptr;
   int comm_rank = 0, comm_nranks = 1;
+  cudaStream_t comm_stream = nullptr;  // side stream of the bucketed exchange (fork / join by events)
+  StreamBucketHook hook{};
 };
 
 // ---------------------------------------------------------------------------------
@@ -949,9 +951,17 @@ static void free_sampler(bfx_sampler* s) {
   if (s->progress_host) cudaFreeHost(s->progress_host);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->adv_event) cudaEventDestroy(s->adv_event);
-  if (s->upd_graph) cudaGraphExecDestroy(s->upd_graph);
+  if (s->upd_graph) {  // before the communicator: the captured collective holds a reference on it
+    cudaGraphExecDestroy(s->upd_graph);
+    cudaDeviceSynchronize();
+  }
   if (s->comm) {
     if (NcclApi* api = nccl_api()) api->CommDestroy(s->comm);
+  }
+  if (s->comm_stream) {
+    cudaStreamDestroy(s->comm_stream);
+    for (int i = 0; i < BFX_MAX_LAYERS; ++i) cudaEventDestroy(s->hook.ev_fork[i]);
+    cudaEventDestroy(s->hook.ev_join);
   }
   delete s;
 }
@@ -1372,7 +1382,7 @@ static bool wsplit_valid(const bfx_sampler* s) {
 }
 
 static int32_t stream_grad_local(bfx_sampler* s, int c, const StreamBatch& b, float nb, bool pack, cudaStream_t st,
-                                 float* gb = nullptr) {
+                                 float* gb = nullptr, StreamBucketHook* hook = nullptr) {
   if (!gb) gb = s->gbuf;
   bfx_model* m = s->m;
   int32_t rc = ensure_work(m, b.B);
@@ -1381,8 +1391,8 @@ static int32_t stream_grad_local(bfx_sampler* s, int c, const StreamBatch& b, fl
   const bool valid = wsplit_valid(s);
   if (!valid) m->wsplit_owner = nullptr;
   CK(stream_zero(gb, m->M.P, s->ssc + c, st));
-  CK(stream_eval_like(m->SM, m->W, th, m->x, m->y, b, nb, true, gb, s->ssc + c, st, nullptr, valid));
-  if (pack) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, st));
+  CK(stream_eval_like(m->SM, m->W, th, m->x, m->y, b, nb, true, gb, s->ssc + c, st, nullptr, valid, hook));
+  if (pack && !(hook && hook->used)) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, st));
   return BFX_OK;
 }
 
@@ -1435,12 +1445,16 @@ static int32_t stream_apply(bfx_sampler* s, int c, float nb, bool from_buffer, u
 }
 
 // the all-reduce of the exchange buffer [g ; sum1 ; sum2 ; B] of a minibatch-sharded chain
-static int32_t stream_allreduce(bfx_sampler* s, float* gb, cudaStream_t st) {
+static int32_t stream_allreduce(bfx_sampler* s, float* gb, cudaStream_t st, long long count = -1) {
   NcclApi* api = nccl_api();
   if (!api || !s->comm) return fail(BFX_ERR_STATE, "minibatch-sharded update without a communicator");
-  const int r = api->AllReduce(gb, gb, (size_t)s->m->M.P + 3, kNcclFloat32, kNcclSum, s->comm, st);
+  if (count < 0) count = (long long)s->m->M.P + 3;
+  const int r = api->AllReduce(gb, gb, (size_t)count, kNcclFloat32, kNcclSum, s->comm, st);
   if (r != 0) return fail(BFX_ERR_CUDA, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
   return BFX_OK;
+}
+static cudaError_t hook_reduce(void* ctx, float* ptr, long long count, cudaStream_t st) {
+  return stream_allreduce(static_cast<bfx_sampler*>(ctx), ptr, st, count) == BFX_OK ? cudaSuccess : cudaErrorUnknown;
 }
 
 // one whole update! of chain c, scheduled batch
@@ -1453,11 +1467,17 @@ static int32_t stream_update_once(bfx_sampler* s, const bfx_run_desc* run, int c
   // update with the shared noise key 0: identical Philox streams keep theta / p / xi bit-identical on every rank
   const unsigned noisekey = sharded ? 0u : permkey;
   StreamBatch b = stream_batch(m, run, permkey, s->gstep, device_step);
-  int32_t rc = stream_grad_local(s, c, b, nbat, sharded, st);
+  // per-layer buckets on the side stream while the backward pass continues (BFX_NO_BUCKETS=1: one all-reduce)
+  StreamBucketHook* hook = sharded && s->comm_stream && !std::getenv("BFX_NO_BUCKETS") ? &s->hook : nullptr;
+  int32_t rc = stream_grad_local(s, c, b, nbat, sharded, st, nullptr, hook);
   if (rc) return rc;
   if (sharded) {
-    rc = stream_allreduce(s, s->gbuf, st);
-    if (rc) return rc;
+    if (hook && hook->used) {
+      CK(cudaStreamWaitEvent(st, hook->ev_join, 0));
+    } else {
+      rc = stream_allreduce(s, s->gbuf, st);
+      if (rc) return rc;
+    }
   }
   return stream_apply(s, c, nbat, sharded, run->seed, noisekey, nullptr, rec, st, nullptr, device_step);
 }
@@ -1511,12 +1531,13 @@ static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nstep
     CK(stream_set_gstep(s->ssc, s->gstep, st));
     struct Key {
       long long B, nbat, n, ke, slots, base, nnew;
-      int shuffle, batch_mode, shard, tc;
+      int shuffle, batch_mode, shard, tc, nobuckets, pad;
       unsigned long long seed;
       long long chain_offset;
       const void *samples_dev, *d_kin, *comm, *x, *w;
     } key{B, nbat, m->n, ke, samples_dev ? slots : 0, d_kin ? base : 0, d_kin ? nnew : 0, run->shuffle, run->batch_mode,
-          run->shard_mode, m->SM.tc, run->seed, run->chain_offset, samples_dev, d_kin, s->comm, m->x, m->W.w_hi};
+          run->shard_mode, m->SM.tc, std::getenv("BFX_NO_BUCKETS") ? 1 : 0, 0, run->seed, run->chain_offset, samples_dev, d_kin,
+          s->comm, m->x, m->W.w_hi};
     std::vector<unsigned char> kb(sizeof key);
     std::memcpy(kb.data(), &key, sizeof key);
     if (!s->upd_graph || kb != s->upd_graph_key) {
@@ -2078,6 +2099,11 @@ int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, in
   NcclApi* api = nccl_api();
   if (!api) return fail(BFX_ERR_UNSUPPORTED, "NCCL could not be loaded (set BFX_NCCL_LIB to libnccl.so.2)");
   CK(cudaSetDevice(s->device));
+  if (s->upd_graph) {
+    cudaGraphExecDestroy(s->upd_graph);
+    s->upd_graph = nullptr;
+    cudaDeviceSynchronize();
+  }
   if (s->comm) {
     api->CommDestroy(s->comm);
     s->comm = nullptr;
@@ -2090,6 +2116,24 @@ int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, in
   s->comm = comm;
   s->comm_rank = rank;
   s->comm_nranks = nranks;
+  if (!s->comm_stream) {
+    CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < BFX_MAX_LAYERS; ++i) CK(cudaEventCreateWithFlags(&s->hook.ev_fork[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->hook.ev_join, cudaEventDisableTiming));
+    s->hook.reduce = hook_reduce;
+    s->hook.ctx = s;
+    s->hook.side = s->comm_stream;
+  }
+  // One eager collective on the exchange buffer now: NCCL establishes its transports (peer mappings, host-side
+  // bootstrap between the ranks) on first use, which must not fall inside the stream capture of the update graph.
+  {
+    int32_t st = ensure_stream(s->m);
+    if (st) return st;
+    CK(cudaMemsetAsync(s->gbuf, 0, ((size_t)s->m->M.P + 3) * sizeof(float), s->m->stream));
+    st = stream_allreduce(s, s->gbuf, s->m->stream);
+    if (st) return st;
+    CK(cudaStreamSynchronize(s->m->stream));
+  }
   if (s->upd_graph) {
     cudaGraphExecDestroy(s->upd_graph);
     s->upd_graph = nullptr;
@@ -2099,16 +2143,19 @@ int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, in
 
 int32_t bfx_sampler_comm_destroy(bfx_sampler* s) {
   if (!s) return fail(BFX_ERR_BAD_ARG, "NULL argument");
-  if (s->comm) {
-    CK(cudaSetDevice(s->device));
-    if (s->m->stream) cudaStreamSynchronize(s->m->stream);
-    if (s->adv_event) cudaEventSynchronize(s->adv_event);
-    if (NcclApi* api = nccl_api()) api->CommDestroy(s->comm);
-    s->comm = nullptr;
-  }
+  CK(cudaSetDevice(s->device));
+  if (s->m->stream) cudaStreamSynchronize(s->m->stream);
+  if (s->adv_event) cudaEventSynchronize(s->adv_event);
+  // the update graph holds a reference on the communicator (captured collective): it goes first, ncclCommDestroy
+  // waits for those references to drop
   if (s->upd_graph) {
     cudaGraphExecDestroy(s->upd_graph);
     s->upd_graph = nullptr;
+    cudaDeviceSynchronize();
+  }
+  if (s->comm) {
+    if (NcclApi* api = nccl_api()) api->CommDestroy(s->comm);
+    s->comm = nullptr;
   }
   s->comm_rank = 0;
   s->comm_nranks = 1;

@@ -793,9 +793,14 @@ cudaError_t stream_set_gstep(StreamScalars* sc, long long gstep, cudaStream_t st
 
 cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* theta, const float* x, const float* y,
                              const StreamBatch& b, float nb, bool want_grad, float* g, StreamScalars* sc,
-                             cudaStream_t st, float* yhat_out, bool theta_split_valid) {
+                             cudaStream_t st, float* yhat_out, bool theta_split_valid, StreamBucketHook* hook) {
   const int nl = M.nlayers;
   const bool htc = head_on_tc(M);
+  // bucketed exchange: every layer below the fused head on the tensor cores, one batch chunk
+  bool bucketed = hook != nullptr && want_grad && htc && b.B <= W.Bc;
+  for (int l = 0; l < nl - 1; ++l) bucketed = bucketed && M.L[l].tc;
+  if (hook) hook->used = bucketed ? 1 : 0;
+  int nbuckets = 0;
   if (M.tc && !theta_split_valid) {  // BF16 halves of theta for the tensor-core layers
     k_split<<<592, 256, 0, st>>>(theta, M.P, W.w_hi, W.w_lo);
     SCK(cudaGetLastError());
@@ -863,6 +868,16 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
       I.dst = dst; I.count = count; I.src = src; I.nparts = nparts; I.stride = stride;
       R.total += count;
     };
+    auto flush_items = [&]() -> cudaError_t {
+      if (R.n == 0) return cudaSuccess;
+      long long maxq = 1;
+      for (int k = 0; k < R.n; ++k) maxq = std::max(maxq, (R.it[k].count + 3) / 4);
+      long long blocks = (maxq + 255) / 256;
+      if (blocks > 296) blocks = 296;
+      k_reduce_list<<<dim3((unsigned)blocks, (unsigned)R.n), 256, 0, st>>>(g, R);
+      R = ReduceList{};
+      return cudaGetLastError();
+    };
     for (int l = nl - 1; l >= 0; --l) {
       const StreamLayer& L = M.L[l];
       if (l == nl - 1 && htc) {
@@ -890,9 +905,22 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
         t.C = W.tc_part[l]; t.ldc = L.nout; t.accumulate = 0; t.kchunk = kch; t.part_stride = cnt;
         SCK(tc2_dw(t, tcg::Operand{Dhi, Dlo, L.nout}, tcg::Operand{W.act_hi[l], W.act_lo[l], L.nin}, ksplit, st));
         add_item(L.w_off, cnt, W.tc_part[l], ksplit, cnt);
-        if (bias_slots > 0) {
-          add_item(L.b_off, L.nout, W.tc_rowpart[l], bias_slots, L.nout);
-        } else if (bias_slots == 0) {  // delta came from an FP32 kernel: deterministic two-level row sum of its FP32 copy
+        if (bias_slots > 0) add_item(L.b_off, L.nout, W.tc_rowpart[l], bias_slots, L.nout);
+        if (bucketed) {
+          // the gradient of this layer (and, for the last hidden layer, of the head with the likelihood sums) is
+          // complete: reduce its partials now and start its all-reduce beside the remaining GEMMs
+          if (l == nl - 2) {
+            k_pack_sums<<<1, 1, 0, st>>>(g, M.P, sc);
+            SCK(cudaGetLastError());
+          }
+          SCK(flush_items());
+          const long long lo = L.w_off, hi = l == nl - 2 ? M.P + 3 : M.L[l + 1].w_off;
+          SCK(cudaEventRecord(hook->ev_fork[nbuckets], st));
+          SCK(cudaStreamWaitEvent(hook->side, hook->ev_fork[nbuckets], 0));
+          SCK(hook->reduce(hook->ctx, g + lo, hi - lo, hook->side));
+          ++nbuckets;
+        }
+        if (bias_slots == 0) {  // delta came from an FP32 kernel: deterministic two-level row sum of its FP32 copy
           dim3 grid((L.nout + 31) / 32, 8);
           k_rowsum_part<<<grid, 256, 0, st>>>(D, L.nout, nc, nullptr, W.rowpart);
           SCK(cudaGetLastError());
@@ -977,14 +1005,8 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
         ping ^= 1;
       }
     }
-    if (R.n > 0) {
-      long long maxq = 1;
-      for (int k = 0; k < R.n; ++k) maxq = std::max(maxq, (R.it[k].count + 3) / 4);
-      long long blocks = (maxq + 255) / 256;
-      if (blocks > 296) blocks = 296;
-      k_reduce_list<<<dim3((unsigned)blocks, (unsigned)R.n), 256, 0, st>>>(g, R);
-      SCK(cudaGetLastError());
-    }
+    SCK(flush_items());
+    if (bucketed && nbuckets > 0) SCK(cudaEventRecord(hook->ev_join, hook->side));
   }
   return cudaSuccess;
 }

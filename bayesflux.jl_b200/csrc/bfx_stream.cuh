@@ -114,12 +114,26 @@ struct StreamBatch {
   int shuffle;
 };
 
+// Bucketed exchange of a minibatch-sharded chain: as soon as the backward pass has finished the gradient of a layer,
+// that slice of the exchange buffer is all-reduced on a side stream while the main stream continues with the GEMMs of
+// the layers below; the slice of the output layer carries the three likelihood sums (g[P .. P+2]).  Fork / join by
+// events, so the whole pattern is capturable in the update graph.
+struct StreamBucketHook {
+  cudaError_t (*reduce)(void* ctx, float* ptr, long long count, cudaStream_t st);
+  void* ctx;
+  cudaStream_t side;
+  cudaEvent_t ev_fork[BFX_MAX_LAYERS];
+  cudaEvent_t ev_join;
+  int used;  // set by stream_eval_like: 1 = the buckets were issued (the caller joins on ev_join), 0 = not applicable
+};
+
 // likelihood part of the evaluation on one minibatch: g[0..Pnet) += num_batches * d loglike / d theta_net
 // (g must be zeroed by the caller), sc->ds0/ds1/bcount += sums.  theta_split_valid: W.w_hi / w_lo already hold
 // the BF16 halves of theta (the sampler updates keep them current).
 cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* theta, const float* x, const float* y,
                              const StreamBatch& b, float nb, bool want_grad, float* g, StreamScalars* sc,
-                             cudaStream_t st, float* yhat_out = nullptr, bool theta_split_valid = false);
+                             cudaStream_t st, float* yhat_out = nullptr, bool theta_split_valid = false,
+                             StreamBucketHook* hook = nullptr);
 // prior + sigma prior + value + ||g||^2 (one kernel; nothing is synchronised).  from_buffer: the likelihood sums are
 // taken from g[P .. P+2] (the all-reduced exchange buffer) instead of the scalars.
 cudaError_t stream_finish(const StreamModel& M, const float* theta, float* g, StreamScalars* sc, float nb, bool want_grad,

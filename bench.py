@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+T_START = time.time()
 SEED = 6150533  # the reference's test seed (test/runtests.jl:10)
 D_IN, H, N_DATA = 10, 64, 1_000_000
 P_TOTAL = D_IN * H + H + H * H + H + H + 1 + 1  # 4930
@@ -187,6 +188,12 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # secondary workloads measured in the same run (BASELINE.json configs[0], [2], [3], [4]); the headline stays configs[1]
 # ----------------------------------------------------------------------------------------------
+def log(msg):
+    """progress on stderr (stdout carries the one JSON line only)"""
+    sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} +{time.time() - T_START:6.1f}s] {msg}\n")
+    sys.stderr.flush()
+
+
 def _ev(torch):
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -218,16 +225,19 @@ def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
     s = bf.SGNHTS(1e-3, 1.0)
     s.initialise(bnn, th0)
     shard = "minibatch" if world > 1 else None
+    log("cfg3: model and sampler ready")
     if world > 1:
         idt = torch.zeros(L.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(bf.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         bf.comm_init(s, bytes(idt.cpu().numpy().tobytes()), world, rank)
+        log("cfg3: communicator up")
     st = torch.cuda.Stream()
     kw = dict(seed=SEED, chain_offset=rank, stream=st.cuda_stream, ngpus=world, shard_mode=shard)
     bf.advance(s, Bl, 5, **kw)
     torch.cuda.synchronize()
+    log("cfg3: warm-up updates done")
     if world > 1:
         dist.barrier()
     e0, e1 = _ev(torch)
@@ -236,7 +246,22 @@ def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
     e1.record(st)
     torch.cuda.synchronize()
     ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / steps
+    log(f"cfg3: {ms * 1e3:.1f} us per update")
     replays = bf.graph_replays(s)
+    # the same update with ONE all-reduce of the whole buffer after the backward pass (no per-layer buckets)
+    ms_single = None
+    if world > 1:
+        os.environ["BFX_NO_BUCKETS"] = "1"
+        bf.advance(s, Bl, 3, **kw)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record(st)
+        bf.advance(s, Bl, steps, **kw)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms_single = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / steps
+        del os.environ["BFX_NO_BUCKETS"]
+        log(f"cfg3: {ms_single * 1e3:.1f} us per update with a single all-reduce")
     # phase split through the three-call form of the same update (direct launches, one event between the phases)
     run = A._run_desc(Bl, 0, True, True, True, 1, SEED, "per_chain", rank, world, shard)
     buf = torch.empty(P + 3, dtype=torch.float32, device="cuda")
@@ -285,8 +310,10 @@ def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
                                         "sum": (tg + tc + tu) / ksplit},
            "allreduce_bytes": ar_bytes,
            "allreduce_busbw_gbs": (2.0 * (world - 1) / world * ar_bytes / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
-           "collective": "ncclAllReduce(P+3 floats) issued by libbfx on the engine's stream, inside the update graph" if world > 1
-                         else "none (single rank)",
+           "collective": "per-layer ncclAllReduce buckets (P+3 floats in total) issued by libbfx on a side stream while the "
+                         "backward GEMMs continue, fork/join inside the update graph" if world > 1 else "none (single rank)",
+           "ms_per_update_single_allreduce": ms_single,
+           "allreduce_hidden_ms": (ms_single - ms) if ms_single is not None else None,
            "replicas_bit_identical": identical, "finite": ok}
     bnn.close() if hasattr(bnn, "close") else None
     return out
@@ -440,6 +467,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm (`value`) ----------------
+    log("device-resident arm")
     stream = torch.cuda.Stream()
     ring = torch.empty((C, U, P), dtype=torch.float32, device="cuda")  # HBM ring of recorded samples
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -484,6 +512,7 @@ def run_ours(args):
     value = units / (dev_ms * 1e-3)
 
     # ---------------- end-to-end arm through the public API (`e2e`) ----------------
+    log("end-to-end arm")
     e2e_steps = max(2, min(args.steps, 5))
     theta_h = theta0.copy(order="F")
     s2 = bf.SGLD()
@@ -514,37 +543,8 @@ def run_ours(args):
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     e2e_value = world * C * U * e2e_steps / float(tw.item())
 
-    # reference semantics of the egress: EVERY sample crosses to the host (sgld.jl:106 keeps all of them)
-    e2e_all = None
-    if not args.no_secondary:
-        s3 = bf.SGLD()
-        out_all = np.empty((P, U, C), np.float32, order="F")
-        bf.mcmc(bnn, B, U, s3, theta_start=theta_h, keep_every=1, seed=SEED, chain_offset=chain_offset, out=out_all)
-        barrier()
-        w0 = time.perf_counter()
-        for i in range(2):
-            bf.mcmc(bnn, B, U, s3, theta_start=theta_h, keep_every=1, seed=SEED + 100 + i, chain_offset=chain_offset, out=out_all)
-        barrier()
-        tall = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tall, op=dist.ReduceOp.MAX)
-        e2e_all = {"value": world * C * U * 2 / float(tall.item()), "unit": "grad-evals/s",
-                   "d2h_bytes_per_step": int(out_all.nbytes), "h2d_bytes_per_step": int(theta0.nbytes),
-                   "note": "keep_every = 1: all 128 samples of every chain are copied to the host each call (PCIe-bound)"}
-        del out_all, s3
-
-    # secondary workloads (every rank takes part: chains sharded, or the minibatch-sharded chain of configs[2])
-    secondary = {}
-    if not args.no_secondary:
-        del ring
-        torch.cuda.empty_cache()
-        for name, fn in (("cfg3", secondary_cfg3), ("cfg1", secondary_cfg1), ("cfg5", secondary_cfg5), ("cfg4", secondary_cfg4)):
-            try:
-                secondary[name] = fn(bf, torch, dist, world, rank, local)
-            except Exception as exc:  # a secondary leg never takes the headline down
-                secondary[name] = {"error": f"{type(exc).__name__}: {exc}"}
-            barrier()
-
+    # ---------------- the headline line is complete here; everything below only adds keys to it ----------------
+    out = None
     if rank == 0:
         flops, q = algorithmic(B)
         hbm, sm_max, src = peaks()
@@ -585,14 +585,67 @@ def run_ours(args):
                                         "frac_of_fp32_pipe": per_gpu * flops / 1e12 / fp32_peak,
                                         "tensor_flops_issued_tflops": (3 if tc else 0) * per_gpu * flops / 1e12}},
         }
-        if e2e_all is not None:
-            out["e2e"]["every_sample_to_host"] = e2e_all
-        if secondary:
-            out["secondary"] = secondary
         if not args.no_cpu and world == 1:
+            log("cpu baseline")
             cb = cpu_sgld(B, args.cpu_seconds)
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        emit(json.dumps(out))
+    barrier()
+
+    # A hang in an optional leg (a collective that never completes) must not cost the headline: past the deadline a
+    # watchdog thread emits the line as it stands (rank 0) and ends the process on every rank.
+    emitted = threading.Event()
+
+    def finish(note=None):
+        if emitted.is_set():
+            return
+        emitted.set()
+        if rank == 0:
+            if note:
+                out.setdefault("secondary", {})["aborted"] = note
+            emit(json.dumps(out))
+
+    def watchdog():
+        if not emitted.wait(args.secondary_budget):
+            log(f"secondary legs exceeded {args.secondary_budget:.0f} s: emitting the headline and leaving")
+            finish(f"optional legs stopped after {args.secondary_budget:.0f} s")
+            os._exit(0)
+
+    if not args.no_secondary:
+        threading.Thread(target=watchdog, daemon=True).start()
+        # reference semantics of the egress: EVERY sample crosses to the host (sgld.jl:106 keeps all of them)
+        log("e2e with every sample copied to the host")
+        s3 = bf.SGLD()
+        out_all = np.empty((P, U, C), np.float32, order="F")
+        bf.mcmc(bnn, B, U, s3, theta_start=theta_h, keep_every=1, seed=SEED, chain_offset=chain_offset, out=out_all)
+        barrier()
+        w0 = time.perf_counter()
+        for i in range(2):
+            bf.mcmc(bnn, B, U, s3, theta_start=theta_h, keep_every=1, seed=SEED + 100 + i, chain_offset=chain_offset, out=out_all)
+        barrier()
+        tall = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tall, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            out["e2e"]["every_sample_to_host"] = {
+                "value": world * C * U * 2 / float(tall.item()), "unit": "grad-evals/s",
+                "d2h_bytes_per_step": int(out_all.nbytes), "h2d_bytes_per_step": int(theta0.nbytes),
+                "note": "keep_every = 1: all 128 samples of every chain are copied to the host each call (PCIe-bound)"}
+        del out_all, s3
+        # secondary workloads (every rank takes part: chains sharded, or the minibatch-sharded chain of configs[2])
+        del ring
+        torch.cuda.empty_cache()
+        for name, fn in (("cfg3", secondary_cfg3), ("cfg1", secondary_cfg1), ("cfg5", secondary_cfg5), ("cfg4", secondary_cfg4)):
+            log(f"secondary {name}")
+            try:
+                res = fn(bf, torch, dist, world, rank, local)
+            except Exception as exc:  # a secondary leg never takes the headline down
+                res = {"error": f"{type(exc).__name__}: {exc}"}
+                log(f"secondary {name} failed: {res['error']}")
+            if rank == 0:
+                out.setdefault("secondary", {})[name] = res
+            barrier()
+    finish()
+    log("done")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -637,6 +690,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (configs[0], [2], [3], [4])")
+    ap.add_argument("--secondary-budget", type=float, default=150.0,
+                    help="seconds the optional legs may take before the headline line is emitted without them")
     ap.add_argument("--compute", default="tc", choices=["fp32", "tc", "auto"],
                     help="contraction arithmetic: tc = tcgen05 tensor cores (3-term BF16 split), fp32 = CUDA-core gate path")
     args = ap.parse_args()
