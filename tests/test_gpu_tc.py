@@ -65,6 +65,8 @@ def test_tc_grad_and_value_parity(bf, net, like, B):
                                      y[idx[:, c]].astype(np.float64), 6.0)
         rel = np.linalg.norm(g[:, c] - go) / np.linalg.norm(go)
         assert rel < TOL, f"chain {c}: gradient rel err {rel}"
+        # the same max-abs bound the FP32 matrix holds (tests/test_gpu_parity.py): no single entry may be off
+        assert np.max(np.abs(g[:, c] - go)) <= TOL * max(1.0, np.max(np.abs(go))), f"chain {c}: max-abs gradient error"
         assert abs(v[c] - vo) <= TOL * abs(vo)
         assert abs(v2[c] - vo) <= TOL * abs(vo)
 
