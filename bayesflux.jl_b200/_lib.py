@@ -94,6 +94,8 @@ SYMBOLS = {
     "bfx_progress": [_vp, _pi64],
     "bfx_mcmc_advance": [_vp, C.POINTER(RunDesc), _i64, _vp, _vp, _i64],
     "bfx_sampler_launch_count": [_vp, _pi64],
+    "bfx_host_register": [_vp, C.c_size_t],
+    "bfx_host_unregister": [_vp],
     "bfx_model_regime": [_vp, _pi32],
     "bfx_stream_grad_local": [_vp, C.POINTER(RunDesc), _f32, _vp, _vp, _i64],
     "bfx_stream_apply_update": [_vp, C.POINTER(RunDesc), _f32, _vp, _vp, _vp],

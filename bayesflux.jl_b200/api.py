@@ -582,6 +582,9 @@ class MCMCState:
         return -(-(n_new * getattr(self, "path_len", 1)) // nbatches)
 
     def close(self):
+        for ptr in list(self.__dict__.get("_pinned", {})):
+            L.lib.bfx_host_unregister(C.c_void_p(ptr))
+        self.__dict__.pop("_pinned", None)
         if self._h is not None:
             L.lib.bfx_sampler_destroy(self._h)
             self._h = None
@@ -757,6 +760,12 @@ def mcmc(bnn: BNN, batchsize: int, numsamples: int, sampler: MCMCState, shuffle=
                 and out.shape == (P, nkept, nchains)):
             raise ValueError(f"out must be a Fortran-ordered float32 array of shape {(P, nkept, nchains)}")
         new = out
+        # a caller-owned result buffer is reused call after call: page-lock it once (DMA copies, no bounce buffer);
+        # the sampler keeps a reference and unlocks it when it is closed
+        pins = sampler.__dict__.setdefault("_pinned", {})
+        if out.nbytes >= (1 << 20) and out.ctypes.data not in pins:
+            if L.lib.bfx_host_register(C.c_void_p(out.ctypes.data), out.nbytes) == L.OK:
+                pins[out.ctypes.data] = out
     else:
         new = np.empty((P, nkept, nchains), np.float32, order="F")
     kin = np.zeros((nnew, nchains), np.float32, order="F") if sampler.kind in (L.SGNHT, L.SGNHTS) else None

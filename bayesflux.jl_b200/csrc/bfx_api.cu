@@ -2029,6 +2029,30 @@ int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps
   return mark_advance(s, stream);
 }
 
+// Page-lock / unlock a caller-owned host buffer that is reused over many bfx_mcmc_run calls: copies to and from
+// pinned memory are plain DMA transfers (no staging through the driver's bounce buffer, no host memcpy), which is
+// what keeps several processes on one box from competing for host memory bandwidth.
+int32_t bfx_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return BFX_OK;
+  }
+  if (e != cudaSuccess) return fail(BFX_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  return BFX_OK;
+}
+
+int32_t bfx_host_unregister(void* ptr) {
+  if (!ptr) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BFX_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+  }
+  return BFX_OK;
+}
+
 int32_t bfx_sampler_launch_count(const bfx_sampler* s, int64_t* n) {
   if (!s || !n) return fail(BFX_ERR_BAD_ARG, "NULL argument");
   *n = s->launches;

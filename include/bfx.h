@@ -295,6 +295,13 @@ int32_t bfx_progress(const bfx_sampler* s, int64_t* nsampled);
  * Asynchronous: returns after enqueueing.  stream_handle: a cudaStream_t or 0 (own stream). */
 int32_t bfx_mcmc_advance(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, void* stream_handle,
                          float* samples_dev, int64_t ring_slots);
+/* Optional: page-lock a caller-owned host buffer that is passed to bfx_mcmc_run again and again (theta_start,
+ * samples_out).  Transfers to / from registered memory are DMA copies without the driver's bounce buffer; with
+ * several processes per box this removes the contention for host memory bandwidth.  The caller keeps the buffer
+ * alive (GC.@preserve / a held reference) until bfx_host_unregister.  Thin wrappers of cudaHostRegister. */
+int32_t bfx_host_register(void* ptr, size_t bytes);
+int32_t bfx_host_unregister(void* ptr);
+
 /* number of kernel launches issued by this sampler handle so far */
 int32_t bfx_sampler_launch_count(const bfx_sampler* s, int64_t* n);
 
