@@ -619,7 +619,43 @@ __global__ void __launch_bounds__(256) k_reduce_list(float* __restrict__ g, cons
   const ReduceItem& I = R.it[blockIdx.y];
   const bool vec = (I.count & 3) == 0 && (I.stride & 3) == 0 && (I.dst & 3) == 0 &&
                    (reinterpret_cast<unsigned long long>(I.src) & 15ull) == 0;
-  if (vec) {
+  if (vec && I.nparts >= 32) {
+    // many partials of a short vector (bias row sums: 64 slots, the head's partial sums: one per 32 columns): a thread
+    // walking all of them is a chain of dependent memory round trips, so eight threads share a quad (slots g, g + 8,
+    // ...), and their sums are folded in group order through shared memory
+    __shared__ float4 sh[8][32];
+    const long long nq = I.count >> 2;
+    const int pg = threadIdx.x >> 5, ql = threadIdx.x & 31;
+    const long long sq = I.stride >> 2;
+    for (long long q0 = (long long)blockIdx.x * 32; q0 < nq; q0 += (long long)gridDim.x * 32) {
+      const long long q = q0 + ql;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < nq) {
+        const float4* src = reinterpret_cast<const float4*>(I.src) + q;
+        int z = pg;
+        for (; z + 56 < I.nparts; z += 64) {
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldcs(src + (long long)(z + 8 * j) * sq);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+        }
+        for (; z < I.nparts; z += 8) {
+          const float4 v = __ldcs(src + (long long)z * sq);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      sh[pg][ql] = acc;
+      __syncthreads();
+      if (pg == 0 && q < nq) {
+        float4 t = *reinterpret_cast<const float4*>(g + I.dst + 4 * q);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t.x += sh[k][ql].x; t.y += sh[k][ql].y; t.z += sh[k][ql].z; t.w += sh[k][ql].w; }
+        *reinterpret_cast<float4*>(g + I.dst + 4 * q) = t;
+      }
+      __syncthreads();
+    }
+  } else if (vec) {
     const long long nq = I.count >> 2;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
       const float4* src = reinterpret_cast<const float4*>(I.src) + q;
@@ -665,6 +701,11 @@ static bool head_on_tc(const StreamModel& M) {  // 1-wide output layer fed by a 
   const int nl = M.nlayers;
   return M.tc && nl >= 2 && M.L[nl - 1].nout == 1 && M.L[nl - 2].tc && M.L[nl - 1].nin % 8 == 0;
 }
+
+// distance between the split-K partials of a weight gradient: NOT the power of two the matrix size usually is (16
+// partial copies of a 512 x 512 matrix exactly 1 MB apart fall onto the same L2 slices / DRAM channels and the
+// list-reduce that reads them slot by slot ran at 0.6 TB/s), 16-byte aligned
+static long long tc_part_stride(const StreamLayer& L) { return (long long)L.nout * L.nin + 1056; }
 
 static int tc_ksplit_for(const StreamLayer& L, long long nc) {
   const int tiles = ((L.nout + 255) / 256) * ((L.nin + 255) / 256);
@@ -724,7 +765,7 @@ cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W)
     for (int l = 0; l < nl && e == cudaSuccess; ++l) {
       if (!M.L[l].tc) continue;
       W.tc_ksplit[l] = tc_ksplit_for(M.L[l], Bc);
-      e = cudaMalloc(&W.tc_part[l], (size_t)W.tc_ksplit[l] * M.L[l].nout * M.L[l].nin * sizeof(float));
+      e = cudaMalloc(&W.tc_part[l], (size_t)W.tc_ksplit[l] * tc_part_stride(M.L[l]) * sizeof(float));
       W.tc_rowslots[l] = 2 * (int)((Bc + tcg::BN - 1) / tcg::BN);
       if (e == cudaSuccess) e = cudaMalloc(&W.tc_rowpart[l], (size_t)W.tc_rowslots[l] * M.L[l].nout * sizeof(float));
     }
@@ -902,9 +943,9 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
         ksplit = (nc + kch - 1) / kch;
         tcg::Args t{};
         t.M = L.nout; t.N = L.nin; t.K = nc;
-        t.C = W.tc_part[l]; t.ldc = L.nout; t.accumulate = 0; t.kchunk = kch; t.part_stride = cnt;
+        t.C = W.tc_part[l]; t.ldc = L.nout; t.accumulate = 0; t.kchunk = kch; t.part_stride = tc_part_stride(L);
         SCK(tc2_dw(t, tcg::Operand{Dhi, Dlo, L.nout}, tcg::Operand{W.act_hi[l], W.act_lo[l], L.nin}, ksplit, st));
-        add_item(L.w_off, cnt, W.tc_part[l], ksplit, cnt);
+        add_item(L.w_off, cnt, W.tc_part[l], ksplit, tc_part_stride(L));
         if (bias_slots > 0) add_item(L.b_off, L.nout, W.tc_rowpart[l], bias_slots, L.nout);
         if (bucketed) {
           // the gradient of this layer (and, for the last hidden layer, of the head with the likelihood sums) is
