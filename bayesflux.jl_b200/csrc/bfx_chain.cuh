@@ -9,7 +9,7 @@ namespace bfx {
 // value (and gradient into s.g) of  num_batches*loglike + logprior  on one minibatch.
 // src/model/BNN.jl:50-69.  Returns the value on every thread; gn2 = ||g||^2 over all P.
 // ---------------------------------------------------------------------------------
-template <int NT>
+template <int NT, class SP = TcDyn>
 BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, float nb, double ds0, double ds1,
                            bool want_grad, float& gn2);
 
@@ -40,17 +40,17 @@ BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __
 
 // likelihood sums -> value; sigma prior; network prior; finishes the gradient in s.g (which on entry
 // holds the gradient of  sum_b dl[b]*yhat[b]  w.r.t. theta_net) and its squared norm.
-template <int NT>
+template <int NT, class SP>
 BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, float nb, double ds0, double ds1,
                            bool want_grad, float& gn2) {
-  const float sl = s.th[M.like_s];
+  const float sl = s.th[SP::like_s(M)];
   const float sigma = expf(sl);
   // prior over theta_net + the network part of the gradient; theta_like (element 0 of its own quad) is handled
   // after the reduction because its gradient needs the reduced likelihood sums
   float acc[2] = {0.f, 0.f};  // sum theta_net^2, sum g_net^2
   const float c2 = M.prior_c2;
-  const int like_q = M.like_s;
-  for_each_quad<NT>(M, [&](int k) {
+  const int like_q = SP::like_s(M);
+  for_each_quad_n<NT, SP::fixed>(SP::S(M), [&](int k) {
     const unsigned m = s.mask[k >> 2];
     float4 th = ld4(s.th + k);
     if (k == like_q) th.x = 0.f;

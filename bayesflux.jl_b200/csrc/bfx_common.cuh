@@ -106,6 +106,107 @@ struct ModelDev {
   const unsigned char* pad_mask;  // [S/4]
 };
 
+// ---- shape policies of the tensor-core kernels -------------------------------------------------------------------
+// The fused tensor-core kernel reads every tile offset, leading dimension and layer width through one of these.
+// TcDyn forwards to the run-time descriptors (any eligible model).  TcFixed<...> restates the host's layout rules
+// (bfx_api.cu: build_model_dev / build_tc) as constant expressions for one MLP shape with two hidden layers, so that
+// the layer loops unroll and all address arithmetic folds; the launcher uses such an instance only after `matches`
+// has compared every field with the run-time descriptors, everything else runs the TcDyn instance.
+#if defined(__CUDACC__)
+#define BFX_HD __host__ __device__
+#else
+#define BFX_HD
+#endif
+struct TcDyn {
+  static constexpr bool fixed = false;
+  BFX_HD static int nh(const ModelDev& M) { return M.tc.nh; }
+  BFX_HD static const TcLayer& tl(const ModelDev& M, int l) { return M.tc.L[l]; }
+  BFX_HD static const LayerDev& ld(const ModelDev& M, int l) { return M.L[l]; }
+  BFX_HD static int d_off(const ModelDev& M) { return M.tc.d_off; }
+  BFX_HD static int d_bytes(const ModelDev& M) { return M.tc.d_bytes; }
+  BFX_HD static int S(const ModelDev& M) { return M.S; }
+  BFX_HD static int like_s(const ModelDev& M) { return M.like_s; }
+  BFX_HD static int d_in(const ModelDev& M) { return M.d_in; }
+};
+template <int DIN, int H1, int H2, int ACT1, int ACT2>
+struct TcFixed {
+  static constexpr bool fixed = true;
+  BFX_HD static constexpr int r4(int v) { return (v + 3) & ~3; }
+  BFX_HD static constexpr int oddld(int v) { return ((r4(v) >> 2) & 1) ? r4(v) : r4(v) + 4; }
+  BFX_HD static constexpr int nin(int l) { return l == 0 ? DIN : l == 1 ? H1 : H2; }
+  BFX_HD static constexpr int nout(int l) { return l == 0 ? H1 : l == 1 ? H2 : 1; }
+  BFX_HD static constexpr int nh(const ModelDev&) { return 2; }
+  BFX_HD static constexpr TcLayer tl(const ModelDev&, int l) {
+    TcLayer L{};
+    int off = 0, col = 64;
+    for (int i = 0; i <= l; ++i) {
+      L.kpad = (nin(i) + 15) & ~15;
+      L.ccols = L.kpad + 8;
+      L.hout = nout(i);
+      L.a_bytes = 64 * L.ccols * 2;
+      L.w_bytes = L.kpad * L.hout * 2;
+      L.a_off = off;
+      off += 2 * L.a_bytes;
+      L.w_off = off;
+      off += 2 * L.w_bytes;
+      off = (off + 127) & ~127;
+      L.dw_col = col;
+      col += L.ccols;
+    }
+    return L;
+  }
+  BFX_HD static constexpr int d_off(const ModelDev& M) {
+    const TcLayer L = tl(M, 1);
+    return (L.w_off + 2 * L.w_bytes + 127) & ~127;
+  }
+  BFX_HD static constexpr int d_bytes(const ModelDev&) { return 64 * 64 * 2; }
+  BFX_HD static constexpr LayerDev ld(const ModelDev&, int l) {
+    LayerDev L{};
+    int s_off = 0;
+    for (int i = 0; i <= l; ++i) {
+      L.kind = L_DENSE;
+      L.nin = nin(i);
+      L.nout = nout(i);
+      L.act = i == 0 ? ACT1 : i == 1 ? ACT2 : A_IDENTITY;
+      L.H = L.nout;
+      L.nin_pad = r4(L.nin);
+      L.nout_pad = r4(L.nout);
+      L.ldw = oddld(L.nout);
+      L.ldh = 0;
+      L.w_s = s_off;
+      s_off += L.nin_pad * L.ldw;
+      L.wh_s = 0;
+      L.b_s = s_off;
+      s_off += L.nout_pad;
+    }
+    return L;
+  }
+  BFX_HD static constexpr int like_s(const ModelDev& M) { return ld(M, 2).b_s + 4; }
+  BFX_HD static constexpr int S(const ModelDev& M) { return like_s(M) + 4; }
+  BFX_HD static constexpr int d_in(const ModelDev&) { return DIN; }
+  // host: does the run-time model have exactly this layout?
+  static bool matches(const ModelDev& M) {
+    if (!M.tc.enabled || M.nlayers != 3 || M.tc.nh != 2 || M.rec_layer >= 0 || M.seq) return false;
+    if (M.S != S(M) || M.like_s != like_s(M) || M.d_in != DIN) return false;
+    if (M.tc.d_off != d_off(M) || M.tc.d_bytes != d_bytes(M)) return false;
+    for (int l = 0; l < 3; ++l) {
+      const LayerDev a = ld(M, l);
+      const LayerDev& b = M.L[l];
+      if (a.kind != b.kind || a.nin != b.nin || a.nout != b.nout || a.act != b.act || a.nin_pad != b.nin_pad ||
+          a.nout_pad != b.nout_pad || a.ldw != b.ldw || a.w_s != b.w_s || a.b_s != b.b_s)
+        return false;
+    }
+    for (int l = 0; l < 2; ++l) {
+      const TcLayer a = tl(M, l);
+      const TcLayer& b = M.tc.L[l];
+      if (a.kpad != b.kpad || a.ccols != b.ccols || a.hout != b.hout || a.a_off != b.a_off || a.a_bytes != b.a_bytes ||
+          a.w_off != b.w_off || a.w_bytes != b.w_bytes || a.dw_col != b.dw_col)
+        return false;
+    }
+    return true;
+  }
+};
+
 // sampler hyper-parameters (device copy of bfx_sampler_desc, see include/bfx.h)
 struct SamplerDev {
   int kind, steps, path_len, sadapter_kind, madapter_kind;

@@ -413,6 +413,21 @@ BFX_DEV void for_each_quad(const ModelDev& M, F f) {
   for (int k = 4 * threadIdx.x; k < M.S; k += 4 * NT) f(k);
 }
 
+// the same over S floats given directly; UNROLL: S is a compile-time constant at the call site (shape-specialised
+// kernels, TcFixed), so the loop has a known trip count
+template <int NT, bool UNROLL, class F>
+BFX_DEV void for_each_quad_n(int S, F f) {
+  if (UNROLL) {
+#pragma unroll
+    for (int k0 = 0; k0 < S; k0 += 4 * NT) {
+      const int k = k0 + 4 * (int)threadIdx.x;
+      if (k0 + 4 * NT <= S || k < S) f(k);
+    }
+  } else {
+    for (int k = 4 * threadIdx.x; k < S; k += 4 * NT) f(k);
+  }
+}
+
 // call f(flat index J, padded index k) for every parameter (boundary code only: one table load each)
 template <int NT, class F>
 BFX_DEV void for_each_flat(const ModelDev& M, F f) {

@@ -110,7 +110,7 @@ BFX_DEV ChainScalars load_scalars(const ChainScalars* p) {
 // (chain, chunk) work items from a counter: item i = chunk i / C of chain i % C, chunk_len updates each.  Chunks
 // of one chain run in order (the per-chain counter work[1 + c] is the hand-over), so a launch is balanced over
 // the SMs for any number of chains instead of running ceil(C / resident CTAs) full waves.
-template <int NT, int BT, int KIND, bool TC>
+template <int NT, int BT, int KIND, bool TC, class SP = TcDyn>
 // (at least 512 resident threads per SM for every launch shape = a 128-register cap, and 24 one-warp CTAs = an
 // 80-register cap for the 32-thread shape: without it the small shapes took 200+ registers and ran 10 CTAs per SM;
 // cfg1 127 M -> 200 M grad-evals/s)
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 24 : 512 / NT)) k_mcmc(const _
   const int nchunks = (R.nsteps + R.chunk_len - 1) / R.chunk_len;
   const int ccount = R.c_count > 0 ? R.c_count : R.C;
   const int total = ccount * nchunks;
-  Ctx<NT, BT, TC> X(R, s);
+  Ctx<NT, BT, TC, SP> X(R, s);
   X.tcr = &tr;
   X.key.seed = R.seed;
   while (true) {
@@ -211,14 +211,16 @@ inline cudaError_t launch_eval_t(const EvalDev& E, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int NT, int BT, bool TC = false>
+// SP = a TcFixed shape: only the kinds in KINDS (bit mask) are compiled for it, the launcher of the generic instance
+// handles the rest
+template <int NT, int BT, bool TC = false, class SP = TcDyn, int KINDS = 63>
 inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
   size_t smem = chain_smem_bytes<BT>(R.M) + (size_t)R.M.tc.smem_pad;
   cudaError_t e;
   const RunDev Rf = with_fastdiv(R);
 #define BFX_LAUNCH(KIND)                                                                        \
   {                                                                                             \
-    auto kern = k_mcmc<NT, BT, KIND, TC>;                                                           \
+    auto kern = k_mcmc<NT, BT, KIND, TC, SP>;                                                       \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     if (e != cudaSuccess) return e;                                                             \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,              \
@@ -252,14 +254,16 @@ inline cudaError_t launch_mcmc_t(const RunDev& R, cudaStream_t st) {
                    NT, BT, (int)KIND, (int)TC, smem, R.M.S, R.M.tc.total_bytes, R.M.tc.smem_pad, per_sm, grid); \
     kern<<<(unsigned)grid, NT, smem, st>>>(Rf);                                                 \
   }
+  e = cudaErrorInvalidValue;
   switch (R.S.kind) {
-    case S_SGLD: BFX_LAUNCH(S_SGLD); break;
-    case S_SGNHT: BFX_LAUNCH(S_SGNHT); break;
-    case S_SGNHTS: BFX_LAUNCH(S_SGNHTS); break;
-    case S_GGMC: BFX_LAUNCH(S_GGMC); break;
-    case S_HMC: BFX_LAUNCH(S_HMC); break;
-    default: BFX_LAUNCH(S_MODE); break;
+    case S_SGLD: if constexpr ((KINDS >> S_SGLD) & 1) BFX_LAUNCH(S_SGLD); break;
+    case S_SGNHT: if constexpr ((KINDS >> S_SGNHT) & 1) BFX_LAUNCH(S_SGNHT); break;
+    case S_SGNHTS: if constexpr ((KINDS >> S_SGNHTS) & 1) BFX_LAUNCH(S_SGNHTS); break;
+    case S_GGMC: if constexpr ((KINDS >> S_GGMC) & 1) BFX_LAUNCH(S_GGMC); break;
+    case S_HMC: if constexpr ((KINDS >> S_HMC) & 1) BFX_LAUNCH(S_HMC); break;
+    default: if constexpr ((KINDS >> S_MODE) & 1) BFX_LAUNCH(S_MODE); break;
   }
+  if (e != cudaSuccess) return e;
 #undef BFX_LAUNCH
   return cudaGetLastError();
 }

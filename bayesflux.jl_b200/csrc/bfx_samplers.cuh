@@ -7,8 +7,9 @@
 
 namespace bfx {
 
-template <int NT, int BT, bool TC = false>
+template <int NT, int BT, bool TC = false, class SP = TcDyn>
 struct Ctx {
+  using Shape = SP;
   const RunDev& R;
   tc::Region* tcr = nullptr;  // tensor-core region of this CTA (TC builds only)
   ChainSmem s;
@@ -34,7 +35,7 @@ struct Ctx {
   BFX_DEV float uniform() const { return R.inj_uniforms ? R.inj_uniforms[c] : uniform_draw(key, gstep); }
 
   BFX_DEV double eval(const BatchSrc& b, long long Bn, float nbs, bool want_grad, float& gn2) {
-    if constexpr (TC) return tc::chain_eval_tc<NT>(R.M, s, *tcr, R.x, R.xs, R.y, b, Bn, nbs, want_grad, gn2);
+    if constexpr (TC) return tc::chain_eval_tc<NT, tc::NoShadow, SP>(R.M, s, *tcr, R.x, R.xs, R.y, b, Bn, nbs, want_grad, gn2);
     else return chain_eval<NT, BT>(R.M, s, R.x, R.y, b, Bn, nbs, want_grad, gn2);
   }
   BFX_DEV double grad(float& gn2) { return eval(bs, Bk, R.num_batches, true, gn2); }
@@ -42,7 +43,7 @@ struct Ctx {
   template <class Shadow>
   BFX_DEV double grad_shadow(float& gn2, Shadow job) {
     static_assert(TC, "shadow jobs exist on the tensor-core path only");
-    return tc::chain_eval_tc<NT>(R.M, s, *tcr, R.x, R.xs, R.y, bs, Bk, R.num_batches, true, gn2, job);
+    return tc::chain_eval_tc<NT, Shadow, SP>(R.M, s, *tcr, R.x, R.xs, R.y, bs, Bk, R.num_batches, true, gn2, job);
   }
   // loglikeprior(bnn, θ, bnn.x, bnn.y): full data, num_batches = 1 (ggmc.jl:147,176; hmc.jl:135-136)
   BFX_DEV double full_lp() {
@@ -64,8 +65,8 @@ BFX_DEV bool block_any(bool f, float* red) {
 }
 
 // where the ns-th sample of this chain is kept (flat row of P floats), or nullptr when it is not kept
-template <int NT, int BT, bool TC>
-BFX_DEV float* sample_slot(const Ctx<NT, BT, TC>& X, long long ns) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV float* sample_slot(const Ctx<NT, BT, TC, SP>& X, long long ns) {
   const RunDev& R = X.R;
   if (!R.samples) return nullptr;
   unsigned long long q, r;
@@ -88,8 +89,8 @@ BFX_DEV long long hist_index(const RunDev& R, int c, long long i) {
   return (k < 0 || k >= R.hist_stride) ? -1 : (long long)c * R.hist_stride + k;
 }
 // row of the DiagCov window ring (padded layout) that takes the ns-th sample
-template <int NT, int BT, bool TC>
-BFX_DEV float* window_slot(const Ctx<NT, BT, TC>& X, long long ns) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV float* window_slot(const Ctx<NT, BT, TC, SP>& X, long long ns) {
   unsigned long long q, r;
   fdivmod(X.R.fd_window, (unsigned long long)(ns - 1), q, r);
   return X.ring + (long long)r * (long long)X.R.Ps;
@@ -124,8 +125,8 @@ BFX_DEV void rec_store(const Recorder& r, int k, unsigned m, const float4& t, in
 
 // s.samples[:, t] = copy(θ)  (+ DiagCov window ring).  ns = nsampled AFTER the increment.
 // Recorded samples leave the engine in the reference's flat order; the window ring is internal (padded).
-template <int NT, int BT, bool TC>
-BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV void record_sample(Ctx<NT, BT, TC, SP>& X, long long ns) {
   const RunDev& R = X.R;
   float* dst = sample_slot(X, ns);
   if (dst) {
@@ -143,8 +144,8 @@ BFX_DEV void record_sample(Ctx<NT, BT, TC>& X, long long ns) {
   }
 }
 
-template <int NT, int BT, bool TC>
-BFX_DEV Recorder make_recorder(Ctx<NT, BT, TC>& X, long long ns) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV Recorder make_recorder(Ctx<NT, BT, TC, SP>& X, long long ns) {
   Recorder r{sample_slot(X, ns), nullptr};
   if (X.ring) r.rdst = window_slot(X, ns);
   return r;
@@ -185,8 +186,8 @@ BFX_DEV bool any_nan(const float4& v) { return v.x != v.x || v.y != v.y || v.z !
 
 // madapter(s, θ, bnn, ∇θ) -> Minv (diagonal).  The gradient RMSProp asks for is the one
 // of the current minibatch at the current θ, which is what s.g already holds.
-template <int NT, int BT, bool TC>
-BFX_DEV void mass_adapt(Ctx<NT, BT, TC>& X, float gn2) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV void mass_adapt(Ctx<NT, BT, TC, SP>& X, float gn2) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   if (S.madapter_kind == MA_RMSPROP) {
@@ -238,8 +239,8 @@ BFX_DEV void mass_adapt(Ctx<NT, BT, TC>& X, float gn2) {
 // --------------------------------------------------------------------------------
 // SGLD  (src/inference/mcmc/sgld.jl:96-112)
 // --------------------------------------------------------------------------------
-template <int NT, int BT, bool TC>
-BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV void step_sgld(Ctx<NT, BT, TC, SP>& X) {
   const SamplerDev& S = X.R.S;
   // sgld.jl:12  a (b + t)^(-gamma): exp2(-gamma log2(b + t)) with the full-precision log2f / exp2f, within 2e-6
   // relative of powf for t < 2^24 and a third of its instructions
@@ -275,7 +276,7 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
   const float* inj = X.inj(0);
   X.sc.nsampled += 1;
   BFX_TICK(14);
-  for_each_quad<NT>(X.R.M, [&](int k) {
+  for_each_quad_n<NT, SP::fixed>(SP::S(X.R.M), [&](int k) {
     const unsigned m = X.s.mask[k >> 2];
     if (!m) return;
     const int J0 = X.s.qflat[k >> 2];
@@ -295,8 +296,8 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC>& X) {
 // --------------------------------------------------------------------------------
 // SGNHT  (src/inference/mcmc/sgnht.jl:64-90)
 // --------------------------------------------------------------------------------
-template <int NT, int BT, bool TC>
-BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV void step_sgnht(Ctx<NT, BT, TC, SP>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   float gn2;
@@ -346,8 +347,8 @@ BFX_DEV void step_sgnht(Ctx<NT, BT, TC>& X) {
 // --------------------------------------------------------------------------------
 // SGNHTS  (src/inference/mcmc/sgnht-s.jl:81-116), BAOAB-like splitting, diagonal Minv
 // --------------------------------------------------------------------------------
-template <int NT, int BT, bool TC>
-BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV void step_sgnhts(Ctx<NT, BT, TC, SP>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   float gn2;
@@ -424,8 +425,8 @@ BFX_DEV void step_sgnhts(Ctx<NT, BT, TC>& X) {
 // --------------------------------------------------------------------------------
 // GGMC  (src/inference/mcmc/ggmc.jl:140-198), diagonal mass
 // --------------------------------------------------------------------------------
-template <int NT, int BT, bool TC>
-BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV void step_ggmc(Ctx<NT, BT, TC, SP>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   const float N = (float)R.n;
@@ -530,8 +531,8 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC>& X) {
 // --------------------------------------------------------------------------------
 // HMC  (src/inference/mcmc/hmc.jl:105-159): one call = one leapfrog stage
 // --------------------------------------------------------------------------------
-template <int NT, int BT, bool TC>
-BFX_DEV void step_hmc(Ctx<NT, BT, TC>& X) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV void step_hmc(Ctx<NT, BT, TC, SP>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   const float l = X.sc.l;
@@ -635,8 +636,8 @@ BFX_DEV float block_max(float v, float* red) {
   return v;
 }
 
-template <int NT, int BT, bool TC>
-BFX_DEV void step_mode(Ctx<NT, BT, TC>& X) {
+template <int NT, int BT, bool TC, class SP>
+BFX_DEV void step_mode(Ctx<NT, BT, TC, SP>& X) {
   const RunDev& R = X.R;
   const SamplerDev& S = R.S;
   if (X.sc.converged) return;

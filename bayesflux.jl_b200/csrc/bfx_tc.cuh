@@ -271,12 +271,12 @@ BFX_DEV void teardown(const ModelDev& M, Region& R) {
 }
 
 // theta (FP32 master copy in s.th) -> hi/lo BF16 weight tiles.  Tile element (r = fan-in i, c = fan-out o).
-template <int NT>
+template <int NT, class SP = TcDyn>
 BFX_DEV void pack_weights(const ModelDev& M, const ChainSmem& s, const Region& R) {
-  const TcDesc& T = M.tc;
-  for (int l = 0; l < T.nh; ++l) {
-    const TcLayer& L = T.L[l];
-    const LayerDev& D = M.L[l];
+#pragma unroll(SP::fixed ? 2 : 1)
+  for (int l = 0; l < SP::nh(M); ++l) {
+    const TcLayer& L = SP::tl(M, l);
+    const LayerDev& D = SP::ld(M, l);
     const int noc = L.hout >> 3;           // 8-wide fan-out chunks
     const int nin8 = (D.nin + 7) >> 3;     // 8-row fan-in blocks (rows i >= nin stay zero)
     unsigned char* hi = R.base + L.w_off;
@@ -319,13 +319,12 @@ BFX_DEV void mma3(uint32_t d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t
 struct NoShadow {
   BFX_DEV void operator()() const {}
 };
-template <int NT, class Shadow = NoShadow>
+template <int NT, class Shadow = NoShadow, class SP = TcDyn>
 BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, const float* __restrict__ x,
                              const uint4* __restrict__ xs, const float* __restrict__ y, const BatchSrc& bs, long long B,
                              float nb, bool want_grad, float& gn2, Shadow shadow = Shadow{}) {
   static_assert(NT == 256, "the tensor-core path uses 8 warps: 4 lane quadrants x 2 column halves");
-  const TcDesc& T = M.tc;
-  const int nh = T.nh;
+  const int nh = SP::nh(M);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // warp index / TMEM base broadcast from lane 0: tells the compiler they are warp-uniform, so the MMA-issue code
   // (descriptor arithmetic included) runs on the uniform datapath instead of per-thread registers + R2UR moves
@@ -334,15 +333,15 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   const int q = warp & 3, h = warp >> 2;
   const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8;  // the two batch rows of this thread's fragment
   const uint32_t zaddr = R.tmem + ((uint32_t)(32 * q) << 16);
-  const LayerDev& LO = M.L[M.nlayers - 1];  // the 1-wide output layer
-  const float sl = s.th[M.like_s];
+  const LayerDev& LO = SP::ld(M, nh);  // the 1-wide output layer
+  const float sl = s.th[SP::like_s(M)];
   const float inv_sigma = 1.f / expf(sl);
   double ds0 = 0.0, ds1 = 0.0;
 
   BFX_TICK(0);  // everything since the previous evaluation ended (update, record, bookkeeping)
   if (want_grad)
     for (int k = tid; k < 72; k += NT) R.glast[k] = 0.f;
-  if (!xs) pack_weights<NT>(M, s, R);  // (with xs: packed while the first tile's copies are in flight)
+  if (!xs) pack_weights<NT, SP>(M, s, R);  // (with xs: packed while the first tile's copies are in flight)
   // (made visible to the async proxy by the fence + barrier after the first tile is staged)
 
   // ---- dW accumulators (TMEM) -> s.g in the padded parameter layout.  ADD = std::true_type: add to what an earlier
@@ -358,9 +357,10 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
     constexpr bool add = decltype(ADD)::value;
     auto put = [&](float* p, float v) { *p = add ? *p + v : v; };
     fence_after();
+#pragma unroll(SP::fixed ? 2 : 1)
     for (int l = 0; l < nh; ++l) {
-      const TcLayer& L = T.L[l];
-      const LayerDev& D = M.L[l];
+      const TcLayer& L = SP::tl(M, l);
+      const LayerDev& D = SP::ld(M, l);
       const int ngroups = L.ccols >> 3;
       // 64 columns that lie fully inside the weight matrix: one 32-column fragment per column half
       int g0 = 0;
@@ -409,7 +409,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   };
   int acc_tiles = 0;
   bool dumped = false;
-  const int d = M.d_in;
+  const int d = SP::d_in(M);
   for (long long t0 = 0; t0 < B; t0 += 64) {
     const int nvalid = (int)((B - t0) < 64 ? (B - t0) : 64);
     const bool first_tile = t0 == 0;
@@ -418,7 +418,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       // x was split once per data set into rows of [hi chunks | lo chunks] (16 bytes = 8 bf16 each): staging is one
       // asynchronous 16-byte copy per chunk straight into the core-block tile.  Four adjacent threads own one
       // batch row (each derives the row's observation index itself: no index exchange, no barrier).
-      const TcLayer& L0 = T.L[0];
+      const TcLayer& L0 = SP::tl(M, 0);
       const int nch = L0.kpad >> 3, cpr = 2 * nch;
       const int sbo = (L0.ccols >> 3) * 128;
       const int b = tid >> 2;
@@ -431,7 +431,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       }
       if ((tid & 3) == 0) cp_async4(s.ys + b, y + (o >= 0 ? o : 0), o >= 0 ? 4 : 0);
       BFX_TICK(1);  // stage: indices + copy issue
-      if (first_tile) pack_weights<NT>(M, s, R);  // theta -> bf16 weight tiles, in the shadow of the copies
+      if (first_tile) pack_weights<NT, SP>(M, s, R);  // theta -> bf16 weight tiles, in the shadow of the copies
       cp_async_wait_all();
     } else {
       if (tid < 64) {
@@ -440,7 +440,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         s.ys[tid] = (o >= 0) ? __ldg(y + o) : 0.f;
       }
       __syncthreads();
-      const TcLayer& L0 = T.L[0];
+      const TcLayer& L0 = SP::tl(M, 0);
       const int nch = L0.kpad >> 3;
       const int sbo = (L0.ccols >> 3) * 128;
       unsigned char* hi = R.base + L0.a_off;
@@ -473,13 +473,14 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
     // ---- forward ---------------------------------------------------------------------------------
     float a[16];       // activations of the last hidden layer (this thread's fragment)
     float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll(SP::fixed ? 2 : 1)
     for (int l = 0; l < nh; ++l) {
-      const TcLayer& L = T.L[l];
-      const LayerDev& D = M.L[l];
+      const TcLayer& L = SP::tl(M, l);
+      const LayerDev& D = SP::ld(M, l);
       if (warp_u == 0) {
         fence_after();
         const bool lead = elect_one();
-        const IssueDesc& D = R.idesc[__shfl_sync(0xffffffffu, l, 0)];  // (uniform layer index: see warp_u)
+        const IssueDesc& D = R.idesc[SP::fixed ? l : __shfl_sync(0xffffffffu, l, 0)];  // (uniform layer index: see warp_u)
         uint64_t dahi = D.f_ahi, dalo = D.f_alo, dbhi = D.f_bhi, dblo = D.f_blo;
         const uint32_t idesc = D.idesc_f;
         const uint64_t astep = 256 >> 4, bstep = D.bstep_f;  // a k-step only moves the start-address field
@@ -525,7 +526,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       });
       if (l + 1 < nh) {
         // next layer's input tile
-        const TcLayer& Ln = T.L[l + 1];
+        const TcLayer& Ln = SP::tl(M, l + 1);
         const int sbo = (Ln.ccols >> 3) * 128;
         unsigned char* hi = R.base + Ln.a_off;
         unsigned char* lo = hi + Ln.a_bytes;
@@ -553,7 +554,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       }
     }
     // ---- output layer (fan-out 1) + likelihood on the fragment of the last hidden layer -----------
-    const int hl = T.L[nh - 1].hout;
+    const int hl = SP::tl(M, nh - 1).hout;
     const int cbase = 32 * h + 2 * (lane & 3);
     float wl[8];
     {
@@ -636,9 +637,9 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
       }
       // delta of the last hidden layer -> D tile (64 x 64, zero beyond hl)
       {
-        const int act_l = M.L[nh - 1].act;
-        unsigned char* hi = R.base + T.d_off;
-        unsigned char* lo = hi + T.d_bytes;
+        const int act_l = SP::ld(M, nh - 1).act;
+        unsigned char* hi = R.base + SP::d_off(M);
+        unsigned char* lo = hi + SP::d_bytes(M);
         const int offb = (r0 >> 3) * 1024 + (r0 & 7) * 16 + (lane & 3) * 4 + h * 512;
         with_act(act_l, [&](auto A) {
           using AT = decltype(A);
@@ -666,13 +667,14 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
         R.glast[tid] += (R.gpart[tid] + R.gpart[65 + tid]) + (R.gpart[130 + tid] + R.gpart[195 + tid]);
       BFX_TICK(5);  // output layer + likelihood + delta tile
       // ---- backward ------------------------------------------------------------------------------
+#pragma unroll(SP::fixed ? 2 : 1)
       for (int lv = nh - 1; lv >= 0; --lv) {
         const int l = lv;
-        const TcLayer& L = T.L[l];
+        const TcLayer& L = SP::tl(M, l);
         if (warp_u == 0) {
           fence_after();
           const bool lead = elect_one();
-          const int l = __shfl_sync(0xffffffffu, lv, 0);  // (uniform layer index: see warp_u)
+          const int l = SP::fixed ? lv : __shfl_sync(0xffffffffu, lv, 0);  // (uniform layer index: see warp_u)
           const IssueDesc& D = R.idesc[l];
           if (lead) {
             if (l > 0) {
@@ -712,7 +714,7 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           BFX_TICK(6);  // backward MMA issue + wait (dA)
           // delta of layer l-1 = dA * act'(A_{l-1}); A_{l-1} is the input tile of layer l
           const int hp = L.kpad;  // = fan-out of layer l-1
-          const int act_p = M.L[l - 1].act;
+          const int act_p = SP::ld(M, l - 1).act;
           const bool active = 32 * h < hp;
           float da[16];
           if (active) ld_16x256b_x4(zaddr + (uint32_t)(32 * h), da);
@@ -746,8 +748,8 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
           // the dW MMAs of layer l still read the D tile: wait for them before overwriting it
           mbar_wait(&R.bar[2], R.par[2]);
           R.par[2] ^= 1;
-          unsigned char* hi = R.base + T.d_off;
-          unsigned char* lo = hi + T.d_bytes;
+          unsigned char* hi = R.base + SP::d_off(M);
+          unsigned char* lo = hi + SP::d_bytes(M);
           const int offd = (r0 >> 3) * 1024 + (r0 & 7) * 16 + (lane & 3) * 4 + h * 512;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -784,14 +786,14 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   if (want_grad) {
     if (dumped) dump(std::true_type{});
     else dump(std::false_type{});
-    const int hl = T.L[nh - 1].hout;
+    const int hl = SP::tl(M, nh - 1).hout;
     for (int k = tid; k < hl; k += NT) s.g[LO.w_s + k * LO.ldw] = R.glast[k];
     if (tid == 0) s.g[LO.b_s] = R.glast[64];
     fence_before();
   }
   __syncthreads();
   BFX_TICK(9);  // gradient dump
-  const double v__ = eval_finish<NT>(M, s, B, nb, ds0, ds1, want_grad, gn2);
+  const double v__ = eval_finish<NT, SP>(M, s, B, nb, ds0, ds1, want_grad, gn2);
   BFX_TICK(10);  // prior + norms + value
   return v__;
 }

@@ -157,11 +157,11 @@ BFX_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c
 #define BFX_GT(i) do { } while (0)
 #endif
 
-// D = F32, A = B = BF16, M = 128 * CG, N = 256
+// D = F32, A = B = BF16, M = 128 * CG, N = bn
 template <int CG>
-BFX_DEV uint32_t idesc_of(int a_mn, int b_mn) {
+BFX_DEV uint32_t idesc_of(int a_mn, int b_mn, int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+         ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 }
 
 // stage `rows` rows (mn) x 64 k of one operand half at `dst`
@@ -179,7 +179,8 @@ template <int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(256, 1)
 k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
            const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
-           const __grid_constant__ CUtensorMap mChi, const __grid_constant__ CUtensorMap mClo, const Args g) {
+           const __grid_constant__ CUtensorMap mChi, const __grid_constant__ CUtensorMap mClo,
+           const __grid_constant__ CUtensorMap mChi2, const __grid_constant__ CUtensorMap mClo2, const Args g) {
   using C = Cfg<CG>;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[C::STAGES], bar_empty[C::STAGES], bar_acc;
@@ -189,8 +190,10 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const int mtile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int m0 = mtile * (BM * CG) + (int)rank * BM;         // first accumulator row of this CTA
-  const int n0 = (int)blockIdx.y * BN;                        // first accumulator column
-  const int nb0 = n0 + (int)rank * C::BROWS;                  // first B row staged by this CTA
+  const int bn = g.bn ? g.bn : BN;                            // accumulator columns of this launch (256 or 224)
+  const int brows = bn / CG;                                  // rows of B staged by one CTA
+  const int n0 = (int)blockIdx.y * bn;                        // first accumulator column
+  const int nb0 = n0 + (int)rank * brows;                     // first B row staged by this CTA
   const int kbeg = (int)blockIdx.z * g.kchunk;
   int kend = kbeg + g.kchunk;
   if (kend > g.K) kend = g.K;
@@ -212,11 +215,21 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mBlo) : "memory");
   }
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // barrier inits visible (to the peer) before anything arrives
+  // The producer starts fetching at once; the TMEM allocation (warp 2) is awaited by warps 1-7 only (named barrier),
+  // warp 0 picks the address up after the accumulator barrier, which orders it behind the allocation.
+#ifdef BFX_GEMM_NO_EARLY
   if (warp == 2) tmem_alloc<CG>(&tmem_slot, (uint32_t)BN);
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
-  const uint32_t tmem = tmem_slot;
+#else
+  if (warp != 0) {
+    if (warp == 2) tmem_alloc<CG>(&tmem_slot, (uint32_t)BN);
+    tc::fence_before();
+    asm volatile("bar.sync 3, 224;" ::: "memory");
+    tc::fence_after();
+  }
+#endif
   BFX_GT(7);
 
   if (warp == 0) {
@@ -226,19 +239,20 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
         const int s = kb % C::STAGES;
         const uint32_t ph = (uint32_t)(kb / C::STAGES) & 1u;
         tc::mbar_wait(&bar_empty[s], ph ^ 1u);
-        if (rank == 0) mbar_expect_tx(&bar_full[s], (uint32_t)(C::STAGE * CG));
+        if (rank == 0) mbar_expect_tx(&bar_full[s], (uint32_t)((2 * TILE_A + 2 * brows * BK * 2) * CG));
         unsigned char* st = smem + s * C::STAGE;
         const int k0 = kbeg + kb * BK;
         load_operand<CG, A_MN>(st, &mAhi, &bar_full[s], m0, k0, BM);
         load_operand<CG, A_MN>(st + TILE_A, &mAlo, &bar_full[s], m0, k0, BM);
-        load_operand<CG, B_MN>(st + 2 * TILE_A, &mBhi, &bar_full[s], nb0, k0, C::BROWS);
-        load_operand<CG, B_MN>(st + 2 * TILE_A + C::TILE_B, &mBlo, &bar_full[s], nb0, k0, C::BROWS);
+        load_operand<CG, B_MN>(st + 2 * TILE_A, &mBhi, &bar_full[s], nb0, k0, brows);
+        load_operand<CG, B_MN>(st + 2 * TILE_A + C::TILE_B, &mBlo, &bar_full[s], nb0, k0, brows);
       }
     }
     __syncwarp();
   } else if (warp == 1 && rank == 0) {
     // ---------------- MMA issuer (leader CTA) ----------------
-    const uint32_t idesc = idesc_of<CG>(A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint32_t idesc = idesc_of<CG>(A_MN ? 1 : 0, B_MN ? 1 : 0, bn);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % C::STAGES;
       const uint32_t ph = (uint32_t)(kb / C::STAGES) & 1u;
@@ -273,7 +287,9 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
     tc::mbar_wait(&bar_acc, 0u);
     tc::fence_after();
     BFX_GT(3);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
     const int q = warp & 3, half = warp >> 2;
+    const int nblk = half == 0 ? 4 : (bn - 128) / 32;   // 32-column blocks of this warp half (bn = 224: 4 + 3)
     const int mloc = 32 * q + lane;
     const long long m = (long long)m0 + mloc;
     float* Cp = g.C ? g.C + (long long)blockIdx.z * g.part_stride : nullptr;
@@ -353,7 +369,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
     if (EPI == EPI_PLAIN) {  // FP32 stores only: the plain loop keeps 32 stores in flight per load
       const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * half);
 #pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
+      for (int cb = 0; cb < nblk; ++cb) {
         uint32_t ra[32];
         ld_row32_issue(tbase + 32 * cb, ra);
         ld_row32_wait(ra);
@@ -370,10 +386,12 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
       ld_row32_issue(tbase + 64, ra);
       process(1, rb);
       ld_row32_wait(ra);
-      ld_row32_issue(tbase + 96, rb);
+      if (nblk > 3) ld_row32_issue(tbase + 96, rb);
       process(2, ra);
-      ld_row32_wait(rb);
-      process(3, rb);
+      if (nblk > 3) {
+        ld_row32_wait(rb);
+        process(3, rb);
+      }
     }
     if (EPI == EPI_MUL_DACT && g.rowpart && m < g.M) g.rowpart[(long long)(2 * blockIdx.y + half) * g.M + m] = rsum;
     BFX_GT(4);
@@ -381,8 +399,9 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
       tc::fence_async_smem();  // generic-proxy stores -> visible to the TMA engine
       asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
       if (q == 0 && lane == 0 && m0 < g.M && n0 + 128 * half < g.N) {  // rows / columns beyond M / N are clipped by the TMA
-        tma_store_2d(&mChi, stage_hi, m0, n0 + 128 * half);
-        tma_store_2d(&mClo, stage_lo, m0, n0 + 128 * half);
+        // (the second half's box is bn - 128 columns wide: it must not reach into the next tile)
+        tma_store_2d(half ? &mChi2 : &mChi, stage_hi, m0, n0 + 128 * half);
+        tma_store_2d(half ? &mClo2 : &mClo, stage_lo, m0, n0 + 128 * half);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
@@ -391,7 +410,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
   }
   tc::fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 2) tmem_free<CG>(tmem, (uint32_t)BN);
+  if (warp == 2) tmem_free<CG>(*reinterpret_cast<volatile uint32_t*>(&tmem_slot), (uint32_t)BN);
   BFX_GT(6);
 }
 
@@ -431,11 +450,12 @@ inline cudaError_t make_map(CUtensorMap* map, const __nv_bfloat16* base, bool mn
 }
 
 // output halves: element (m, n) at base[m + ldc * n], box 128 rows x 128 columns, no swizzle
-inline cudaError_t make_store_map(CUtensorMap* map, __nv_bfloat16* base, long long M, long long N, long long ldc) {
+inline cudaError_t make_store_map(CUtensorMap* map, __nv_bfloat16* base, long long M, long long N, long long ldc,
+                                  int box_cols = 128) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return cudaErrorNotSupported;
   cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)N}, strides[1] = {(cuuint64_t)ldc * 2};
-  cuuint32_t box[2] = {128, 128}, estr[2] = {1, 1};
+  cuuint32_t box[2] = {128, (cuuint32_t)box_cols}, estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -446,20 +466,28 @@ template <int CG, bool A_MN, bool B_MN, int EPI>
 inline cudaError_t launch(const Args& g0, const Operand& A, const Operand& B, const Output& O, int ksplit, cudaStream_t st) {
   using C = Cfg<CG>;
   Args g = g0;
-  CUtensorMap mAhi, mAlo, mBhi, mBlo, mChi, mClo;
+  CUtensorMap mAhi, mAlo, mBhi, mBlo, mChi, mClo, mChi2, mClo2;
   cudaError_t e;
   memset(&mChi, 0, sizeof mChi);
   memset(&mClo, 0, sizeof mClo);
+  memset(&mChi2, 0, sizeof mChi2);
+  memset(&mClo2, 0, sizeof mClo2);
+  // tile width: 224 columns when that fills the machine better (B K-major only: its rows come as one box)
+  const int bn = (CG == 2 && !B_MN && g.bn != BN) ? tile_cols_kmajor_b(g.M, g.N) : BN;
+  g.bn = bn;
+  const int brows = bn / CG;
   g.store_split = 0;
   if (EPI != EPI_PLAIN && O.hi) {
     if ((e = make_store_map(&mChi, O.hi, g.M, g.N, g.ldc)) != cudaSuccess) return e;
     if ((e = make_store_map(&mClo, O.lo, g.M, g.N, g.ldc)) != cudaSuccess) return e;
+    if ((e = make_store_map(&mChi2, O.hi, g.M, g.N, g.ldc, bn - 128)) != cudaSuccess) return e;
+    if ((e = make_store_map(&mClo2, O.lo, g.M, g.N, g.ldc, bn - 128)) != cudaSuccess) return e;
     g.store_split = 1;
   }
   if ((e = make_map(&mAhi, A.hi, A_MN, g.M, g.K, A.ld, BM)) != cudaSuccess) return e;
   if ((e = make_map(&mAlo, A.lo, A_MN, g.M, g.K, A.ld, BM)) != cudaSuccess) return e;
-  if ((e = make_map(&mBhi, B.hi, B_MN, g.N, g.K, B.ld, C::BROWS)) != cudaSuccess) return e;
-  if ((e = make_map(&mBlo, B.lo, B_MN, g.N, g.K, B.ld, C::BROWS)) != cudaSuccess) return e;
+  if ((e = make_map(&mBhi, B.hi, B_MN, g.N, g.K, B.ld, brows)) != cudaSuccess) return e;
+  if ((e = make_map(&mBlo, B.lo, B_MN, g.N, g.K, B.ld, brows)) != cudaSuccess) return e;
   auto kern = k_tc_gemm2<CG, A_MN, B_MN, EPI>;
   {  // once per device and template instance (function attributes are per context)
     static unsigned long long done = 0ull;
@@ -472,7 +500,7 @@ inline cudaError_t launch(const Args& g0, const Operand& A, const Operand& B, co
   }
   cudaLaunchConfig_t cfg{};
   const int mt = (g.M + BM * CG - 1) / (BM * CG);
-  cfg.gridDim = dim3((unsigned)(mt * CG), (unsigned)((g.N + BN - 1) / BN), (unsigned)ksplit);
+  cfg.gridDim = dim3((unsigned)(mt * CG), (unsigned)((g.N + bn - 1) / bn), (unsigned)ksplit);
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = st;
@@ -483,7 +511,7 @@ inline cudaError_t launch(const Args& g0, const Operand& A, const Operand& B, co
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, mAhi, mAlo, mBhi, mBlo, mChi, mClo, g);
+  return cudaLaunchKernelEx(&cfg, kern, mAhi, mAlo, mBhi, mBlo, mChi, mClo, mChi2, mClo2, g);
 }
 
 }  // namespace tcg

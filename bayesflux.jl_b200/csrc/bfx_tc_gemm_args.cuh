@@ -9,7 +9,7 @@ namespace bfx {
 namespace tcg {
 
 constexpr int BM = 128;   // accumulator rows per CTA
-constexpr int BN = 256;   // accumulator columns
+constexpr int BN = 256;   // accumulator columns (TMEM allocation; a launch may use 224 of them, Args::bn)
 constexpr int BK = 64;    // K per stage = one 128-byte swizzle span of BF16
 constexpr int TILE_A = BM * BK * 2;  // one half (hi or lo) of the A stage, 16 KB
 
@@ -33,8 +33,21 @@ struct Args {
   int accumulate;        // EPI_PLAIN, single split: C += acc
   int kchunk;            // split-K: blockIdx.z handles k in [z * kchunk, ...), multiple of BK; writes C + z * part_stride
   long long part_stride;
+  int bn;                // accumulator columns per tile: 256, or 224 when B is K-major (8 192 columns = 37 tiles x 2 row
+                         // pairs = 148 CTAs, one full wave, instead of 128); 0 = 256
   long long* timing;     // BFX_GEMM_TIMING builds: [CTA][8] clock64 marks
 };
+
+// accumulator columns per tile of a cta_group::2 launch whose B operand is K-major (forward, input gradient): 224
+// when that needs fewer waves of the 74 CTA pairs than 256 (every consumer of per-tile partials must use this too)
+inline int tile_cols_kmajor_b(long long M, long long N) {
+#ifdef BFX_GEMM_NO224
+  return BN;
+#endif
+  const long long mt2 = (M + 2 * BM - 1) / (2 * BM);
+  auto cost = [&](long long w) { const long long cl = mt2 * ((N + w - 1) / w); return ((cl + 73) / 74) * w; };
+  return cost(224) < cost(BN) ? 224 : BN;
+}
 
 struct Operand {
   const __nv_bfloat16* hi;
