@@ -253,6 +253,7 @@ static int32_t build_model_dev(bfx_model* m, const bfx_like_desc* like, const bf
   M.sprior_kind = like->sigma_prior_kind;
   M.sprior_a = (float)like->sigma_prior_a;
   M.sprior_b = (float)like->sigma_prior_b;
+  M.sprior_rb = 1.0 / (double)M.sprior_b;
   if (!(like->sigma_prior_a > 0) || !(like->sigma_prior_b > 0)) return fail(BFX_ERR_BAD_ARG, "sigma prior parameters must be > 0");
   if (like->sigma_prior_kind == BFX_SIGMA_GAMMA)
     M.sprior_const = -std::lgamma(like->sigma_prior_a) - like->sigma_prior_a * std::log(like->sigma_prior_b);

@@ -9,9 +9,13 @@ namespace bfx {
 // value (and gradient into s.g) of  num_batches*loglike + logprior  on one minibatch.
 // src/model/BNN.jl:50-69.  Returns the value on every thread; gn2 = ||g||^2 over all P.
 // ---------------------------------------------------------------------------------
-template <int NT, class SP = TcDyn>
+// PASS = false: the caller has already folded the prior into s.g and passes its per-thread partial sums of
+// theta_net^2 (a0) and of the squared finished gradient (a1): only the block reduction is left (tensor-core path)
+// VAL = false: the caller does not use the value (every sampler's gradient call): theta_net^2 and the value
+// arithmetic are skipped, and so is the second likelihood sum when the likelihood is Normal
+template <int NT, class SP = TcDyn, bool PASS = true, bool VAL = true>
 BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, float nb, double ds0, double ds1,
-                           bool want_grad, float& gn2);
+                           bool want_grad, float& gn2, float a0 = 0.f, float a1 = 0.f);
 
 template <int NT, int BT>
 BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
@@ -40,17 +44,17 @@ BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __
 
 // likelihood sums -> value; sigma prior; network prior; finishes the gradient in s.g (which on entry
 // holds the gradient of  sum_b dl[b]*yhat[b]  w.r.t. theta_net) and its squared norm.
-template <int NT, class SP>
+template <int NT, class SP, bool PASS, bool VAL>
 BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, float nb, double ds0, double ds1,
-                           bool want_grad, float& gn2) {
+                           bool want_grad, float& gn2, float a0, float a1) {
   const float sl = s.th[SP::like_s(M)];
   const float sigma = expf(sl);
   // prior over theta_net + the network part of the gradient; theta_like (element 0 of its own quad) is handled
   // after the reduction because its gradient needs the reduced likelihood sums
-  float acc[2] = {0.f, 0.f};  // sum theta_net^2, sum g_net^2
+  float acc[2] = {a0, a1};  // sum theta_net^2, sum g_net^2
   const float c2 = M.prior_c2;
   const int like_q = SP::like_s(M);
-  for_each_quad_n<NT, SP::fixed>(SP::S(M), [&](int k) {
+  if (PASS) for_each_quad_n<NT, SP::fixed>(SP::S(M), [&](int k) {
     const unsigned m = s.mask[k >> 2];
     float4 th = ld4(s.th + k);
     if (k == like_q) th.x = 0.f;
@@ -64,11 +68,12 @@ BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, f
     }
   });
   // ONE block reduction for everything: the likelihood sums in double, the two norms in float
+  const bool two = VAL || M.like_kind != LK_NORMAL;  // (the second likelihood sum only feeds the TDist gradient)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ds0 += __shfl_xor_sync(0xffffffffu, ds0, o);
-    ds1 += __shfl_xor_sync(0xffffffffu, ds1, o);
-    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+    if (two) ds1 += __shfl_xor_sync(0xffffffffu, ds1, o);
+    if (VAL) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
     acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], o);
   }
   if (NT > 32) {
@@ -90,19 +95,19 @@ BFX_DEV double eval_finish(const ModelDev& M, const ChainSmem& s, long long B, f
 #pragma unroll
     for (int ww = 0; ww < NT / 32; ++ww) {
       ds0 += dred[2 * ww];
-      ds1 += dred[2 * ww + 1];
-      acc[0] += fred[2 * ww];
+      if (two) ds1 += dred[2 * ww + 1];
+      if (VAL) acc[0] += fred[2 * ww];
       acc[1] += fred[2 * ww + 1];
     }
   }
   // sigma prior (log link): logpdf(prior, e^s) + s and its derivative w.r.t. s
-  double lps, dlps;
+  double lps = 0.0, dlps;
   if (M.sprior_kind == SP_GAMMA) {
-    lps = M.sprior_const + ((double)M.sprior_a - 1.0) * (double)sl - (double)sigma / (double)M.sprior_b + (double)sl;
-    dlps = (double)M.sprior_a - (double)sigma / (double)M.sprior_b;
+    if (VAL) lps = M.sprior_const + ((double)M.sprior_a - 1.0) * (double)sl - (double)sigma / (double)M.sprior_b + (double)sl;
+    dlps = (double)M.sprior_a - (double)sigma * M.sprior_rb;
   } else {
-    lps = M.sprior_const - ((double)M.sprior_a + 1.0) * (double)sl - (double)M.sprior_b / (double)sigma + (double)sl;
-    dlps = -(double)M.sprior_a + (double)M.sprior_b / (double)sigma;
+    if (VAL) lps = M.sprior_const - ((double)M.sprior_a + 1.0) * (double)sl - (double)M.sprior_b / (double)sigma + (double)sl;
+    dlps = -(double)M.sprior_a + (double)M.sprior_b * (double)(1.f / sigma);
   }
   double like, dlike_ds;
   if (M.like_kind == LK_NORMAL) {

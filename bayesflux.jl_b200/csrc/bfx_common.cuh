@@ -87,6 +87,7 @@ struct ModelDev {
   double prior_c0n;    // Pnet*c0
   double tdist_const;  // lgamma((nu+1)/2) - lgamma(nu/2) - 0.5*log(nu*pi)
   double sprior_const; // constant of logpdf(prior_sigma)
+  double sprior_rb;    // 1 / sprior_b (the gradient path multiplies instead of dividing in double)
   int d_in;            // features per observation (per time step)
   int seq;             // 1: x is T x d x n
   int T;

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(NT) k_eval(const __grid_constant__ EvalDev E) 
   }
   load_mask<NT>(M, s);
   for (int k = threadIdx.x; k < M.S; k += NT) s.th[k] = 0.f;
+  if constexpr (TC)  // (the tensor-core evaluation writes only the valid gradient slots: padding stays zero from here)
+    for (int k = threadIdx.x; k < M.S; k += NT) s.g[k] = 0.f;
   __syncthreads();
   const float* th_in = E.theta + (long long)c * M.P;
   for_each_flat<NT>(M, [&](int J, int k) { s.th[k] = th_in[J]; });
@@ -126,6 +128,8 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 24 : 512 / NT)) k_mcmc(const _
   }
   s.scr = R.scratch ? R.scratch + (long long)blockIdx.x * R.scratch_stride : nullptr;
   load_mask<NT>(M, s);
+  if constexpr (TC)  // (the tensor-core evaluation writes only the valid gradient slots: padding stays zero from here)
+    for (int k = threadIdx.x; k < M.S; k += NT) s.g[k] = 0.f;
   const int nchunks = (R.nsteps + R.chunk_len - 1) / R.chunk_len;
   const int ccount = R.c_count > 0 ? R.c_count : R.C;
   const int total = ccount * nchunks;

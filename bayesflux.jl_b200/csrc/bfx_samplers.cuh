@@ -34,16 +34,19 @@ struct Ctx {
   }
   BFX_DEV float uniform() const { return R.inj_uniforms ? R.inj_uniforms[c] : uniform_draw(key, gstep); }
 
+  template <bool VAL = true>
   BFX_DEV double eval(const BatchSrc& b, long long Bn, float nbs, bool want_grad, float& gn2) {
-    if constexpr (TC) return tc::chain_eval_tc<NT, tc::NoShadow, SP>(R.M, s, *tcr, R.x, R.xs, R.y, b, Bn, nbs, want_grad, gn2);
+    if constexpr (TC)
+      return tc::chain_eval_tc<NT, tc::NoShadow, SP, VAL>(R.M, s, *tcr, R.x, R.xs, R.y, b, Bn, nbs, want_grad, gn2);
     else return chain_eval<NT, BT>(R.M, s, R.x, R.y, b, Bn, nbs, want_grad, gn2);
   }
-  BFX_DEV double grad(float& gn2) { return eval(bs, Bk, R.num_batches, true, gn2); }
+  // gradient into s.g and its squared norm (no sampler uses the value of a gradient call)
+  BFX_DEV void grad(float& gn2) { eval<false>(bs, Bk, R.num_batches, true, gn2); }
   // tensor-core builds: the gradient with a shadow job (tc::chain_eval_tc)
   template <class Shadow>
-  BFX_DEV double grad_shadow(float& gn2, Shadow job) {
+  BFX_DEV void grad_shadow(float& gn2, Shadow job) {
     static_assert(TC, "shadow jobs exist on the tensor-core path only");
-    return tc::chain_eval_tc<NT, Shadow, SP>(R.M, s, *tcr, R.x, R.xs, R.y, bs, Bk, R.num_batches, true, gn2, job);
+    tc::chain_eval_tc<NT, Shadow, SP, false>(R.M, s, *tcr, R.x, R.xs, R.y, bs, Bk, R.num_batches, true, gn2, job);
   }
   // loglikeprior(bnn, θ, bnn.x, bnn.y): full data, num_batches = 1 (ggmc.jl:147,176; hmc.jl:135-136)
   BFX_DEV double full_lp() {
@@ -284,7 +287,7 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC, SP>& X) {
     const float4 t = ld4(th + k), gg = ld4(g + k);
     float4 o;
     BFX_MAP4(o, comp(t, c) + ha * comp(gg, c) + sa * comp(z, c));
-    o = mask4(o, m);
+    if (m != 15u) o = mask4(o, m);
     st4(th + k, o);
     rec_store(rec, k, m, o, J0);
   });

@@ -319,7 +319,7 @@ BFX_DEV void mma3(uint32_t d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t
 struct NoShadow {
   BFX_DEV void operator()() const {}
 };
-template <int NT, class Shadow = NoShadow, class SP = TcDyn>
+template <int NT, class Shadow = NoShadow, class SP = TcDyn, bool VAL = true>
 BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, const float* __restrict__ x,
                              const uint4* __restrict__ xs, const float* __restrict__ y, const BatchSrc& bs, long long B,
                              float nb, bool want_grad, float& gn2, Shadow shadow = Shadow{}) {
@@ -353,9 +353,25 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   // and nothing on a cancelling full batch, whose 1.4e-4 comes from ReLU units on the other side of their kink:
   // 1.4e-6 on the observations that keep a margin.  32 keeps the flush below 2 % of a full-batch evaluation.)
   constexpr int kAccTiles = 32;
-  auto dump = [&](auto ADD) {
+  // LAST = std::true_type: the dump that completes the gradient also folds in the prior term and accumulates the
+  // two squared norms (theta_net, finished gradient) per thread, so that eval_finish needs no pass of its own over
+  // the parameters (the element of theta that pairs with a gradient slot sits S floats below it)
+  float fa0 = 0.f, fa1 = 0.f;
+  const float c2 = M.prior_c2;
+  const long long th_off = s.th - s.g;
+  auto dump = [&](auto ADD, auto LAST) {
     constexpr bool add = decltype(ADD)::value;
-    auto put = [&](float* p, float v) { *p = add ? *p + v : v; };
+    constexpr bool last = decltype(LAST)::value;
+    auto put = [&](float* p, float v) {
+      if (add) v += *p;
+      if (last) {
+        const float t = p[th_off];
+        v = fmaf(-c2, t, v);
+        if (VAL) fa0 = fmaf(t, t, fa0);
+        fa1 = fmaf(v, v, fa1);
+      }
+      *p = v;
+    };
     fence_after();
 #pragma unroll(SP::fixed ? 2 : 1)
     for (int l = 0; l < nh; ++l) {
@@ -774,8 +790,8 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
     fence_before();
     __syncthreads();  // tile buffers, yh and the Z accumulator are free again
     if (want_grad && ++acc_tiles == kAccTiles && t0 + 64 < B) {
-      if (dumped) dump(std::true_type{});
-      else dump(std::false_type{});
+      if (dumped) dump(std::true_type{}, std::false_type{});
+      else dump(std::false_type{}, std::false_type{});
       dumped = true;
       acc_tiles = 0;
       fence_before();
@@ -784,16 +800,23 @@ BFX_DEV double chain_eval_tc(const ModelDev& M, const ChainSmem& s, Region& R, c
   }
 
   if (want_grad) {
-    if (dumped) dump(std::true_type{});
-    else dump(std::false_type{});
+    if (dumped) dump(std::true_type{}, std::true_type{});
+    else dump(std::false_type{}, std::true_type{});
     const int hl = SP::tl(M, nh - 1).hout;
-    for (int k = tid; k < hl; k += NT) s.g[LO.w_s + k * LO.ldw] = R.glast[k];
-    if (tid == 0) s.g[LO.b_s] = R.glast[64];
+    for (int k = tid; k <= hl; k += NT) {  // output layer: weights, then its bias
+      const int kk = k < hl ? LO.w_s + k * LO.ldw : LO.b_s;
+      const float t = s.th[kk];
+      const float v = fmaf(-c2, t, R.glast[k < hl ? k : 64]);
+      fa0 = fmaf(t, t, fa0);
+      fa1 = fmaf(v, v, fa1);
+      s.g[kk] = v;
+    }
     fence_before();
   }
   __syncthreads();
   BFX_TICK(9);  // gradient dump
-  const double v__ = eval_finish<NT, SP>(M, s, B, nb, ds0, ds1, want_grad, gn2);
+  const double v__ = want_grad ? eval_finish<NT, SP, false, VAL>(M, s, B, nb, ds0, ds1, true, gn2, fa0, fa1)
+                               : eval_finish<NT, SP, true, VAL>(M, s, B, nb, ds0, ds1, false, gn2);
   BFX_TICK(10);  // prior + norms + value
   return v__;
 }
