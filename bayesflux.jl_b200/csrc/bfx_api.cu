@@ -1468,8 +1468,10 @@ static int32_t stream_update_once(bfx_sampler* s, const bfx_run_desc* run, int c
   // update with the shared noise key 0: identical Philox streams keep theta / p / xi bit-identical on every rank
   const unsigned noisekey = sharded ? 0u : permkey;
   StreamBatch b = stream_batch(m, run, permkey, s->gstep, device_step);
-  // per-layer buckets on the side stream while the backward pass continues (BFX_NO_BUCKETS=1: one all-reduce)
-  StreamBucketHook* hook = sharded && s->comm_stream && !std::getenv("BFX_NO_BUCKETS") ? &s->hook : nullptr;
+  // Default: ONE all-reduce of the P + 3 floats behind the backward pass.  BFX_BUCKETS=1 issues per-layer buckets on
+  // the side stream while the backward pass continues instead: measured slower since the GEMM grids fill all 148 SMs
+  // in one wave (the NCCL kernels take SMs from them: 0.245 against 0.216 ms per update on 2 B200, profiles/).
+  StreamBucketHook* hook = sharded && s->comm_stream && std::getenv("BFX_BUCKETS") ? &s->hook : nullptr;
   int32_t rc = stream_grad_local(s, c, b, nbat, sharded, st, nullptr, hook);
   if (rc) return rc;
   if (sharded) {
@@ -1537,7 +1539,7 @@ static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nstep
       long long chain_offset;
       const void *samples_dev, *d_kin, *comm, *x, *w;
     } key{B, nbat, m->n, ke, samples_dev ? slots : 0, d_kin ? base : 0, d_kin ? nnew : 0, run->shuffle, run->batch_mode,
-          run->shard_mode, m->SM.tc, std::getenv("BFX_NO_BUCKETS") ? 1 : 0, 0, run->seed, run->chain_offset, samples_dev, d_kin,
+          run->shard_mode, m->SM.tc, std::getenv("BFX_BUCKETS") ? 0 : 1, 0, run->seed, run->chain_offset, samples_dev, d_kin,
           s->comm, m->x, m->W.w_hi};
     std::vector<unsigned char> kb(sizeof key);
     std::memcpy(kb.data(), &key, sizeof key);

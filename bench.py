@@ -248,10 +248,10 @@ def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
     ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / steps
     log(f"cfg3: {ms * 1e3:.1f} us per update")
     replays = bf.graph_replays(s)
-    # the same update with ONE all-reduce of the whole buffer after the backward pass (no per-layer buckets)
+    # the same update with per-layer all-reduce buckets on a side stream inside the backward pass (BFX_BUCKETS=1)
     ms_single = None
     if world > 1:
-        os.environ["BFX_NO_BUCKETS"] = "1"
+        os.environ["BFX_BUCKETS"] = "1"
         bf.advance(s, Bl, 3, **kw)
         torch.cuda.synchronize()
         dist.barrier()
@@ -260,8 +260,8 @@ def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
         e1.record(st)
         torch.cuda.synchronize()
         ms_single = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / steps
-        del os.environ["BFX_NO_BUCKETS"]
-        log(f"cfg3: {ms_single * 1e3:.1f} us per update with a single all-reduce")
+        del os.environ["BFX_BUCKETS"]
+        log(f"cfg3: {ms_single * 1e3:.1f} us per update with per-layer buckets")
     # phase split through the three-call form of the same update (direct launches, one event between the phases)
     run = A._run_desc(Bl, 0, True, True, True, 1, SEED, "per_chain", rank, world, shard)
     buf = torch.empty(P + 3, dtype=torch.float32, device="cuda")
@@ -310,10 +310,11 @@ def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
                                         "sum": (tg + tc + tu) / ksplit},
            "allreduce_bytes": ar_bytes,
            "allreduce_busbw_gbs": (2.0 * (world - 1) / world * ar_bytes / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
-           "collective": "per-layer ncclAllReduce buckets (P+3 floats in total) issued by libbfx on a side stream while the "
-                         "backward GEMMs continue, fork/join inside the update graph" if world > 1 else "none (single rank)",
-           "ms_per_update_single_allreduce": ms_single,
-           "allreduce_hidden_ms": (ms_single - ms) if ms_single is not None else None,
+           "collective": "one ncclAllReduce of P+3 floats issued by libbfx on the engine's stream inside the update graph "
+                         "(per-layer buckets on a side stream are the BFX_BUCKETS=1 variant, timed beside it)"
+                         if world > 1 else "none (single rank)",
+           "ms_per_update_bucketed": ms_single,
+           "bucketed_minus_single_ms": (ms_single - ms) if ms_single is not None else None,
            "replicas_bit_identical": identical, "finite": ok}
     bnn.close() if hasattr(bnn, "close") else None
     return out

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/s9_tests.log 2>&1; tail -3 gpurun_out/s9_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; echo "exit $?"; tail -5 gpurun_out/r02_bench_n2.err; cut -c1-300 gpurun_out/r02_bench_n2.json
