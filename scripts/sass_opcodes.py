@@ -34,7 +34,8 @@ with open(out, "w") as f:
         n = sum(h.values())
         tot.update(h)
         name = demangle(k)
-        name = re.sub(r"\(.*$", "", name)[:110]
+        name = re.sub(r"\((int|bool|unsigned)\)", "", name)
+        name = re.sub(r"\(.*$", "", name)[:130]
         f.write(f"{name} | {n} | " + " ".join(f"{key}={h.get(key, 0)}" for key in KEY if h.get(key, 0)) + " | " +
                 " ".join(f"{o}:{c}" for o, c in h.most_common(10)) + "\n")
     f.write("# whole library: " + " ".join(f"{key}={tot.get(key, 0)}" for key in KEY) + f" kernels={len(hist)}\n")

@@ -41,7 +41,12 @@ def main():
     bnn = bf.BNN(x, y, bf.FeedforwardNormal(nc, bf.Gamma(2.0, 0.5)), bf.GaussianPrior(nc, 1.0), compute="tc")
     P = bnn.num_total_params
     th0 = np.asfortranarray((0.1 * rng.standard_normal((P, args.chains))).astype(np.float32))
-    s = {"sgld": bf.SGLD, "sgnht": bf.SGNHT, "sgnhts": bf.SGNHTS}[args.sampler]()
+    if args.sampler == "hmc":  # configs[4] shape class: full-batch trajectories; the table is then per 64-row tile
+        s = bf.HMC(1e-4, 5, sadapter=bf.DualAveragingStepSize(1e-4, target_accept=0.5),
+                   madapter=bf.DiagCovMassAdapter(1000, 100, kappa=0.1))
+        args.batch = x.shape[1]
+    else:
+        s = {"sgld": bf.SGLD, "sgnht": bf.SGNHT, "sgnhts": bf.SGNHTS}[args.sampler]()
     s.initialise(bnn, th0)
     ring = torch.empty((args.chains, 4, P), dtype=torch.float32, device="cuda")
     st = torch.cuda.Stream()
@@ -60,6 +65,9 @@ def main():
     ms = run()
     fn(buf, 1)
     evals = args.chains * args.updates
+    if args.sampler == "hmc":  # gradient tiles + the two full-data value passes of each 5-stage trajectory
+        tiles = (args.batch + 63) // 64
+        evals = args.chains * (args.updates * tiles + 2 * (args.updates // 5) * tiles)
     tot = sum(buf[i] for i in range(24))
     print(f"{ms:.2f} ms for {evals} grad-evals = {evals / ms / 1e3:.2f} M/s (instrumented build)")
     print(f"cycles per grad-eval (thread 0 of the CTA): {tot / evals:.0f}")
