@@ -103,6 +103,7 @@ struct bfx_model {
   int64_t n = 0;
   void* xsplit = nullptr;  // tensor-core path: x as bf16 hi/lo rows (4 * kpad bytes per observation), built lazily
   int xsplit_kpad = 0;
+  int data_epoch = 0;      // bumped whenever the data or the compute mode change (RunDev::data_epoch)
   cudaStream_t stream = nullptr;
   // flat (ABI) <-> padded (engine) parameter layout
   std::vector<int> flat_pad, pad_flat;
@@ -430,6 +431,7 @@ extern "C" {
 int32_t bfx_model_set_compute(bfx_model* m, int32_t mode) {
   if (!m) return fail(BFX_ERR_BAD_ARG, "model is NULL");
   if (mode != BFX_COMPUTE_FP32 && mode != BFX_COMPUTE_TC_BF16X3) return fail(BFX_ERR_BAD_ARG, "unknown compute mode");
+  m->data_epoch += 1;  // values of the two engines differ in the last digits: cached log posteriors are dropped
   if (m->stream_regime) {
     // large-P regime: per layer, the three GEMMs go to the tcgen05 kernel when the layer is a real GEMM whose
     // operands can be fetched in aligned 16-byte chunks (bfx_stream_tc.cu)
@@ -611,6 +613,7 @@ static int32_t set_data_impl(bfx_model* m, const float* x, const int64_t* dims, 
   CK(cudaMemcpyAsync(m->y, y, (size_t)n * sizeof(float), kind, m->stream));
   CK(cudaStreamSynchronize(m->stream));
   m->n = n;
+  m->data_epoch += 1;
   m->M.seq = ndims == 3;
   m->M.T = ndims == 3 ? (int)dims[0] : 1;
   m->scratch_ctas = 0;  // the scratch stride depends on T: force a re-allocation
@@ -1251,7 +1254,13 @@ int32_t bfx_sampler_set_state(bfx_sampler* s, int32_t field, const void* in, int
     float* dst = field == BFX_STATE_THETA ? s->theta : field == BFX_STATE_MOMENTUM ? s->mom : s->minv;
     if (!dst) return fail(BFX_ERR_STATE, "this sampler does not carry that state");
     if (nbytes != (int64_t)P * C * 4) return fail(BFX_ERR_BAD_ARG, "buffer must hold P x C floats");
-    return state_h2d(s, dst, static_cast<const float*>(in), field == BFX_STATE_MINV ? 1.f : 0.f);
+    st = state_h2d(s, dst, static_cast<const float*>(in), field == BFX_STATE_MINV ? 1.f : 0.f);
+    if (st || field != BFX_STATE_THETA || m->stream_regime) return st;
+    std::vector<ChainScalars> sc0;  // theta changed from outside: cached full-data log posteriors are stale
+    st = fetch_scalars(s, sc0);
+    if (st) return st;
+    for (auto& c : sc0) c.lp_epoch = 0;
+    return store_scalars(s, sc0);
   }
   std::vector<ChainScalars> sc;
   st = fetch_scalars(s, sc);
@@ -1290,6 +1299,7 @@ static int32_t fill_run_common(bfx_sampler* s, RunDev& R) {
   if (int32_t xst = ensure_xsplit(m)) return xst;
   R.xs = m->M.tc.enabled ? static_cast<const uint4*>(m->xsplit) : nullptr;
   R.n = m->n;
+  R.data_epoch = m->data_epoch;
   R.C = s->C;
   R.chain0 = 0;
   R.Ps = s->Ps;

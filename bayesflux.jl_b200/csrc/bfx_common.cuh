@@ -237,11 +237,16 @@ struct ChainScalars {
   // mass adapters: own counter t (diagcovariancemassadapter.jl:13-20, rmspropmassadapter.jl:9-16)
   int ma_t;
   int status;           // 0 | BFX_ERR_NAN_G | BFX_ERR_NAN_THETA
-  double start_lp;      // HMC: -loglikeprior(theta_old) cache is NOT used (reference recomputes)
+  double start_lp;      // GGMC / HMC: loglikeprior of the full data at the start of the window / trajectory
   long long accepted_total;
   // find_mode: FluxModeFinder.i, convergence flag, ADAM's running beta powers
   int mode_i, converged;
   float bp1, bp2;
+  // GGMC / HMC: start_lp is the full-data log posterior of the CURRENT theta iff lp_epoch == RunDev::data_epoch + 1.
+  // The MH test leaves it behind (the end-of-window value on accept, the old start value on reject, which is exactly
+  // what the reference recomputes at ggmc.jl:147 / hmc.jl:135 for the next window), so every window after the first
+  // costs one full-data pass instead of two.  Reset by anything that changes theta or the data from outside.
+  int lp_epoch, pad_;
 };
 
 // everything a launch needs (passed by value as a __grid_constant__ kernel parameter)
@@ -307,6 +312,7 @@ struct RunDev {
   // a launch may cover only the chains [c_begin, c_begin + c_count) (c_count = 0: all C): bfx_mcmc_run pipelines
   // chain groups so that the host copies of one group overlap the kernel of the next
   int c_begin, c_count;
+  int data_epoch;  // bumped by bfx_model_set_data* / set_compute: invalidates cached full-data log posteriors
   // filled by the launcher from nb, keep_every, ring_slots, S.ma_windowlength
   FastDiv fd_nb, fd_keep, fd_slots, fd_window;
 };

@@ -442,7 +442,8 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC, SP>& X) {
   if (X.sc.current_step == 1) {
     // :146-148  lMH = -lπ_full(θ): the log posterior of the full data set is O(n) large, so the window's start value
     // stays in double (start_lp) and only the kinetic-energy terms accumulate in the float lMH
-    X.sc.start_lp = X.full_lp();
+    if (X.sc.lp_epoch != R.data_epoch + 1) X.sc.start_lp = X.full_lp();  // (else: left behind by the last MH test)
+    X.sc.lp_epoch = 0;
     X.sc.lMH = 0.f;
     // θ at the start of the window = samples[:, nsampled - steps] on a later reject
     for_each_quad<NT>(R.M, [&](int k) { st4(X.thold + k, ld4(th + k)); });
@@ -506,7 +507,8 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC, SP>& X) {
   record_sample(X, ns);  // samples[:, t] with t == nsampled for GGMC
   if (X.sc.current_step == S.steps && X.sc.t > S.steps) {
     __syncthreads();
-    X.sc.lMH = (float)((X.full_lp() - X.sc.start_lp) + (double)X.sc.lMH);  // :176, the difference formed in double
+    const double end_lp = X.full_lp();
+    X.sc.lMH = (float)((end_lp - X.sc.start_lp) + (double)X.sc.lMH);  // :176, the difference formed in double
     const float pacc = mh_prob_of(X.sc.lMH);
     X.sc.l = stepsize_adapt(X.sc, S, pacc);
     mass_adapt(X, gn2);
@@ -518,6 +520,9 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC, SP>& X) {
         if (hi_ >= 0) R.accepted_out[hi_] = accept ? 1 : 0;
       }
     }
+    // the next window starts from theta (accept) or from theta_old (reject): its full-data log posterior is known
+    if (accept) X.sc.start_lp = end_lp;
+    X.sc.lp_epoch = R.data_epoch + 1;
     if (accept) {
       X.sc.accepted_total += S.steps;
     } else {
@@ -546,7 +551,8 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC, SP>& X) {
   if (stage == 1) {
     // new trajectory: p ~ N(0, Minv); θold, pold kept for the MH test (:117-121).
     // -loglikeprior(θold) and logpdf(moment_dist, pold) are evaluated here, while θ == θold.
-    X.sc.start_lp = X.full_lp();
+    if (X.sc.lp_epoch != R.data_epoch + 1) X.sc.start_lp = X.full_lp();  // (else: left behind by the last MH test)
+    X.sc.lp_epoch = 0;
     float acc[1] = {0.f};
     const float* inj = X.inj(0);
     for_each_quad<NT>(R.M, [&](int k) {
@@ -592,7 +598,8 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC, SP>& X) {
   if (last) {
     block_sum<NT, 1>(acc, X.s.red);
     const double start_mh = -X.sc.start_lp + (double)X.sc.lMH;
-    const double end_mh = -X.full_lp() + 0.5 * (double)acc[0];
+    const double end_lp = X.full_lp();
+    const double end_mh = -end_lp + 0.5 * (double)acc[0];
     const float lMH = (float)(start_mh - end_mh);
     const float lr = logf(X.uniform());
     X.sc.l = stepsize_adapt(X.sc, S, mh_prob_of(lMH));
@@ -603,6 +610,8 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC, SP>& X) {
       const long long hi_ = hist_index(R, X.c, ns);
       if (hi_ >= 0) R.accepted_out[hi_] = accept ? 1 : 0;
     }
+    if (accept) X.sc.start_lp = end_lp;  // the next trajectory starts from theta (accept) or theta_old (reject)
+    X.sc.lp_epoch = R.data_epoch + 1;
     if (accept) {
       X.sc.accepted_total += 1;
     } else {
