@@ -766,7 +766,7 @@ cudaError_t stream_work_alloc(const StreamModel& M, long long Bc, StreamWork& W)
       if (!M.L[l].tc) continue;
       W.tc_ksplit[l] = tc_ksplit_for(M.L[l], Bc);
       e = cudaMalloc(&W.tc_part[l], (size_t)W.tc_ksplit[l] * tc_part_stride(M.L[l]) * sizeof(float));
-      W.tc_rowslots[l] = 2 * (int)((Bc + 223) / 224);  // (tiles are 224 or 256 columns wide: tcg::tile_cols_kmajor_b)
+      W.tc_rowslots[l] = tcg::ROWSLOTS * (int)((Bc + 223) / 224);  // (tiles are 224 or 256 columns wide: tcg::tile_cols_kmajor_b)
       if (e == cudaSuccess) e = cudaMalloc(&W.tc_rowpart[l], (size_t)W.tc_rowslots[l] * M.L[l].nout * sizeof(float));
     }
     if (htc && e == cudaSuccess) {
@@ -984,7 +984,7 @@ cudaError_t stream_eval_like(const StreamModel& M, StreamWork& W, const float* t
           D = W.delta[ping]; Dhi = W.delta_hi[ping]; Dlo = W.delta_lo[ping];
           {
             const int bn = tcg::tile_cols_kmajor_b(u.M, u.N);
-            bias_slots = prev_tc ? 2 * ((nc + bn - 1) / bn) : 0;
+            bias_slots = prev_tc ? tcg::ROWSLOTS * ((nc + bn - 1) / bn) : 0;
           }
           ping ^= 1;
         }

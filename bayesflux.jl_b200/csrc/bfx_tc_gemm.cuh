@@ -176,7 +176,7 @@ BFX_DEV void load_operand(unsigned char* dst, const CUtensorMap* map, uint64_t* 
 }
 
 template <int CG, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
            const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
            const __grid_constant__ CUtensorMap mChi, const __grid_constant__ CUtensorMap mClo,
@@ -226,7 +226,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
   if (warp != 0) {
     if (warp == 2) tmem_alloc<CG>(&tmem_slot, (uint32_t)BN);
     tc::fence_before();
-    asm volatile("bar.sync 3, 224;" ::: "memory");
+    asm volatile("bar.sync 3, %0;" ::"n"(NTHREADS - 32) : "memory");
     tc::fence_after();
   }
 #endif
@@ -288,8 +288,12 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
     tc::fence_after();
     BFX_GT(3);
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
-    const int q = warp & 3, half = warp >> 2;
-    const int nblk = half == 0 ? 4 : (bn - 128) / 32;   // 32-column blocks of this warp half (bn = 224: 4 + 3)
+    // sixteen warps: lane quadrant q, column group grp = 64 columns (two 32-column blocks), two groups per 128-column
+    // half (the unit of the TMA stores).  The epilogue is instruction-bound (about 11 k warp instructions per CTA):
+    // eight warps ran it at IPC 1.2, sixteen hide each other's latencies.
+    const int q = warp & 3, grp = warp >> 2, half = grp >> 1, sub = grp & 1;
+    const int nblk = half == 0 ? 4 : (bn - 128) / 32;   // 32-column blocks of this 128-column half (bn = 224: 4 + 3)
+    const int cb0 = 2 * sub, cb1 = (cb0 + 2 < nblk) ? cb0 + 2 : nblk;  // this warp's blocks [cb0, cb1)
     const int mloc = 32 * q + lane;
     const long long m = (long long)m0 + mloc;
     float* Cp = g.C ? g.C + (long long)blockIdx.z * g.part_stride : nullptr;
@@ -366,39 +370,33 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUt
         }
       }
     };
+    const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * half);
     if (EPI == EPI_PLAIN) {  // FP32 stores only: the plain loop keeps 32 stores in flight per load
-      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * half);
 #pragma unroll 1
-      for (int cb = 0; cb < nblk; ++cb) {
+      for (int cb = cb0; cb < cb1; ++cb) {
         uint32_t ra[32];
         ld_row32_issue(tbase + 32 * cb, ra);
         ld_row32_wait(ra);
         process(cb, ra);
       }
-    } else {
-      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * half);
+    } else if (cb0 < cb1) {
       uint32_t ra[32], rb[32];
-      ld_row32_issue(tbase, ra);
+      const bool two = cb0 + 1 < cb1;
+      ld_row32_issue(tbase + 32 * cb0, ra);
       ld_row32_wait(ra);
-      ld_row32_issue(tbase + 32, rb);   // block 1 streams out of TMEM while block 0 is processed
-      process(0, ra);
-      ld_row32_wait(rb);
-      ld_row32_issue(tbase + 64, ra);
-      process(1, rb);
-      ld_row32_wait(ra);
-      if (nblk > 3) ld_row32_issue(tbase + 96, rb);
-      process(2, ra);
-      if (nblk > 3) {
+      if (two) ld_row32_issue(tbase + 32 * (cb0 + 1), rb);   // the second block streams out of TMEM while the first is processed
+      process(cb0, ra);
+      if (two) {
         ld_row32_wait(rb);
-        process(3, rb);
+        process(cb0 + 1, rb);
       }
     }
-    if (EPI == EPI_MUL_DACT && g.rowpart && m < g.M) g.rowpart[(long long)(2 * blockIdx.y + half) * g.M + m] = rsum;
+    if (EPI == EPI_MUL_DACT && g.rowpart && m < g.M) g.rowpart[(long long)(ROWSLOTS * blockIdx.y + grp) * g.M + m] = rsum;
     BFX_GT(4);
     if (split) {
       tc::fence_async_smem();  // generic-proxy stores -> visible to the TMA engine
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-      if (q == 0 && lane == 0 && m0 < g.M && n0 + 128 * half < g.N) {  // rows / columns beyond M / N are clipped by the TMA
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+      if (q == 0 && sub == 0 && lane == 0 && m0 < g.M && n0 + 128 * half < g.N) {  // rows / columns beyond M / N are clipped by the TMA
         // (the second half's box is bn - 128 columns wide: it must not reach into the next tile)
         tma_store_2d(half ? &mChi2 : &mChi, stage_hi, m0, n0 + 128 * half);
         tma_store_2d(half ? &mClo2 : &mClo, stage_lo, m0, n0 + 128 * half);
@@ -501,7 +499,7 @@ inline cudaError_t launch(const Args& g0, const Operand& A, const Operand& B, co
   cudaLaunchConfig_t cfg{};
   const int mt = (g.M + BM * CG - 1) / (BM * CG);
   cfg.gridDim = dim3((unsigned)(mt * CG), (unsigned)((g.N + bn - 1) / bn), (unsigned)ksplit);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[1];

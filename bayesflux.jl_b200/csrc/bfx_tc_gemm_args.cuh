@@ -12,6 +12,8 @@ constexpr int BM = 128;   // accumulator rows per CTA
 constexpr int BN = 256;   // accumulator columns (TMEM allocation; a launch may use 224 of them, Args::bn)
 constexpr int BK = 64;    // K per stage = one 128-byte swizzle span of BF16
 constexpr int TILE_A = BM * BK * 2;  // one half (hi or lo) of the A stage, 16 KB
+constexpr int NTHREADS = 512;        // producer warp, MMA warp, allocator warp; all sixteen warps run the epilogue
+constexpr int ROWSLOTS = 4;          // bias-gradient row-sum partials per tile (one per 64-column group)
 
 enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1, EPI_PLAIN = 2 };
 

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc.py tests/test_gpu_recurrent.py tests/test_gpu_statistical.py tests/test_gpu_edges.py -x -q -m gpu > gpurun_out/s12_tests.log 2>&1; tail -3 gpurun_out/s12_tests.log
-python tools/bench_cfg.py --cfg 5 2>&1 | tail -1
-python tools/bench_cfg.py --cfg 4 2>&1 | tail -1
+for i in 1 2 3; do timeout 120 tools/gemm_probe.exe 2 1 > gpurun_out/s13_probe.$i.log 2>&1; echo "probe rc $? mism $(grep -c MISMATCH gpurun_out/s13_probe.$i.log)"; done
+grep -A2 "^cfg3" gpurun_out/s13_probe.1.log | grep -v "^--"
+timeout 600 python -m pytest tests/test_gpu_stream.py -x -q -m gpu > gpurun_out/s13_stream.log 2>&1; tail -2 gpurun_out/s13_stream.log
+timeout 120 python tools/cfg3_probe.py --steps 100 2>&1 | tail -1

@@ -70,7 +70,7 @@ static int run_case(const Case& c, bool timeit) {
   CK(cudaMemset(dC, 0xFF, (size_t)M * N * 4 * ksplit));
   __nv_bfloat16 *dChi = nullptr, *dClo = nullptr;
   CK(cudaMalloc(&dChi, (size_t)M * N * 2)); CK(cudaMalloc(&dClo, (size_t)M * N * 2));
-  const int nslots = 2 * ((N + 223) / 224);  // tiles are 224 or 256 columns wide (tcg::tile_cols_kmajor_b); unused slots stay 0
+  const int nslots = tcg::ROWSLOTS * ((N + 223) / 224);  // tiles are 224 or 256 columns wide (tcg::tile_cols_kmajor_b); unused slots stay 0
   float* drow = nullptr;
   CK(cudaMalloc(&drow, (size_t)nslots * M * 4));
   CK(cudaMemset(drow, 0, (size_t)nslots * M * 4));
