@@ -29,6 +29,17 @@ BFX_DEV double chain_eval(const ModelDev& M, const ChainSmem& s, const float* __
   lc.nb = nb;
   double ds0 = 0.0, ds1 = 0.0;
   __syncthreads();
+  if (!want_grad && !yhat && lstm_value_ok<NT>(M)) {  // forward-only LSTM pass: 64 sequences per tile (bfx_device.cuh)
+    for (long long t0 = 0; t0 < B; t0 += 64) {
+      const int nvalid = (int)((B - t0) < 64 ? (B - t0) : 64);
+      float sums[2] = {0.f, 0.f};
+      lstm_value_tile64<NT>(M, s, x, y, bs, t0, nvalid, lc, sums);
+      ds0 += (double)sums[0];
+      ds1 += (double)sums[1];
+      __syncthreads();
+    }
+    return eval_finish<NT>(M, s, B, nb, ds0, ds1, false, gn2);
+  }
   for (long long t0 = 0; t0 < B; t0 += BT) {
     int nvalid = (int)((B - t0) < (long long)BT ? (B - t0) : (long long)BT);
     float sums[2] = {0.f, 0.f};

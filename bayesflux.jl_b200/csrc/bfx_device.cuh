@@ -684,6 +684,125 @@ BFX_DEV void rec_stage_x(const ModelDev& M, const ChainSmem& s, const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Forward-only pass of an LSTM(d, H <= 64) + Dense(H, 1) chain over a tile of 64 sequences: the full-data log
+// posteriors of the GGMC / HMC acceptance tests (ggmc.jl:147,176; hmc.jl:135-136) and bfx_loglikeprior, which need no
+// gradient and no per-step records.  A thread owns two units x eight sequences and computes ALL FOUR gate rows of its
+// units (64 accumulators: every weight pair and every h value loaded from shared memory feeds 8 / 8 FMAs instead of
+// the 4 / 4 of the 16-sequence gradient tile), so the gate nonlinearities and the cell update are thread-local: c stays
+// in registers over the whole sequence, h ping-pongs between two buffers, no gate buffer and one barrier per time step.
+// Same accumulation order as rec_tile (bias, input features, recurrent features), so the values agree with it.
+// Workspace: the gradient buffer s.g (unused by a value-only evaluation).
+// ---------------------------------------------------------------------------------
+template <int NT>
+BFX_DEV bool lstm_value_ok(const ModelDev& M) {
+  if (M.rec_layer != 0 || M.nlayers != 2) return false;
+  const LayerDev& L = M.L[0];
+  const LayerDev& LO = M.L[1];
+  if (L.kind != L_LSTM || (L.H & 1) || L.H > 64 || (L.H / 2) * 8 > NT || LO.kind != L_DENSE || LO.nout != 1) return false;
+  return 2 * 64 * 68 + L.nin_pad * 68 + 128 <= M.S;
+}
+
+template <int NT>
+BFX_DEV void lstm_value_tile64(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
+                               const float* __restrict__ y, const BatchSrc& bs, long long tile0, int nvalid,
+                               const LikeCoef& lc, float (&sums)[2]) {
+  constexpr int LDH = 68;
+  const LayerDev& L = M.L[0];
+  const LayerDev& LO = M.L[1];
+  const int H = L.H, T = M.T, d = M.d_in, dpad = L.nin_pad;
+  float* ws = s.g;
+  float* Hb0 = ws;
+  float* Hb1 = ws + 64 * LDH;
+  float* X = ws + 2 * 64 * LDH;  // [dpad][LDH] features of the current time step
+  float* ys = X + dpad * LDH;    // [64]
+  int* idx = reinterpret_cast<int*>(ys + 64);
+  const int tid = threadIdx.x;
+  for (int b = tid; b < 64; b += NT) {
+    const long long o = (b < nvalid) ? batch_obs(bs, tile0 + b) : -1;
+    idx[b] = (int)o;
+    ys[b] = (o >= 0) ? __ldg(y + o) : 0.f;
+  }
+  for (int e = tid; e < 64 * LDH; e += NT) Hb0[e] = 0.f;
+  __syncthreads();
+  const bool active = tid < (H / 2) * 8;
+  const int r = 2 * (tid >> 3), c0 = 8 * (tid & 7);  // first unit, first sequence of this thread
+  float c[2][8];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[u][j] = 0.f;
+  const float* Wi = s.th + L.w_s + r;
+  const float* Wh = s.th + L.wh_s + r;
+  for (int t = 0; t < T; ++t) {
+    for (int e = tid; e < dpad * 64; e += NT) {
+      const int f = e >> 6, b = e & 63;
+      const int o = idx[b];
+      X[f * LDH + b] = (o >= 0 && f < d) ? __ldg(x + ((long long)o * d + f) * T + t) : 0.f;
+    }
+    __syncthreads();
+    const float* hp = (t & 1) ? Hb1 : Hb0;
+    float* hn = (t & 1) ? Hb0 : Hb1;
+    if (active) {
+      float acc[4][2][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float2 bb = *reinterpret_cast<const float2*>(s.th + L.b_s + g * H + r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[g][0][j] = bb.x;
+          acc[g][1][j] = bb.y;
+        }
+      }
+      auto kstep = [&](const float* wcol, const float* arow) {
+        const float4 a0 = ld4(arow), a1 = ld4(arow + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float2 w = *reinterpret_cast<const float2*>(wcol + g * H);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[g][0][j] = fmaf(w.x, a[j], acc[g][0][j]);
+            acc[g][1][j] = fmaf(w.y, a[j], acc[g][1][j]);
+          }
+        }
+      };
+      for (int k = 0; k < d; ++k) kstep(Wi + k * L.ldw, X + k * LDH + c0);
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) kstep(Wh + k * L.ldh, hp + k * LDH + c0);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float ig = sigm(acc[0][u][j]), fg = sigm(acc[1][u][j]);
+          const float cg = tanhf(acc[2][u][j]), og = sigm(acc[3][u][j]);
+          c[u][j] = fg * c[u][j] + ig * cg;
+          hv[j] = og * tanhf(c[u][j]);
+        }
+        st4(hn + (r + u) * LDH + c0, make_float4(hv[0], hv[1], hv[2], hv[3]));
+        st4(hn + (r + u) * LDH + c0 + 4, make_float4(hv[4], hv[5], hv[6], hv[7]));
+      }
+    }
+    __syncthreads();
+  }
+  // Dense(H, 1) head on h_T and the likelihood sums (like_epilogue, value part)
+  const float* hT = (T & 1) ? Hb1 : Hb0;
+  for (int b = tid; b < nvalid; b += NT) {
+    float yh = s.th[LO.b_s];
+    for (int k = 0; k < H; ++k) yh = fmaf(s.th[LO.w_s + k * LO.ldw], hT[k * LDH + b], yh);
+    yh = act_apply(LO.act, yh);
+    const float z = (ys[b] - yh) * lc.inv_sigma;
+    if (M.like_kind == LK_NORMAL) {
+      sums[0] += z * z;
+    } else {
+      const float zz = z * z;
+      sums[0] += log1pf(zz / M.nu);
+      sums[1] += (M.nu + 1.f) * z / (M.nu + zz) * z;
+    }
+  }
+}
+
 template <int NT, int BT>
 BFX_DEV void rec_tile(const ModelDev& M, const ChainSmem& s, const float* __restrict__ x,
                       const float* __restrict__ y, const BatchSrc& bs, long long tile0, int nvalid,

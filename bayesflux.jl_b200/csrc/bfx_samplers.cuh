@@ -507,11 +507,13 @@ BFX_DEV void step_ggmc(Ctx<NT, BT, TC, SP>& X) {
   record_sample(X, ns);  // samples[:, t] with t == nsampled for GGMC
   if (X.sc.current_step == S.steps && X.sc.t > S.steps) {
     __syncthreads();
+    // (the mass adapter reads the minibatch gradient in s.g, which a value-only evaluation may use as workspace: it runs
+    // before the full-data pass; nothing it changes enters the acceptance test)
+    mass_adapt(X, gn2);
     const double end_lp = X.full_lp();
     X.sc.lMH = (float)((end_lp - X.sc.start_lp) + (double)X.sc.lMH);  // :176, the difference formed in double
     const float pacc = mh_prob_of(X.sc.lMH);
     X.sc.l = stepsize_adapt(X.sc, S, pacc);
-    mass_adapt(X, gn2);
     const float r = X.uniform();
     const bool accept = r < pacc;
     if (R.accepted_out && threadIdx.x == 0) {
@@ -598,12 +600,12 @@ BFX_DEV void step_hmc(Ctx<NT, BT, TC, SP>& X) {
   if (last) {
     block_sum<NT, 1>(acc, X.s.red);
     const double start_mh = -X.sc.start_lp + (double)X.sc.lMH;
+    mass_adapt(X, gn2);  // (before the full-data pass, which may use s.g as workspace: see step_ggmc)
     const double end_lp = X.full_lp();
     const double end_mh = -end_lp + 0.5 * (double)acc[0];
     const float lMH = (float)(start_mh - end_mh);
     const float lr = logf(X.uniform());
     X.sc.l = stepsize_adapt(X.sc, S, mh_prob_of(lMH));
-    mass_adapt(X, gn2);
     const bool accept = lr < lMH;
     const long long ns = X.sc.nsampled + 1;
     if (R.accepted_out && threadIdx.x == 0) {
