@@ -116,7 +116,9 @@ template <int NT, int BT, int KIND, bool TC, class SP = TcDyn>
 // (at least 512 resident threads per SM for every launch shape = a 128-register cap, and 24 one-warp CTAs = an
 // 80-register cap for the 32-thread shape: without it the small shapes took 200+ registers and ran 10 CTAs per SM;
 // cfg1 127 M -> 200 M grad-evals/s)
-__global__ void __launch_bounds__(NT, (NT == 32 ? 24 : 512 / NT)) k_mcmc(const __grid_constant__ RunDev R) {
+// (the recurrent shape <256,16> runs one CTA per SM at configs[3]'s size, 207 KB: no register cap there, the 64
+// accumulators of the forward-only LSTM tile spilled under the 128-register one)
+__global__ void __launch_bounds__(NT, (NT == 32 ? 24 : (BT == 16 ? 1 : 512 / NT))) k_mcmc(const __grid_constant__ RunDev R) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_item;
   const ModelDev& M = R.M;
