@@ -1,11 +1,5 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_recurrent.py -x -q -m gpu > gpurun_out/s16_tests.log 2>&1; tail -2 gpurun_out/s16_tests.log
-python tools/lstm_probe.py 2>&1 | tail -1
-python - <<'PY'
-import json, subprocess, sys
-sys.path.insert(0, '.')
-import bench, torch
-import bayesflux_b200 as bf
-r=bench.secondary_cfg4(bf, torch, None, 1, 0, 0); print(r['ms'], r['grad_evals_per_s'])
-r=bench.secondary_cfg4(bf, torch, None, 1, 0, 0, chains=256); print('256 chains', r['ms'], r['grad_evals_per_s'])
-PY
+for z in 0 1; do
+  if [ $z = 1 ]; then export BFX_NO_ZEROCOPY=1; else unset BFX_NO_ZEROCOPY; fi
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2953$z bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu --no-secondary 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('nozc=$z', d['value'], d['e2e']['value'])"
+done
