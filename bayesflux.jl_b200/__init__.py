@@ -12,7 +12,7 @@ from .api import (BNN, Chain, Dense, LSTM, RNN, NetConstructor, destruct, Gamma,
                   MixtureScalePrior, InitialiseAllSame, split_params, loglikeprior, grad_loglikeprior,
                   ConstantStepsize, DualAveragingStepSize, FixedMassAdapter, DiagCovMassAdapter,
                   RMSPropMassAdapter, FullCovMassAdapter, MCMCState, SGLD, SGNHT, SGNHTS, GGMC, HMC, mcmc,
-                  advance, launch_count, comm_unique_id, comm_init, comm_destroy, graph_replays, Descent, Momentum, RMSProp, ADAM, FluxModeFinder, find_mode, predict,
+                  advance, launch_count, comm_unique_id, comm_init, comm_destroy, graph_replays, peer_ranks, Descent, Momentum, RMSProp, ADAM, FluxModeFinder, find_mode, predict,
                   sample_posterior_predict, get_posterior_networks, chain_diagnostics,
                   identity, relu, tanh, sigmoid)
 from .sharded import (shard_chains, shard_data, global_num_batches, model_regime, ShardedChain,  # noqa: F401,E402

@@ -104,6 +104,7 @@ SYMBOLS = {
     "bfx_sampler_comm_init": [_vp, _vp, _i32, _i32],
     "bfx_sampler_comm_destroy": [_vp],
     "bfx_sampler_graph_replays": [_vp, _pi64],
+    "bfx_sampler_peer_ranks": [_vp, C.POINTER(C.c_int32)],
     "bfx_debug_batch_indices": [_vp, C.POINTER(RunDesc), _i64, _i64, _vp, _pi64],
     "bfx_debug_noise": [_vp, C.POINTER(RunDesc), _i64, _i64, _i32, _vp, _vp],
 }

@@ -820,6 +820,13 @@ def comm_destroy(sampler: MCMCState):
     L.check(L.lib.bfx_sampler_comm_destroy(sampler._h))
 
 
+def peer_ranks(sampler: MCMCState) -> int:
+    """Ranks whose exchange buffers a minibatch-sharded sampler reads over peer memory (0: NCCL all-reduce)."""
+    n = C.c_int32()
+    L.check(L.lib.bfx_sampler_peer_ranks(sampler._h, C.byref(n)))
+    return n.value
+
+
 def graph_replays(sampler: MCMCState) -> int:
     n = C.c_int64()
     L.check(L.lib.bfx_sampler_graph_replays(sampler._h, C.byref(n)))

@@ -59,6 +59,7 @@ struct NcclApi {
   int (*CommInitAll)(void**, int, const int*) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   std::string err;
 };
@@ -80,6 +81,7 @@ NcclApi* nccl_api() {
   api.CommInitAll = (int (*)(void**, int, const int*))dlsym(api.handle, "ncclCommInitAll");
   api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
   api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+  api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllGather");
   api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
   if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) {
     api.err = "NCCL symbols missing";
@@ -88,7 +90,7 @@ NcclApi* nccl_api() {
   }
   return &api;
 }
-constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+constexpr int kNcclFloat32 = 7, kNcclInt8 = 0, kNcclSum = 0;
 }  // namespace
 
 
@@ -156,6 +158,12 @@ struct bfx_sampler {
   int comm_rank = 0, comm_nranks = 1;
   cudaStream_t comm_stream = nullptr;  // side stream of the bucketed exchange (fork / join by events)
   StreamBucketHook hook{};
+  // peer-memory exchange (bfx_stream.cuh: PeerDev): the ranks' exchange buffers and flag blocks opened through CUDA
+  // IPC; n > 1 only when EVERY rank managed to open every peer (else the NCCL all-reduce is used)
+  PeerDev peer{};
+  float* gsum = nullptr;                 // [P + 4] the summed gradient (the peers keep reading gbuf meanwhile)
+  unsigned long long* peer_flags = nullptr;
+  void* peer_opened[2 * PEER_MAX] = {};  // IPC mappings to close
 };
 
 // ---------------------------------------------------------------------------------
@@ -951,6 +959,12 @@ static void free_sampler(bfx_sampler* s) {
   cudaFree(s->samp_cache[0]);
   cudaFree(s->samp_cache[1]);
   cudaFree(s->ssc);
+  for (void*& p : s->peer_opened) {
+    if (p) cudaIpcCloseMemHandle(p);
+    p = nullptr;
+  }
+  cudaFree(s->gsum);
+  cudaFree(s->peer_flags);
   cudaFree(s->gbuf);
   if (s->progress_host) cudaFreeHost(s->progress_host);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -1393,7 +1407,7 @@ static bool wsplit_valid(const bfx_sampler* s) {
 }
 
 static int32_t stream_grad_local(bfx_sampler* s, int c, const StreamBatch& b, float nb, bool pack, cudaStream_t st,
-                                 float* gb = nullptr, StreamBucketHook* hook = nullptr) {
+                                 float* gb = nullptr, StreamBucketHook* hook = nullptr, const PeerDev* pd = nullptr) {
   if (!gb) gb = s->gbuf;
   bfx_model* m = s->m;
   int32_t rc = ensure_work(m, b.B);
@@ -1401,9 +1415,11 @@ static int32_t stream_grad_local(bfx_sampler* s, int c, const StreamBatch& b, fl
   const float* th = s->theta + (size_t)c * s->Ps;
   const bool valid = wsplit_valid(s);
   if (!valid) m->wsplit_owner = nullptr;
-  CK(stream_zero(gb, m->M.P, s->ssc + c, st));
+  if (pd) CK(stream_zero_peer(gb, m->M.P, s->ssc + c, *pd, st));  // (waits until no peer reads the previous epoch's buffer)
+  else CK(stream_zero(gb, m->M.P, s->ssc + c, st));
   CK(stream_eval_like(m->SM, m->W, th, m->x, m->y, b, nb, true, gb, s->ssc + c, st, nullptr, valid, hook));
-  if (pack && !(hook && hook->used)) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, st));
+  if (pack && pd) CK(stream_pack_sums_signal(gb, m->M.P, s->ssc + c, *pd, st));  // (sums + the peers' ready flags)
+  else if (pack && !(hook && hook->used)) CK(stream_pack_sums(gb, m->M.P, s->ssc + c, st));
   return BFX_OK;
 }
 
@@ -1420,11 +1436,16 @@ struct StreamRecord {
 
 static int32_t stream_apply(bfx_sampler* s, int c, float nb, bool from_buffer, unsigned long long seed, unsigned chainkey,
                             const float* inj, const StreamRecord& rec, cudaStream_t st, float* gb = nullptr,
-                            bool device_step = false) {
+                            bool device_step = false, const PeerDev* pd = nullptr) {
   bfx_model* m = s->m;
   if (!gb) gb = s->gbuf;
   float* th = s->theta + (size_t)c * s->Ps;
-  CK(stream_finish(m->SM, th, gb, s->ssc + c, nb, true, from_buffer, st));
+  if (pd) {  // the exchange IS the finish pass: sum of all ranks' buffers read over NVLink, result in gsum
+    gb = s->gsum;
+    CK(stream_finish_peer(m->SM, th, gb, s->ssc + c, nb, *pd, st));
+  } else {
+    CK(stream_finish(m->SM, th, gb, s->ssc + c, nb, true, from_buffer, st));
+  }
   StreamUpdate U{};
   U.S = &s->S;
   U.P = m->M.P;
@@ -1482,17 +1503,21 @@ static int32_t stream_update_once(bfx_sampler* s, const bfx_run_desc* run, int c
   // the side stream while the backward pass continues instead: measured slower since the GEMM grids fill all 148 SMs
   // in one wave (the NCCL kernels take SMs from them: 0.245 against 0.216 ms per update on 2 B200, profiles/).
   StreamBucketHook* hook = sharded && s->comm_stream && std::getenv("BFX_BUCKETS") ? &s->hook : nullptr;
-  int32_t rc = stream_grad_local(s, c, b, nbat, sharded, st, nullptr, hook);
+  // peer-memory exchange (all ranks opened all peers at comm_init; BFX_NO_P2P=1 keeps the NCCL call)
+  const PeerDev* pd = sharded && s->peer.n > 1 && !hook && !std::getenv("BFX_NO_P2P") ? &s->peer : nullptr;
+  int32_t rc = stream_grad_local(s, c, b, nbat, sharded, st, nullptr, hook, pd);
   if (rc) return rc;
   if (sharded) {
-    if (hook && hook->used) {
+    if (pd) {
+      // (the ready flags went out with the likelihood sums, stream_grad_local)
+    } else if (hook && hook->used) {
       CK(cudaStreamWaitEvent(st, hook->ev_join, 0));
     } else {
       rc = stream_allreduce(s, s->gbuf, st);
       if (rc) return rc;
     }
   }
-  return stream_apply(s, c, nbat, sharded, run->seed, noisekey, nullptr, rec, st, nullptr, device_step);
+  return stream_apply(s, c, nbat, sharded, run->seed, noisekey, nullptr, rec, st, nullptr, device_step, pd);
 }
 
 static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nsteps, int64_t base, float* samples_host,
@@ -1549,7 +1574,7 @@ static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nstep
       long long chain_offset;
       const void *samples_dev, *d_kin, *comm, *x, *w;
     } key{B, nbat, m->n, ke, samples_dev ? slots : 0, d_kin ? base : 0, d_kin ? nnew : 0, run->shuffle, run->batch_mode,
-          run->shard_mode, m->SM.tc, std::getenv("BFX_BUCKETS") ? 0 : 1, 0, run->seed, run->chain_offset, samples_dev, d_kin,
+          run->shard_mode, m->SM.tc, std::getenv("BFX_BUCKETS") ? 0 : 1, std::getenv("BFX_NO_P2P") ? 0 : s->peer.n, run->seed, run->chain_offset, samples_dev, d_kin,
           s->comm, m->x, m->W.w_hi};
     std::vector<unsigned char> kb(sizeof key);
     std::memcpy(kb.data(), &key, sizeof key);
@@ -2128,6 +2153,83 @@ int32_t bfx_comm_unique_id(void* id_out) {
   return BFX_OK;
 }
 
+// ---- peer-memory exchange: export gbuf + the flag block with CUDA IPC, gather everybody's handles through the
+// communicator, open the peers'.  Used only if EVERY rank succeeded (one all-reduced vote); otherwise the ranks keep
+// the NCCL all-reduce.  Nothing here is an error for the caller.
+static void peers_close(bfx_sampler* s) {
+  for (void*& p : s->peer_opened) {
+    if (p) cudaIpcCloseMemHandle(p);
+    p = nullptr;
+  }
+  s->peer = PeerDev{};
+}
+
+static void peers_setup(bfx_sampler* s, int nranks, int rank) {
+  peers_close(s);
+  NcclApi* api = nccl_api();
+  if (nranks < 2 || nranks > PEER_MAX || !api || !api->AllGather || std::getenv("BFX_NO_P2P_SETUP")) return;
+  bfx_model* m = s->m;
+  cudaStream_t st = m->stream;
+  const size_t P = (size_t)m->M.P;
+  struct Handles { cudaIpcMemHandle_t buf, flg; };
+  int ok = 1;
+  if (!s->gsum && cudaMalloc(&s->gsum, (P + 4) * sizeof(float)) != cudaSuccess) ok = 0;
+  if (!s->peer_flags && cudaMalloc(&s->peer_flags, PEER_WORDS * sizeof(unsigned long long)) != cudaSuccess) ok = 0;
+  if (ok) cudaMemsetAsync(s->peer_flags, 0, PEER_WORDS * sizeof(unsigned long long), st);
+  std::vector<Handles> all((size_t)nranks);
+  Handles mine{};
+  if (ok && cudaIpcGetMemHandle(&mine.buf, s->gbuf) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine.flg, s->peer_flags) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  // gather the handles (every rank takes part in the collectives whatever its own outcome)
+  Handles* d_h = nullptr;
+  float* d_vote = nullptr;
+  if (cudaMalloc(&d_h, sizeof(Handles) * (size_t)nranks) != cudaSuccess || cudaMalloc(&d_vote, sizeof(float)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(d_h);
+    cudaFree(d_vote);
+    return;  // (cannot even vote: extremely unlikely; the peers' gather would hang, so this is left to fail loudly there)
+  }
+  cudaMemcpyAsync(d_h + rank, &mine, sizeof mine, cudaMemcpyHostToDevice, st);
+  int r1 = api->AllGather(d_h + rank, d_h, sizeof(Handles), kNcclInt8, s->comm, st);
+  cudaMemcpyAsync(all.data(), d_h, sizeof(Handles) * (size_t)nranks, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess || r1 != 0) ok = 0;
+  PeerDev pd{};
+  pd.n = nranks;
+  pd.self = rank;
+  for (int r = 0; r < nranks && ok; ++r) {
+    if (r == rank) {
+      pd.buf[r] = s->gbuf;
+      pd.flg[r] = s->peer_flags;
+      continue;
+    }
+    void *pb = nullptr, *pf = nullptr;
+    if (cudaIpcOpenMemHandle(&pb, all[r].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pf, all[r].flg, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      if (pb) cudaIpcCloseMemHandle(pb);
+      ok = 0;
+      break;
+    }
+    s->peer_opened[2 * r] = pb;
+    s->peer_opened[2 * r + 1] = pf;
+    pd.buf[r] = static_cast<const float*>(pb);
+    pd.flg[r] = static_cast<unsigned long long*>(pf);
+  }
+  // the vote: the exchange is used only if all ranks can reach all peers
+  const float v = ok ? 1.f : 0.f;
+  float total = 0.f;
+  cudaMemcpyAsync(d_vote, &v, sizeof v, cudaMemcpyHostToDevice, st);
+  const int r2 = api->AllReduce(d_vote, d_vote, 1, kNcclFloat32, kNcclSum, s->comm, st);
+  cudaMemcpyAsync(&total, d_vote, sizeof total, cudaMemcpyDeviceToHost, st);
+  const bool all_ok = cudaStreamSynchronize(st) == cudaSuccess && r2 == 0 && total > (float)nranks - 0.5f;
+  cudaFree(d_h);
+  cudaFree(d_vote);
+  cudaGetLastError();
+  if (all_ok) s->peer = pd;
+  else peers_close(s);
+}
+
 int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, int32_t rank) {
   if (!s || !id) return fail(BFX_ERR_BAD_ARG, "NULL argument");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(BFX_ERR_BAD_ARG, "bad rank / nranks");
@@ -2141,6 +2243,7 @@ int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, in
     s->upd_graph = nullptr;
     cudaDeviceSynchronize();
   }
+  peers_close(s);
   if (s->comm) {
     api->CommDestroy(s->comm);
     s->comm = nullptr;
@@ -2170,6 +2273,7 @@ int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, in
     st = stream_allreduce(s, s->gbuf, s->m->stream);
     if (st) return st;
     CK(cudaStreamSynchronize(s->m->stream));
+    peers_setup(s, nranks, rank);
   }
   if (s->upd_graph) {
     cudaGraphExecDestroy(s->upd_graph);
@@ -2190,12 +2294,19 @@ int32_t bfx_sampler_comm_destroy(bfx_sampler* s) {
     s->upd_graph = nullptr;
     cudaDeviceSynchronize();
   }
+  peers_close(s);
   if (s->comm) {
     if (NcclApi* api = nccl_api()) api->CommDestroy(s->comm);
     s->comm = nullptr;
   }
   s->comm_rank = 0;
   s->comm_nranks = 1;
+  return BFX_OK;
+}
+
+int32_t bfx_sampler_peer_ranks(const bfx_sampler* s, int32_t* n) {
+  if (!s || !n) return fail(BFX_ERR_BAD_ARG, "NULL argument");
+  *n = (s->peer.n > 1 && !std::getenv("BFX_NO_P2P")) ? s->peer.n : 0;
   return BFX_OK;
 }
 

@@ -510,15 +510,82 @@ __global__ void k_pack_sums(float* g, long long P, const StreamScalars* sc) {
   g[P + 1] = (float)sc->ds1;
   g[P + 2] = (float)sc->bcount;
 }
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v);
+// the same, then the local gradient is complete: publish the epoch in every peer's ready[self] (one launch less)
+__global__ void k_pack_sums_signal(float* g, long long P, const StreamScalars* sc, const __grid_constant__ PeerDev pd) {
+  if (threadIdx.x == 0) {
+    g[P] = (float)sc->ds0;
+    g[P + 1] = (float)sc->ds1;
+    g[P + 2] = (float)sc->bcount;
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r < pd.n && r != pd.self) st_release_sys(pd.flg[r] + PEER_READY + pd.self, pd.flg[pd.self][PEER_EPOCH] + 1ull);
+}
 
 __global__ void k_set_gstep(StreamScalars* sc, long long gstep) { sc->gstep = gstep; }
 
 // prior, sigma prior, d/d theta_like, the value and the norms in one pass:
 //   g_net -= c2 * theta_net;  g_like = glike;  value = nb * loglike + logprior
-__global__ void k_finish(StreamModel M, const float* __restrict__ theta, float* __restrict__ g, StreamScalars* sc, float nb,
-                         int want_grad, int from_buffer) {
+// (PEER: the gradient and the likelihood sums are the rank-ordered sums over all ranks' exchange buffers, read over
+// NVLink behind the peers' ready flags; the result goes to the local buffer g)
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// thread 0 of the block waits until word[j] >= e for every peer j; false after ~2 s (a peer died): the caller flags
+// the chain instead of hanging the GPU
+__device__ __forceinline__ bool peer_wait(const unsigned long long* words, int n, int self, unsigned long long e) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    int ok = 1;
+    const long long t0 = clock64();
+    for (int j = 0; j < n && ok; ++j) {
+      if (j == self) continue;
+      while (ld_acquire_sys(words + j) < e) {
+        if (clock64() - t0 > 4000000000LL) {
+          ok = 0;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+template <bool PEER>
+__device__ __forceinline__ void finish_body(const StreamModel& M, const float* __restrict__ theta, float* __restrict__ g,
+                                            StreamScalars* sc, float nb, int want_grad, int from_buffer, const PeerDev& pd) {
   double ds0, ds1, B;
-  if (from_buffer) {
+  unsigned long long epoch = 0;
+  if (PEER) {
+    epoch = pd.flg[pd.self][PEER_EPOCH] + 1ull;
+    if (!peer_wait(pd.flg[pd.self] + PEER_READY, pd.n, pd.self, epoch)) {
+      if (grid_last(&sc->ticket) && threadIdx.x == 0) sc->status = 8;  // peer exchange timed out
+      return;
+    }
+    // the three likelihood sums: one thread per block fetches the ranks' tails (remote reads), the block shares them
+    __shared__ double s_sum[3];
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0, c = 0.0;
+      for (int r = 0; r < pd.n; ++r) {
+        a += (double)__ldcg(pd.buf[r] + M.P);
+        b += (double)__ldcg(pd.buf[r] + M.P + 1);
+        c += (double)__ldcg(pd.buf[r] + M.P + 2);
+      }
+      s_sum[0] = a; s_sum[1] = b; s_sum[2] = c;
+    }
+    __syncthreads();
+    ds0 = s_sum[0]; ds1 = s_sum[1]; B = s_sum[2];
+  } else if (from_buffer) {
     ds0 = (double)g[M.P];
     ds1 = (double)g[M.P + 1];
     B = (double)g[M.P + 2];
@@ -557,14 +624,30 @@ __global__ void k_finish(StreamModel M, const float* __restrict__ theta, float* 
     float th[4], gg[4];
     if (cnt == 4) {
       const float4 t = *reinterpret_cast<const float4*>(theta + i);
-      const float4 gv = *reinterpret_cast<const float4*>(g + i);
       th[0] = t.x; th[1] = t.y; th[2] = t.z; th[3] = t.w;
-      gg[0] = gv.x; gg[1] = gv.y; gg[2] = gv.z; gg[3] = gv.w;
+      if (PEER) {
+        float4 gv = __ldcg(reinterpret_cast<const float4*>(pd.buf[0] + i));
+        for (int r = 1; r < pd.n; ++r) {
+          const float4 o = __ldcg(reinterpret_cast<const float4*>(pd.buf[r] + i));
+          gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
+        }
+        gg[0] = gv.x; gg[1] = gv.y; gg[2] = gv.z; gg[3] = gv.w;
+      } else {
+        const float4 gv = *reinterpret_cast<const float4*>(g + i);
+        gg[0] = gv.x; gg[1] = gv.y; gg[2] = gv.z; gg[3] = gv.w;
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         th[j] = j < cnt ? theta[i + j] : 0.f;
-        gg[j] = j < cnt ? g[i + j] : 0.f;
+        if (PEER) {
+          float a = 0.f;
+          if (j < cnt)
+            for (int r = 0; r < pd.n; ++r) a += __ldcg(pd.buf[r] + i + j);
+          gg[j] = a;
+        } else {
+          gg[j] = j < cnt ? g[i + j] : 0.f;
+        }
       }
     }
 #pragma unroll
@@ -593,13 +676,50 @@ __global__ void k_finish(StreamModel M, const float* __restrict__ theta, float* 
     sc->gn2 = tot[1];
     sc->glike = glike;
     sc->value = (double)nb * like + M.prior_c0n - 0.5 * (double)M.prior_c2 * tot[0];
-    if (from_buffer) {
+    if (from_buffer || PEER) {
       sc->ds0 = ds0;
       sc->ds1 = ds1;
       sc->bcount = B;
     }
+    if (PEER) {  // every block of this grid has finished reading the peers' buffers (it arrived at the reduction)
+      __threadfence_system();
+      for (int r = 0; r < pd.n; ++r)
+        if (r != pd.self) st_release_sys(pd.flg[r] + PEER_DONE + pd.self, epoch);
+      pd.flg[pd.self][PEER_EPOCH] = epoch;
+    }
   }
 }
+
+__global__ void k_finish(StreamModel M, const float* __restrict__ theta, float* __restrict__ g, StreamScalars* sc, float nb,
+                         int want_grad, int from_buffer) {
+  finish_body<false>(M, theta, g, sc, nb, want_grad, from_buffer, PeerDev{});
+}
+__global__ void k_finish_peer(StreamModel M, const float* __restrict__ theta, float* __restrict__ g, StreamScalars* sc,
+                              float nb, const __grid_constant__ PeerDev pd) {
+  finish_body<true>(M, theta, g, sc, nb, 1, 1, pd);
+}
+// behind the local gradient (stream order): publish the epoch in every peer's ready[self]
+__global__ void k_peer_signal(const __grid_constant__ PeerDev pd) {
+  const int r = threadIdx.x;
+  if (r < pd.n && r != pd.self) {
+    const unsigned long long e = pd.flg[pd.self][PEER_EPOCH] + 1ull;
+    __threadfence_system();
+    st_release_sys(pd.flg[r] + PEER_READY + pd.self, e);
+  }
+}
+// k_zero behind the peers' done flags: nobody reads this rank's buffer of the previous epoch any more
+__global__ void k_zero_peer(float* g, long long P, StreamScalars* sc, const __grid_constant__ PeerDev pd) {
+  const unsigned long long e = pd.flg[pd.self][PEER_EPOCH];
+  const bool ok = peer_wait(pd.flg[pd.self] + PEER_DONE, pd.n, pd.self, e);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) g[i] = 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->ds0 = sc->ds1 = sc->bcount = 0.0;
+    sc->th2 = sc->gn2 = sc->acc0 = sc->acc1 = 0.0;
+    if (!ok) sc->status = 8;
+  }
+}
+
+
 
 // g[dst + e] += sum_z src[z * stride + e] for a list of vectors (split-K partials of the weight gradients, bias-
 // gradient row sums, the head's partial sums), summed in slot order
@@ -813,6 +933,24 @@ void stream_work_free(StreamWork& W) {
 
 cudaError_t stream_zero(float* g, long long P, StreamScalars* sc, cudaStream_t st) {
   k_zero<<<296, 256, 0, st>>>(g, P, sc);
+  return cudaGetLastError();
+}
+
+cudaError_t stream_zero_peer(float* g, long long P, StreamScalars* sc, const PeerDev& pd, cudaStream_t st) {
+  k_zero_peer<<<296, 256, 0, st>>>(g, P, sc, pd);
+  return cudaGetLastError();
+}
+cudaError_t stream_peer_signal(const PeerDev& pd, cudaStream_t st) {
+  k_peer_signal<<<1, 32, 0, st>>>(pd);
+  return cudaGetLastError();
+}
+cudaError_t stream_pack_sums_signal(float* g, long long P, StreamScalars* sc, const PeerDev& pd, cudaStream_t st) {
+  k_pack_sums_signal<<<1, 32, 0, st>>>(g, P, sc, pd);
+  return cudaGetLastError();
+}
+cudaError_t stream_finish_peer(const StreamModel& M, const float* theta, float* g_out, StreamScalars* sc, float nb,
+                               const PeerDev& pd, cudaStream_t st) {
+  k_finish_peer<<<STREAM_RED_BLOCKS, 256, 0, st>>>(M, theta, g_out, sc, nb, pd);
   return cudaGetLastError();
 }
 

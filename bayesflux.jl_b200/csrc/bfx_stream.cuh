@@ -127,6 +127,30 @@ struct StreamBucketHook {
   int used;  // set by stream_eval_like: 1 = the buckets were issued (the caller joins on ev_join), 0 = not applicable
 };
 
+// ---- peer-memory exchange of the minibatch-sharded chain (NVLink / NVSwitch) -----------------------
+// Every rank exports its exchange buffer [g ; ds0 ; ds1 ; B] (P + 3 floats) and a block of flags with CUDA IPC; the
+// finish kernel of every rank then READS all ranks' buffers over NVLink and sums them in rank order while it applies
+// the prior: the all-reduce and the finish pass are one kernel, the sums are bit-identical on every rank, and nothing
+// but two flag words per peer crosses the fabric besides the payload.  Flags of rank q (in q's memory, written by the
+// peers with system-scope stores): ready[j] = last epoch whose local gradient rank j has completed, done[j] = last
+// epoch whose buffers rank j has finished reading, epoch = updates this rank has finished.
+constexpr int PEER_MAX = 8;
+constexpr int PEER_READY = 0, PEER_DONE = PEER_MAX, PEER_EPOCH = 2 * PEER_MAX, PEER_WORDS = 2 * PEER_MAX + 8;
+struct PeerDev {
+  int n, self;                          // n <= 1: no exchange
+  const float* buf[PEER_MAX];           // exchange buffers of all ranks (own one included)
+  unsigned long long* flg[PEER_MAX];    // flag blocks of all ranks
+};
+// behind the local gradient: publish epoch + 1 in every rank's ready[self]
+cudaError_t stream_peer_signal(const PeerDev& pd, cudaStream_t st);
+// stream_pack_sums and the signal in one launch
+cudaError_t stream_pack_sums_signal(float* g, long long P, StreamScalars* sc, const PeerDev& pd, cudaStream_t st);
+// stream_finish with the exchange folded in: g_out[i] = sum_r buf[r][i] - c2 theta (...), likelihood sums from the tails
+cudaError_t stream_finish_peer(const StreamModel& M, const float* theta, float* g_out, StreamScalars* sc, float nb,
+                               const PeerDev& pd, cudaStream_t st);
+// stream_zero that first waits until every peer has finished reading this rank's buffer of the previous epoch
+cudaError_t stream_zero_peer(float* g, long long P, StreamScalars* sc, const PeerDev& pd, cudaStream_t st);
+
 // likelihood part of the evaluation on one minibatch: g[0..Pnet) += num_batches * d loglike / d theta_net
 // (g must be zeroed by the caller), sc->ds0/ds1/bcount += sums.  theta_split_valid: W.w_hi / w_lo already hold
 // the BF16 halves of theta (the sampler updates keep them current).

@@ -262,6 +262,21 @@ def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
         ms_single = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / steps
         del os.environ["BFX_BUCKETS"]
         log(f"cfg3: {ms_single * 1e3:.1f} us per update with per-layer buckets")
+    # ... and with the NCCL all-reduce in place of the peer-memory exchange (BFX_NO_P2P=1), when the latter is in use
+    peers = bf.peer_ranks(s) if world > 1 else 0
+    ms_nccl = None
+    if world > 1 and peers > 1:
+        os.environ["BFX_NO_P2P"] = "1"
+        bf.advance(s, Bl, 3, **kw)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record(st)
+        bf.advance(s, Bl, steps, **kw)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms_nccl = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1)) / steps
+        del os.environ["BFX_NO_P2P"]
+        log(f"cfg3: {ms_nccl * 1e3:.1f} us per update with the NCCL all-reduce")
     # phase split through the three-call form of the same update (direct launches, one event between the phases)
     run = A._run_desc(Bl, 0, True, True, True, 1, SEED, "per_chain", rank, world, shard)
     buf = torch.empty(P + 3, dtype=torch.float32, device="cuda")
@@ -310,9 +325,12 @@ def secondary_cfg3(bf, torch, dist, world, rank, local, steps=30):
                                         "sum": (tg + tc + tu) / ksplit},
            "allreduce_bytes": ar_bytes,
            "allreduce_busbw_gbs": (2.0 * (world - 1) / world * ar_bytes / (ar_ms * 1e-3) / 1e9) if world > 1 and ar_ms > 0 else None,
-           "collective": "one ncclAllReduce of P+3 floats issued by libbfx on the engine's stream inside the update graph "
-                         "(per-layer buckets on a side stream are the BFX_BUCKETS=1 variant, timed beside it)"
+           "collective": ("peer-memory exchange: every rank's finish kernel reads the P+3 floats of all ranks over NVLink "
+                          "(CUDA IPC mappings, flags in peer memory) and sums them in rank order; no collective call"
+                          if peers > 1 else
+                          "one ncclAllReduce of P+3 floats issued by libbfx on the engine's stream inside the update graph")
                          if world > 1 else "none (single rank)",
+           "peer_ranks": peers, "ms_per_update_nccl_allreduce": ms_nccl,
            "ms_per_update_bucketed": ms_single,
            "bucketed_minus_single_ms": (ms_single - ms) if ms_single is not None else None,
            "replicas_bit_identical": identical, "finite": ok}

@@ -335,12 +335,18 @@ int32_t bfx_stream_allreduce(bfx_sampler* s, void* stream_handle, float* buf_dev
  * NCCL.jl) shares that copy.  Rank 0 creates the 128-byte id, the caller distributes it (MPI, torch.distributed, a
  * file ...), every rank calls bfx_sampler_comm_init (collective).  With a communicator attached and
  * run->shard_mode == BFX_SHARD_MINIBATCH, bfx_mcmc_run / bfx_mcmc_advance perform
- *     local gradient  ->  ncclAllReduce(P + 3 floats) on the engine's stream  ->  replicated update
- * for every update!, captured together in one CUDA graph per update. */
+ *     local gradient  ->  sum of the P + 3 floats over the ranks  ->  replicated update
+ * for every update!, captured together in one CUDA graph per update.  The sum: bfx_sampler_comm_init also exports
+ * every rank's exchange buffer with CUDA IPC; when all ranks can open all peers (one box, NVLink / NVSwitch), the
+ * finish kernel of each rank reads the peers' buffers directly and sums them in rank order (exchange and finish pass
+ * are one kernel, flags in peer memory order it: no collective call); otherwise, and with BFX_NO_P2P=1,
+ * ncclAllReduce on the engine's stream.  bfx_sampler_peer_ranks reports which one is in use. */
 #define BFX_COMM_ID_BYTES 128
 int32_t bfx_comm_unique_id(void* id_out /* BFX_COMM_ID_BYTES */);
 int32_t bfx_sampler_comm_init(bfx_sampler* s, const void* id, int32_t nranks, int32_t rank);
 int32_t bfx_sampler_comm_destroy(bfx_sampler* s);
+/* ranks whose exchange buffers this sampler reads over peer memory (0 or 1: the NCCL all-reduce is used instead) */
+int32_t bfx_sampler_peer_ranks(const bfx_sampler* s, int32_t* n);
 /* number of update! graphs replayed by this sampler so far (stream regime: one cudaGraphLaunch per update!) */
 int32_t bfx_sampler_graph_replays(const bfx_sampler* s, int64_t* n);
 
