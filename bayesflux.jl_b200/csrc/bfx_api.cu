@@ -163,7 +163,7 @@ struct bfx_sampler {
   PeerDev peer{};
   float* gsum = nullptr;                 // [P + 4] the summed gradient (the peers keep reading gbuf meanwhile)
   unsigned long long* peer_flags = nullptr;
-  void* peer_opened[2 * PEER_MAX] = {};  // IPC mappings to close
+  void* peer_opened[3 * PEER_MAX] = {};  // IPC mappings to close
 };
 
 // ---------------------------------------------------------------------------------
@@ -1415,7 +1415,8 @@ static int32_t stream_grad_local(bfx_sampler* s, int c, const StreamBatch& b, fl
   const float* th = s->theta + (size_t)c * s->Ps;
   const bool valid = wsplit_valid(s);
   if (!valid) m->wsplit_owner = nullptr;
-  if (pd) CK(stream_zero_peer(gb, m->M.P, s->ssc + c, *pd, st));  // (waits until no peer reads the previous epoch's buffer)
+  // (PULL: waits until no peer reads the previous epoch's buffer; SCATTER: the join kernel of the previous update did)
+  if (pd && pd->mode == PEER_MODE_PULL) CK(stream_zero_peer(gb, m->M.P, s->ssc + c, *pd, st));
   else CK(stream_zero(gb, m->M.P, s->ssc + c, st));
   CK(stream_eval_like(m->SM, m->W, th, m->x, m->y, b, nb, true, gb, s->ssc + c, st, nullptr, valid, hook));
   if (pack && pd) CK(stream_pack_sums_signal(gb, m->M.P, s->ssc + c, *pd, st));  // (sums + the peers' ready flags)
@@ -1442,7 +1443,8 @@ static int32_t stream_apply(bfx_sampler* s, int c, float nb, bool from_buffer, u
   float* th = s->theta + (size_t)c * s->Ps;
   if (pd) {  // the exchange IS the finish pass: sum of all ranks' buffers read over NVLink, result in gsum
     gb = s->gsum;
-    CK(stream_finish_peer(m->SM, th, gb, s->ssc + c, nb, *pd, st));
+    if (pd->mode == PEER_MODE_SCATTER) CK(stream_finish_scatter(m->SM, th, s->ssc + c, nb, *pd, st));
+    else CK(stream_finish_peer(m->SM, th, gb, s->ssc + c, nb, *pd, st));
   } else {
     CK(stream_finish(m->SM, th, gb, s->ssc + c, nb, true, from_buffer, st));
   }
@@ -1574,7 +1576,7 @@ static int32_t stream_run(bfx_sampler* s, const bfx_run_desc* run, int64_t nstep
       long long chain_offset;
       const void *samples_dev, *d_kin, *comm, *x, *w;
     } key{B, nbat, m->n, ke, samples_dev ? slots : 0, d_kin ? base : 0, d_kin ? nnew : 0, run->shuffle, run->batch_mode,
-          run->shard_mode, m->SM.tc, std::getenv("BFX_BUCKETS") ? 0 : 1, std::getenv("BFX_NO_P2P") ? 0 : s->peer.n, run->seed, run->chain_offset, samples_dev, d_kin,
+          run->shard_mode, m->SM.tc, std::getenv("BFX_BUCKETS") ? 0 : 1, std::getenv("BFX_NO_P2P") ? 0 : s->peer.n * 4 + s->peer.mode, run->seed, run->chain_offset, samples_dev, d_kin,
           s->comm, m->x, m->W.w_hi};
     std::vector<unsigned char> kb(sizeof key);
     std::memcpy(kb.data(), &key, sizeof key);
@@ -2167,11 +2169,13 @@ static void peers_close(bfx_sampler* s) {
 static void peers_setup(bfx_sampler* s, int nranks, int rank) {
   peers_close(s);
   NcclApi* api = nccl_api();
-  if (nranks < 2 || nranks > PEER_MAX || !api || !api->AllGather || std::getenv("BFX_NO_P2P_SETUP")) return;
+  int max_ranks = PEER_MAX;
+  if (const char* e = std::getenv("BFX_P2P_MAX_RANKS")) max_ranks = std::atoi(e);
+  if (nranks < 2 || nranks > PEER_MAX || nranks > max_ranks || !api || !api->AllGather) return;
   bfx_model* m = s->m;
   cudaStream_t st = m->stream;
   const size_t P = (size_t)m->M.P;
-  struct Handles { cudaIpcMemHandle_t buf, flg; };
+  struct Handles { cudaIpcMemHandle_t buf, flg, sum; };
   int ok = 1;
   if (!s->gsum && cudaMalloc(&s->gsum, (P + 4) * sizeof(float)) != cudaSuccess) ok = 0;
   if (!s->peer_flags && cudaMalloc(&s->peer_flags, PEER_WORDS * sizeof(unsigned long long)) != cudaSuccess) ok = 0;
@@ -2180,6 +2184,7 @@ static void peers_setup(bfx_sampler* s, int nranks, int rank) {
   Handles mine{};
   if (ok && cudaIpcGetMemHandle(&mine.buf, s->gbuf) != cudaSuccess) ok = 0;
   if (ok && cudaIpcGetMemHandle(&mine.flg, s->peer_flags) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine.sum, s->gsum) != cudaSuccess) ok = 0;
   cudaGetLastError();
   // gather the handles (every rank takes part in the collectives whatever its own outcome)
   Handles* d_h = nullptr;
@@ -2201,21 +2206,29 @@ static void peers_setup(bfx_sampler* s, int nranks, int rank) {
     if (r == rank) {
       pd.buf[r] = s->gbuf;
       pd.flg[r] = s->peer_flags;
+      pd.sum[r] = s->gsum;
       continue;
     }
-    void *pb = nullptr, *pf = nullptr;
+    void *pb = nullptr, *pf = nullptr, *ps = nullptr;
     if (cudaIpcOpenMemHandle(&pb, all[r].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&pf, all[r].flg, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaIpcOpenMemHandle(&pf, all[r].flg, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&ps, all[r].sum, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
       cudaGetLastError();
       if (pb) cudaIpcCloseMemHandle(pb);
+      if (pf) cudaIpcCloseMemHandle(pf);
       ok = 0;
       break;
     }
-    s->peer_opened[2 * r] = pb;
-    s->peer_opened[2 * r + 1] = pf;
+    s->peer_opened[3 * r] = pb;
+    s->peer_opened[3 * r + 1] = pf;
+    s->peer_opened[3 * r + 2] = ps;
     pd.buf[r] = static_cast<const float*>(pb);
     pd.flg[r] = static_cast<unsigned long long*>(pf);
+    pd.sum[r] = static_cast<float*>(ps);
   }
+  // protocol: pull for two ranks, scatter beyond ($BFX_P2P_MODE = 1 | 2 overrides)
+  pd.mode = nranks <= 2 ? PEER_MODE_PULL : PEER_MODE_SCATTER;
+  if (const char* e = std::getenv("BFX_P2P_MODE")) pd.mode = std::atoi(e) == 2 ? PEER_MODE_SCATTER : PEER_MODE_PULL;
   // the vote: the exchange is used only if all ranks can reach all peers
   const float v = ok ? 1.f : 0.f;
   float total = 0.f;

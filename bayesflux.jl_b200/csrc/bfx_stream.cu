@@ -698,6 +698,135 @@ __global__ void k_finish_peer(StreamModel M, const float* __restrict__ theta, fl
                               float nb, const __grid_constant__ PeerDev pd) {
   finish_body<true>(M, theta, g, sc, nb, 1, 1, pd);
 }
+// ---- SCATTER protocol (bfx_stream.cuh) --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finish_scatter(StreamModel M, const float* __restrict__ theta, StreamScalars* sc,
+                                                        float nb, const __grid_constant__ PeerDev pd) {
+  const unsigned long long epoch = pd.flg[pd.self][PEER_EPOCH] + 1ull;
+  if (!peer_wait(pd.flg[pd.self] + PEER_READY, pd.n, pd.self, epoch)) {
+    if (grid_last(&sc->ticket) && threadIdx.x == 0) sc->status = 8;  // peer exchange timed out
+    return;
+  }
+  __shared__ double s_sum[3];
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int r = 0; r < pd.n; ++r) {
+      a += (double)__ldcg(pd.buf[r] + M.P);
+      b += (double)__ldcg(pd.buf[r] + M.P + 1);
+      c += (double)__ldcg(pd.buf[r] + M.P + 2);
+    }
+    s_sum[0] = a; s_sum[1] = b; s_sum[2] = c;
+  }
+  __syncthreads();
+  const double ds0 = s_sum[0], ds1 = s_sum[1], B = s_sum[2];
+  const float sl = theta[M.P - 1];
+  const double sigma = (double)expf(sl);
+  double lps, dlps;
+  if (M.sprior_kind == SP_GAMMA) {
+    lps = M.sprior_const + ((double)M.sprior_a - 1.0) * (double)sl - sigma / (double)M.sprior_b + (double)sl;
+    dlps = (double)M.sprior_a - sigma / (double)M.sprior_b;
+  } else {
+    lps = M.sprior_const - ((double)M.sprior_a + 1.0) * (double)sl - (double)M.sprior_b / sigma + (double)sl;
+    dlps = -(double)M.sprior_a + (double)M.sprior_b / sigma;
+  }
+  double like, dlike;
+  if (M.like_kind == LK_NORMAL) {
+    like = -0.5 * B * 1.8378770664093453 - 0.5 * ds0;
+    dlike = ds0;
+  } else {
+    like = B * M.tdist_const - 0.5 * ((double)M.nu + 1.0) * ds0;
+    dlike = ds1;
+  }
+  like += -B * (double)sl + lps;
+  dlike += -B + dlps;
+  const float glike = (float)((double)nb * dlike);
+  // this rank's slice of the quads
+  const long long nq = (M.P + 3) >> 2, per = (nq + pd.n - 1) / pd.n;
+  const long long q0 = per * pd.self, q1 = (q0 + per < nq) ? q0 + per : nq;
+  float a0 = 0.f, a1 = 0.f;
+  const float c2 = M.prior_c2;
+  for (long long q = q0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; q < q1; q += (long long)gridDim.x * blockDim.x) {
+    const long long i = q << 2;
+    const int cnt = M.P - i < 4 ? (int)(M.P - i) : 4;
+    float th[4], gg[4];
+    if (cnt == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(theta + i);
+      th[0] = t.x; th[1] = t.y; th[2] = t.z; th[3] = t.w;
+      float4 gv = __ldcg(reinterpret_cast<const float4*>(pd.buf[0] + i));
+      for (int r = 1; r < pd.n; ++r) {
+        const float4 o = __ldcg(reinterpret_cast<const float4*>(pd.buf[r] + i));
+        gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
+      }
+      gg[0] = gv.x; gg[1] = gv.y; gg[2] = gv.z; gg[3] = gv.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        th[j] = j < cnt ? theta[i + j] : 0.f;
+        float a = 0.f;
+        if (j < cnt)
+          for (int r = 0; r < pd.n; ++r) a += __ldcg(pd.buf[r] + i + j);
+        gg[j] = a;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < cnt) {
+        if (i + j < M.Pnet) {
+          a0 += th[j] * th[j];
+          gg[j] = gg[j] - c2 * th[j];
+        } else {
+          gg[j] = glike;
+        }
+        a1 += gg[j] * gg[j];
+      }
+    }
+    for (int r = 0; r < pd.n; ++r) {  // the finished slice goes to every rank's result buffer (remote stores)
+      if (cnt == 4) {
+        *reinterpret_cast<float4*>(pd.sum[r] + i) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      } else {
+        for (int j = 0; j < cnt; ++j) pd.sum[r][i + j] = gg[j];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();  // this block's remote stores are ordered before the flag below
+  double tot[2];
+  if (grid_sum2((double)a0, (double)a1, sc, &sc->ticket, tot) && threadIdx.x == 0) {
+    sc->glike = glike;
+    sc->value = (double)nb * like + M.prior_c0n;  // (the join subtracts the prior's quadratic term)
+    sc->ds0 = ds0;
+    sc->ds1 = ds1;
+    sc->bcount = B;
+    for (int r = 0; r < pd.n; ++r) {
+      double* nr = reinterpret_cast<double*>(pd.flg[r] + PEER_NORMS);
+      nr[2 * pd.self] = tot[0];
+      nr[2 * pd.self + 1] = tot[1];
+    }
+    __threadfence_system();
+    for (int r = 0; r < pd.n; ++r) st_release_sys(pd.flg[r] + PEER_SLICED + pd.self, epoch);
+    pd.flg[pd.self][PEER_EPOCH] = epoch;
+  }
+}
+// one block: every slice has arrived (and every peer has finished reading this rank's buffer); norms in rank order
+__global__ void k_peer_join(StreamModel M, StreamScalars* sc, const __grid_constant__ PeerDev pd) {
+  const unsigned long long epoch = pd.flg[pd.self][PEER_EPOCH];
+  const bool ok = peer_wait(pd.flg[pd.self] + PEER_SLICED, pd.n, pd.self, epoch);
+  if (threadIdx.x == 0) {
+    if (!ok) {
+      sc->status = 8;
+    } else {
+      const double* nr = reinterpret_cast<const double*>(pd.flg[pd.self] + PEER_NORMS);
+      double th2 = 0.0, gn2 = 0.0;
+      for (int r = 0; r < pd.n; ++r) {
+        th2 += __ldcg(nr + 2 * r);
+        gn2 += __ldcg(nr + 2 * r + 1);
+      }
+      sc->th2 = th2;
+      sc->gn2 = gn2;
+      sc->value -= 0.5 * (double)M.prior_c2 * th2;
+    }
+  }
+}
+
 // behind the local gradient (stream order): publish the epoch in every peer's ready[self]
 __global__ void k_peer_signal(const __grid_constant__ PeerDev pd) {
   const int r = threadIdx.x;
@@ -942,6 +1071,16 @@ cudaError_t stream_zero_peer(float* g, long long P, StreamScalars* sc, const Pee
 }
 cudaError_t stream_peer_signal(const PeerDev& pd, cudaStream_t st) {
   k_peer_signal<<<1, 32, 0, st>>>(pd);
+  return cudaGetLastError();
+}
+cudaError_t stream_finish_scatter(const StreamModel& M, const float* theta, StreamScalars* sc, float nb, const PeerDev& pd,
+                                  cudaStream_t st) {
+  const long long nq = (M.P + 3) >> 2, per = (nq + pd.n - 1) / pd.n;
+  long long grid = (per + 255) / 256;
+  if (grid > STREAM_RED_BLOCKS) grid = STREAM_RED_BLOCKS;
+  if (grid < 1) grid = 1;
+  k_finish_scatter<<<(unsigned)grid, 256, 0, st>>>(M, theta, sc, nb, pd);
+  k_peer_join<<<1, 32, 0, st>>>(M, sc, pd);
   return cudaGetLastError();
 }
 cudaError_t stream_pack_sums_signal(float* g, long long P, StreamScalars* sc, const PeerDev& pd, cudaStream_t st) {

@@ -135,12 +135,25 @@ struct StreamBucketHook {
 // peers with system-scope stores): ready[j] = last epoch whose local gradient rank j has completed, done[j] = last
 // epoch whose buffers rank j has finished reading, epoch = updates this rank has finished.
 constexpr int PEER_MAX = 8;
-constexpr int PEER_READY = 0, PEER_DONE = PEER_MAX, PEER_EPOCH = 2 * PEER_MAX, PEER_WORDS = 2 * PEER_MAX + 8;
+//
+// Two protocols.  PULL (2 ranks): every rank reads the whole buffer of every peer ((n - 1) x 2.24 MB in).  SCATTER
+// (more ranks): rank r pulls only ITS 1/n slice of every buffer, finishes it (prior, norms) and PUSHES the finished
+// slice into every rank's result buffer (2 x (n - 1) / n x 2.24 MB per rank over the fabric, independent of n); the
+// partial norms travel with a sliced[r] flag, a one-block join kernel waits for all slices and folds the norms in rank
+// order before the update kernels run.  sliced[] doubles as "done reading" of the next epoch's first kernel.
+constexpr int PEER_READY = 0, PEER_DONE = PEER_MAX, PEER_EPOCH = 2 * PEER_MAX, PEER_SLICED = 3 * PEER_MAX,
+              PEER_NORMS = 4 * PEER_MAX /* 2 doubles per rank */, PEER_WORDS = 6 * PEER_MAX;
+enum { PEER_MODE_PULL = 1, PEER_MODE_SCATTER = 2 };
 struct PeerDev {
   int n, self;                          // n <= 1: no exchange
+  int mode, pad_;
   const float* buf[PEER_MAX];           // exchange buffers of all ranks (own one included)
+  float* sum[PEER_MAX];                 // result buffers of all ranks (SCATTER pushes finished slices into them)
   unsigned long long* flg[PEER_MAX];    // flag blocks of all ranks
 };
+// SCATTER: the slice kernel and the join that makes the norms / the gathered gradient available to the update kernels
+cudaError_t stream_finish_scatter(const StreamModel& M, const float* theta, StreamScalars* sc, float nb, const PeerDev& pd,
+                                  cudaStream_t st);
 // behind the local gradient: publish epoch + 1 in every rank's ready[self]
 cudaError_t stream_peer_signal(const PeerDev& pd, cudaStream_t st);
 // stream_pack_sums and the signal in one launch
