@@ -183,7 +183,16 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 24 : (BT == 16 ? 1 : 512 / NT)
     }
     __syncthreads();
     for_each_quad<NT>(M, [&](int k) { st4(X.th_g + k, ld4(s.th + k)); });
-    if (threadIdx.x == 0) R.sc[c] = X.sc;
+    if (threadIdx.x == 0) {
+      if (KIND == S_SGLD) {
+        // SGLD only moves its two counters: writing the whole struct back would keep all 24 words of it live in
+        // registers over the chunk (the fused kernels sit at their register cap)
+        R.sc[c].t = X.sc.t;
+        R.sc[c].nsampled = X.sc.nsampled;
+      } else {
+        R.sc[c] = X.sc;
+      }
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicExch(R.work + 1 + c, chunk + 1);
