@@ -128,6 +128,7 @@ struct TcDyn {
   BFX_HD static int S(const ModelDev& M) { return M.S; }
   BFX_HD static int like_s(const ModelDev& M) { return M.like_s; }
   BFX_HD static int d_in(const ModelDev& M) { return M.d_in; }
+  BFX_HD static int misc_off(const ModelDev& M) { return M.tc.misc_off; }
 };
 template <int DIN, int H1, int H2, int ACT1, int ACT2>
 struct TcFixed {
@@ -185,11 +186,12 @@ struct TcFixed {
   BFX_HD static constexpr int like_s(const ModelDev& M) { return ld(M, 2).b_s + 4; }
   BFX_HD static constexpr int S(const ModelDev& M) { return like_s(M) + 4; }
   BFX_HD static constexpr int d_in(const ModelDev&) { return DIN; }
+  BFX_HD static constexpr int misc_off(const ModelDev& M) { return d_off(M) + 2 * d_bytes(M); }
   // host: does the run-time model have exactly this layout?
   static bool matches(const ModelDev& M) {
     if (!M.tc.enabled || M.nlayers != 3 || M.tc.nh != 2 || M.rec_layer >= 0 || M.seq) return false;
     if (M.S != S(M) || M.like_s != like_s(M) || M.d_in != DIN) return false;
-    if (M.tc.d_off != d_off(M) || M.tc.d_bytes != d_bytes(M)) return false;
+    if (M.tc.d_off != d_off(M) || M.tc.d_bytes != d_bytes(M) || M.tc.misc_off != misc_off(M)) return false;
     for (int l = 0; l < 3; ++l) {
       const LayerDev a = ld(M, l);
       const LayerDev& b = M.L[l];

@@ -503,20 +503,22 @@ __host__ __device__ inline size_t chain_smem_bytes(const ModelDev& M) {
   return b;
 }
 
-template <int BT>
+// (SP: a TcFixed shape makes every offset below a literal, so the pointers cost no registers of their own)
+template <int BT, class SP = TcDyn>
 BFX_DEV ChainSmem carve_smem(const ModelDev& M, unsigned char* base) {
   ChainSmem s;
   double* d = reinterpret_cast<double*>(base);
   s.dacc = d;
+  const int S = SP::S(M);
   float* f = reinterpret_cast<float*>(d + 4);
-  s.th = f; f += M.S;
-  s.g = f; f += M.S;
-  s.act = f; f += (M.tc.enabled ? 0 : M.act_total);
+  s.th = f; f += S;
+  s.g = f; f += S;
+  s.act = f; f += (SP::fixed || M.tc.enabled ? 0 : M.act_total);
   s.ys = f; f += BT;
   s.idx = reinterpret_cast<int*>(f); f += BT;
   s.red = f; f += 32 * 4;
-  s.mask = reinterpret_cast<unsigned char*>(f); f += ((M.S / 4 + 15) & ~15) / 4;
-  s.qflat = reinterpret_cast<unsigned short*>(f); f += ((M.S / 4 + 15) & ~15) / 2;
+  s.mask = reinterpret_cast<unsigned char*>(f); f += ((S / 4 + 15) & ~15) / 4;
+  s.qflat = reinterpret_cast<unsigned short*>(f); f += ((S / 4 + 15) & ~15) / 2;
   s.tc = nullptr;
   s.scr = nullptr;
   if (M.tc.enabled) {

@@ -122,10 +122,10 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 24 : (BT == 16 ? 1 : 512 / NT)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_item;
   const ModelDev& M = R.M;
-  ChainSmem s = carve_smem<BT>(M, smem_raw);
+  ChainSmem s = carve_smem<BT, SP>(M, smem_raw);
   tc::Region tr{};
   if constexpr (TC) {
-    tr = tc::region_of(M, s);
+    tr = tc::region_of<SP>(M, s);
     tc::setup<NT>(M, tr);
   }
   s.scr = R.scratch ? R.scratch + (long long)blockIdx.x * R.scratch_stride : nullptr;

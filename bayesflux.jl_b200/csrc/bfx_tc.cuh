@@ -180,16 +180,17 @@ struct Region {
   uint32_t par[3];      // phase parity of bar[0..2]
 };
 
+template <class SP = TcDyn>
 BFX_DEV Region region_of(const ModelDev& M, const ChainSmem& s) {
   Region R;
   R.base = s.tc;
-  float* f = reinterpret_cast<float*>(s.tc + M.tc.misc_off);
+  float* f = reinterpret_cast<float*>(s.tc + SP::misc_off(M));
   R.yh = f;
   R.glast = f + 128;
   R.bar = reinterpret_cast<uint64_t*>(f + 200);
   R.tmem_slot = reinterpret_cast<uint32_t*>(f + 208);
   R.gpart = f + 256;
-  R.idesc = reinterpret_cast<const IssueDesc*>(s.tc + M.tc.misc_off + 2304);
+  R.idesc = reinterpret_cast<const IssueDesc*>(s.tc + SP::misc_off(M) + 2304);
   R.shadow = f + 520;
   R.tmem = 0;
   R.par[0] = R.par[1] = R.par[2] = 0;
