@@ -526,6 +526,11 @@ BFX_DEV ChainSmem carve_smem(const ModelDev& M, unsigned char* base) {
     // emits LDS / STS with 32-bit addresses for every tile access instead of generic LD / ST
     const unsigned mis = (unsigned)__cvta_generic_to_shared(f) & 127u;
     s.tc = reinterpret_cast<unsigned char*>(f) + ((128u - mis) & 127u);
+    // (opaque to the optimiser: with literal offsets everywhere else it would otherwise RECOMPUTE this alignment at
+    // every use of a tile pointer, 800 instructions per chain-step, instead of holding the one pointer)
+    unsigned tc_off = (unsigned)__cvta_generic_to_shared(s.tc);
+    asm volatile("" : "+r"(tc_off));
+    s.tc = static_cast<unsigned char*>(__cvta_shared_to_generic(tc_off));
   }
   return s;
 }
