@@ -279,18 +279,53 @@ BFX_DEV void step_sgld(Ctx<NT, BT, TC, SP>& X) {
   const float* inj = X.inj(0);
   X.sc.nsampled += 1;
   BFX_TICK(14);
-  for_each_quad_n<NT, SP::fixed>(SP::S(X.R.M), [&](int k) {
-    const unsigned m = X.s.mask[k >> 2];
-    if (!m) return;
-    const int J0 = X.s.qflat[k >> 2];
-    const float4 z = noise_quad(X.R.M, X.key, X.gstep, 0, inj, k);
-    const float4 t = ld4(th + k), gg = ld4(g + k);
-    float4 o;
-    BFX_MAP4(o, comp(t, c) + ha * comp(gg, c) + sa * comp(z, c));
-    if (m != 15u) o = mask4(o, m);
-    st4(th + k, o);
-    rec_store(rec, k, m, o, J0);
-  });
+  if (!inj && X.R.M.philox_rk_set && !rec.rdst) {
+    // the common case (Philox noise, no DiagCov window) with everything that does not depend on the quad hoisted: the
+    // counter words, the alignment of the sample row (19 720-byte rows: every other slot is only 8-byte aligned)
+    const unsigned c1 = (unsigned)X.gstep, c2 = X.key.chain, c3 = (unsigned)((X.gstep >> 32) & 0xFFFFFFu);
+    float* const dst = rec.dst;
+    const unsigned dmis = (unsigned)(reinterpret_cast<unsigned long long>(dst) & 15ull);
+    for_each_quad_n<NT, SP::fixed>(SP::S(X.R.M), [&](int k) {
+      const unsigned m = X.s.mask[k >> 2];
+      if (!m) return;
+      const uint4 r = philox4x32_10_rk(make_uint4((unsigned)(k >> 2), c1, c2, c3), X.R.M.philox_rk);
+      const float2 za = box_muller(r.x, r.y), zb = box_muller(r.z, r.w);
+      const float4 t = ld4(th + k), gg = ld4(g + k);
+      float4 o = make_float4(t.x + ha * gg.x + sa * za.x, t.y + ha * gg.y + sa * za.y, t.z + ha * gg.z + sa * zb.x,
+                             t.w + ha * gg.w + sa * zb.y);
+      if (m != 15u) o = mask4(o, m);
+      st4(th + k, o);
+      if (dst) {
+        const int J0 = X.s.qflat[k >> 2];
+        float* p = dst + J0;
+        const unsigned mis = (dmis + 4u * (unsigned)J0) & 15u;
+        if (m == 15u && mis == 0u) {
+          st4(p, o);
+        } else if (m == 15u && (mis & 7u) == 0u) {
+          *reinterpret_cast<float2*>(p) = make_float2(o.x, o.y);
+          *reinterpret_cast<float2*>(p + 2) = make_float2(o.z, o.w);
+        } else {
+          if (m & 1u) p[0] = o.x;
+          if (m & 2u) p[1] = o.y;
+          if (m & 4u) p[2] = o.z;
+          if (m & 8u) p[3] = o.w;
+        }
+      }
+    });
+  } else {
+    for_each_quad_n<NT, SP::fixed>(SP::S(X.R.M), [&](int k) {
+      const unsigned m = X.s.mask[k >> 2];
+      if (!m) return;
+      const int J0 = X.s.qflat[k >> 2];
+      const float4 z = noise_quad(X.R.M, X.key, X.gstep, 0, inj, k);
+      const float4 t = ld4(th + k), gg = ld4(g + k);
+      float4 o;
+      BFX_MAP4(o, comp(t, c) + ha * comp(gg, c) + sa * comp(z, c));
+      if (m != 15u) o = mask4(o, m);
+      st4(th + k, o);
+      rec_store(rec, k, m, o, J0);
+    });
+  }
   BFX_TICK(15);
   __syncthreads();
   X.sc.t += 1;
