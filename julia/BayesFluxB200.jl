@@ -379,6 +379,12 @@ function comm_init!(m::DeviceBNN, sampler, id::Vector{UInt8}, nranks::Integer, r
 end
 comm_destroy!(sampler) = haskey(HANDLES, sampler) &&
     check(ccall((:bfx_sampler_comm_destroy, libbfx), Int32, (Ptr{Cvoid},), HANDLES[sampler].handle))
+# ranks whose exchange buffers this sampler reads over NVLink peer memory (0: the NCCL all-reduce is in use)
+function peer_ranks(sampler)
+    n = Ref{Int32}(0)
+    check(ccall((:bfx_sampler_peer_ranks, libbfx), Int32, (Ptr{Cvoid}, Ref{Int32}), HANDLES[sampler].handle, n))
+    return Int(n[])
+end
 
 # R̂ / ESS / pooled moments of the samples `mcmc` returned (P × n or P × n × C, Float32), computed on the device.
 # The reference hands `samples'` to MCMCChains for this (README.md:191-193).
