@@ -142,7 +142,12 @@ typedef struct bfx_sampler_desc {
 } bfx_sampler_desc;
 
 /* state fields for bfx_sampler_get_state / set_state (checkpoint / resume,
- * mirrors the mutable fields of the reference structs) */
+ * mirrors the mutable fields of the reference structs).
+ * Scope: these fields restore a chain exactly on a LIVE handle (continue_sampling) and, across processes, for the
+ * samplers whose whole state they are (SGLD; SGNHT / SGNHTS with a fixed mass).  The adapters' internal state
+ * (dual-averaging sums, RMSProp's V, the DiagCov window, GGMC's position in its window) and the engine's own step
+ * counter (batch schedule, Philox counters) are not exported: a GGMC / HMC / adapting chain restored in a new process
+ * restarts its adaptation and its batch / noise streams.  Setting BFX_STATE_THETA drops cached log posteriors. */
 enum {
   BFX_STATE_THETA = 0,    /* float  P x C */
   BFX_STATE_MOMENTUM = 1, /* float  P x C   (p / momentum) */
