@@ -15,5 +15,6 @@ from .api import (BNN, Chain, Dense, LSTM, RNN, NetConstructor, destruct, Gamma,
                   advance, launch_count, comm_unique_id, comm_init, comm_destroy, graph_replays, peer_ranks, Descent, Momentum, RMSProp, ADAM, FluxModeFinder, find_mode, predict,
                   sample_posterior_predict, get_posterior_networks, chain_diagnostics,
                   identity, relu, tanh, sigmoid)
-from .sharded import (shard_chains, shard_data, global_num_batches, model_regime, ShardedChain,  # noqa: F401,E402
+from .sharded import (shard_chains, shard_data, global_num_batches, model_regime, ShardedChain, peer_slice,
+                      peer_exchange_reference,  # noqa: F401,E402
                       mcmc_sharded)

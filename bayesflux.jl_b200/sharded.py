@@ -42,6 +42,36 @@ def global_num_batches(n_global: int, batch_global: int, partial: bool = True) -
     return -(-n_global // batch_global) if partial else max(1, n_global // batch_global)
 
 
+def peer_slice(P: int, rank: int, world: int) -> slice:
+    """The parameters rank ``rank`` finishes in the SCATTER protocol of the peer-memory exchange
+    (csrc/bfx_stream.cu: k_finish_scatter): the quads (groups of four consecutive floats) are split into
+    ``world`` contiguous runs of ``ceil(nq / world)`` quads."""
+    nq = (P + 3) // 4
+    per = -(-nq // world)
+    q0 = min(per * rank, nq)
+    q1 = min(q0 + per, nq)
+    return slice(min(4 * q0, P), min(4 * q1, P))
+
+
+def peer_exchange_reference(buffers, rank: int, protocol: str = "scatter"):
+    """Host restatement of what rank ``rank`` ends up with after the peer-memory exchange of the ranks' buffers
+    ``[g ; sums]`` (float32 arrays of equal length): every element is the sum of the ranks' contributions taken IN RANK
+    ORDER in float32 -- by this rank for every element (``pull``) or by the slice's owner (``scatter``).  Both orders
+    are the same, so every rank holds bit-identical sums whatever the protocol; used by the CPU tests."""
+    world = len(buffers)
+    P = len(buffers[0])
+    out = np.empty(P, np.float32)
+    owners = [rank] * world if protocol == "pull" else list(range(world))
+    for r in (range(world) if protocol == "scatter" else [rank]):
+        sl = peer_slice(P, r, world) if protocol == "scatter" else slice(0, P)
+        acc = buffers[0][sl].astype(np.float32).copy()
+        for j in range(1, world):
+            acc = (acc + buffers[j][sl].astype(np.float32)).astype(np.float32)
+        out[sl] = acc
+    del owners
+    return out
+
+
 def model_regime(bnn: A.BNN) -> str:
     r = C.c_int32()
     L.check(L.lib.bfx_model_regime(bnn._h, C.byref(r)))

@@ -144,3 +144,61 @@ def test_data_sharding_and_global_num_batches():
     assert bf.global_num_batches(2 ** 23, 65536) == 128      # configs[2]
     assert bf.global_num_batches(500, 50) == 10              # configs[0]
     assert bf.global_num_batches(105, 10, partial=False) == 10
+
+
+# ---- peer-memory exchange of the minibatch-sharded chain (csrc/bfx_stream.cu: k_finish_peer / k_finish_scatter) ----
+@pytest.mark.parametrize("P,world", [(559106, 2), (559106, 8), (17, 4), (3, 8), (4096, 3), (1, 2)])
+def test_peer_slices_partition_the_parameters(P, world):
+    bf = _load_sharded()
+    cover = np.zeros(P, int)
+    prev_stop = 0
+    for r in range(world):
+        sl = bf.peer_slice(P, r, world)
+        assert sl.start == prev_stop or sl.start == sl.stop  # contiguous, in rank order (late ranks may own nothing)
+        assert sl.start == sl.stop or sl.start % 4 == 0        # quad aligned: 16-byte loads / stores on the device
+        cover[sl] += 1
+        prev_stop = max(prev_stop, sl.stop)
+    assert (cover == 1).all()
+
+
+def _peer_worker(rank, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        import bayesflux_b200 as bf
+        P = 1003
+        mine = np.random.default_rng(100 + rank).standard_normal(P + 3).astype(np.float32)
+        # every rank can read every rank's buffer (peer memory): emulated by an all-gather of the buffers
+        got = [torch.empty(P + 3) for _ in range(WORLD)]
+        dist.all_gather(got, torch.from_numpy(mine))
+        bufs = [g.numpy() for g in got]
+        pull = bf.peer_exchange_reference(bufs, rank, "pull")
+        scat = bf.peer_exchange_reference(bufs, rank, "scatter")
+        # against the collective it replaces (sum order of gloo's all-reduce is not the rank order: tolerance)
+        red = torch.from_numpy(mine.copy())
+        dist.all_reduce(red)
+        err = float(np.max(np.abs(pull - red.numpy())))
+        # bit-identical on every rank and between the protocols
+        allp = [torch.empty(P + 3) for _ in range(WORLD)]
+        dist.all_gather(allp, torch.from_numpy(scat))
+        same = all(torch.equal(allp[0], t) for t in allp) and np.array_equal(pull, scat)
+        q.put((rank, err, same))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_sums_are_rank_ordered_and_identical_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(WORLD)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, same in res:
+        assert err < 1e-5, (rank, err)
+        assert same
