@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -1
-for i in 1 2; do python bench.py --steps 8 --warmup 3 --no-cpu --no-secondary 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('cfg2', d['value'], d['e2e']['value'])"; done
+mkdir -p gpurun_out
+python tools/lstm_value_probe.py 148 > gpurun_out/r02_lstm_value_probe.log 2>&1; tail -1 gpurun_out/r02_lstm_value_probe.log
+ncu --set full --clock-control none -k regex:k_eval -s 1 -c 1 -f -o gpurun_out/r02_lstm_value python tools/lstm_value_probe.py 148 > gpurun_out/r02_lstm_value_ncu.log 2>&1; echo "ncu value exit $?"
+ncu --set full --clock-control none -k regex:k_mcmc -s 1 -c 1 -f -o gpurun_out/r02_lstm_grad python tools/lstm_probe.py 148 4 > gpurun_out/r02_lstm_grad_ncu.log 2>&1; echo "ncu grad exit $?"
