@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LIBBFX") or os.path.join(_HERE, "libbfx.so")
 
 # names mirror include/bfx.h
-OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NAN_G, ERR_NAN_THETA, ERR_NO_DATA, ERR_STATE = range(8)
+OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NAN_G, ERR_NAN_THETA, ERR_NO_DATA, ERR_STATE, ERR_PEER = range(9)
 DENSE, RNN, LSTM = 0, 1, 2
 IDENTITY, RELU, TANH, SIGMOID = 0, 1, 2, 3
 LIKE_NORMAL, LIKE_TDIST = 0, 1

@@ -1365,8 +1365,11 @@ static int32_t status_after(bfx_sampler* s) {
   }
   s->nsampled = ns >= 0 ? ns : sc[0].nsampled;
   if (bad >= 0) {
-    char buf[96];
-    std::snprintf(buf, sizeof buf, "NaN in %s (chain %d)", sc[bad].status == BFX_ERR_NAN_G ? "g" : "θ", bad);
+    char buf[128];
+    if (sc[bad].status == BFX_ERR_PEER)
+      std::snprintf(buf, sizeof buf, "peer exchange timed out: a rank of the minibatch-sharded chain did not arrive");
+    else
+      std::snprintf(buf, sizeof buf, "NaN in %s (chain %d)", sc[bad].status == BFX_ERR_NAN_G ? "g" : "θ", bad);
     return fail(sc[bad].status, buf);
   }
   return BFX_OK;

@@ -538,8 +538,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// thread 0 of the block waits until word[j] >= e for every peer j; false after ~2 s (a peer died): the caller flags
-// the chain instead of hanging the GPU
+// thread 0 of the block waits until word[j] >= e for every peer j; false after about a minute (a peer died; ranks that
+// merely enter their first update seconds apart must not trip it): the caller flags the chain instead of hanging
 __device__ __forceinline__ bool peer_wait(const unsigned long long* words, int n, int self, unsigned long long e) {
   __shared__ int s_ok;
   if (threadIdx.x == 0) {
@@ -548,7 +548,7 @@ __device__ __forceinline__ bool peer_wait(const unsigned long long* words, int n
     for (int j = 0; j < n && ok; ++j) {
       if (j == self) continue;
       while (ld_acquire_sys(words + j) < e) {
-        if (clock64() - t0 > 4000000000LL) {
+        if (clock64() - t0 > 120000000000LL) {
           ok = 0;
           break;
         }

@@ -44,7 +44,8 @@ enum {
   BFX_ERR_NAN_G = 4,     /* error("NaN in g")  src/inference/mcmc/sgnht.jl:70-72   */
   BFX_ERR_NAN_THETA = 5, /* error("NaN in θ")  src/inference/mcmc/sgnht.jl:81-83, ggmc.jl:160-162 */
   BFX_ERR_NO_DATA = 6,
-  BFX_ERR_STATE = 7
+  BFX_ERR_STATE = 7,
+  BFX_ERR_PEER = 8 /* minibatch-sharded chain: a peer did not publish its part of an update within about a minute */
 };
 
 /* ---- model description ------------------------------------------------- */
@@ -156,7 +157,7 @@ enum {
   BFX_STATE_STEPSIZE = 4, /* float  C       l */
   BFX_STATE_T = 5,        /* int64  C       step counter t (1-based like the reference) */
   BFX_STATE_NSAMPLED = 6, /* int64  C */
-  BFX_STATE_STATUS = 7,   /* int32  C       BFX_OK | BFX_ERR_NAN_G | BFX_ERR_NAN_THETA */
+  BFX_STATE_STATUS = 7,   /* int32  C       BFX_OK | BFX_ERR_NAN_G | BFX_ERR_NAN_THETA | BFX_ERR_PEER */
   BFX_STATE_CONVERGED = 8 /* int32  C       BFX_MODE: 1 once the convergence window fell below ϵ */
 };
 
